@@ -1,0 +1,187 @@
+/*
+ * pop_arrowhead.h -- C ABI of the B200-native arrowhead hot path.
+ *
+ * Drop-in boundary for PiecewiseOrthogonalPolynomials.jl's BBBArrowheadMatrix
+ * linear algebra (reference: /root/reference/src/arrowhead.jl).  Every entry
+ * point cites the reference interface it replaces (file:line relative to the
+ * reference root).  Plain pointers and sizes only; no C++/torch types cross it.
+ * The Julia-side `ccall` bindings are shown in INTEGRATION.md and julia/.
+ *
+ * Conventions
+ *   - Float64 everywhere.  Vectors / matrices use the reference's own ordering
+ *     (src/arrowhead.jl:57-62): nh hats first, then bubble block j (j=0..q-1),
+ *     entry k (element, k=0..m-1) at index nh + j*m + k; n = nh + m*q.
+ *     Matrices are column-major with leading dimension ld >= rows.
+ *   - Return value: 0 ok; >0 = 1-based global index of the first non-positive
+ *     pivot (the reference throws PosDefException from the block factor);
+ *     <0 = POP_ERR_* with a message available from pop_last_error().
+ *     Nothing throws across the boundary.
+ *   - A pop_ctx owns one device + one stream; calls on it are serialised on that
+ *     stream.  Functions taking device pointers are asynchronous on the stream,
+ *     the *_host variants copy in, run, copy out and synchronise.
+ *   - The caller owns every host pointer; the library never retains them.
+ *
+ * Packed arrowhead (all 0-based)
+ *   Ad[nh], Au[nh-1], Al[nh-1]      hat block A: diagonal, super-, sub-diagonal
+ *   B[nB][3][m]   B[b][t][k] = entry (hat k+t-1 , bubble (b,k)), t=0,1,2
+ *   C[nC][3][m]   C[b][t][k] = entry (bubble (b,k), hat k+t-1)
+ *                 (hats outside [0,nh) do not exist: those slots must be 0;
+ *                  ContinuousPolynomial{1}: nh=m+1, slots t=1,2 used ("lower B",
+ *                  src/arrowhead.jl:297); DirichletPolynomial: nh=m-1, slots
+ *                  t=0,1 ("upper B", src/arrowhead.jl:346))
+ *   D[lD+uD+1][q][mD]  D[lD+d][j][k] = D_k[j, j+d], d=-lD..uD (0 outside);
+ *                 mD = m, or 1 when desc.uniform (all elements share one block,
+ *                 the `Fill(D, m)` of src/continuouspolynomial.jl:286).
+ */
+#ifndef POP_ARROWHEAD_H
+#define POP_ARROWHEAD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POP_ABI_VERSION 1
+
+enum {
+    POP_OK = 0,
+    POP_ERR_ARG = -1,    /* bad argument / null pointer                      */
+    POP_ERR_DIM = -2,    /* DimensionMismatch                                 */
+    POP_ERR_STRUCT = -3, /* structure assertion of the reference violated
+                            (src/arrowhead.jl:96-116,299,305,348,356)         */
+    POP_ERR_CUDA = -4,   /* CUDA runtime error                                */
+    POP_ERR_ALLOC = -5,  /* out of device / host memory                       */
+    POP_ERR_NOGPU = -6   /* no CUDA device: there is NO CPU fallback          */
+};
+
+enum { POP_BASIS_C1 = 0, POP_BASIS_DIRICHLET = 1 }; /* ContinuousPolynomial{1} / DirichletPolynomial */
+enum { POP_LEFT = 0, POP_RIGHT = 1 };               /* A*X, A\X  vs  X*A, X/A */
+enum { POP_GENERAL = 0, POP_SYM_UPPER = 1 };        /* Symmetric(P) reads upper data, src/arrowhead.jl:154-167 */
+enum { POP_UPPER = 0, POP_LOWER = 1 };
+enum { POP_SOLVE_AUTO = 0, POP_SOLVE_STAGED = 1, POP_SOLVE_FUSED = 2 }; /* kernel choice for pop_solve */
+
+typedef struct pop_ctx pop_ctx;
+typedef struct pop_arrowhead pop_arrowhead; /* device-resident packed arrowhead or factor */
+
+typedef struct pop_desc {
+    int32_t m;       /* mesh elements = length(A.D)                           */
+    int32_t nh;      /* hats = size(A.A,1)                                    */
+    int32_t q;       /* bubbles per element = size(A.D[1],1) = N-1            */
+    int32_t nB;      /* length(A.B)                                           */
+    int32_t nC;      /* length(A.C)                                           */
+    int32_t lD, uD;  /* bandwidths(A.D[1])                                    */
+    int32_t uniform; /* 1: D given once ([bands][q]) and shared by all k      */
+} pop_desc;
+
+/* ---- context -------------------------------------------------------------------- */
+int pop_abi_version(void);
+const char *pop_last_error(void);
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL to
+ * let the context create its own non-blocking stream. */
+int pop_create(pop_ctx **ctx, int device, void *stream);
+int pop_destroy(pop_ctx *ctx);
+int pop_set_stream(pop_ctx *ctx, void *stream);
+int pop_sync(pop_ctx *ctx);
+/* number of kernels this context has launched so far (bench `gpu_launches`) */
+int64_t pop_launch_count(const pop_ctx *ctx);
+
+/* ---- container (src/arrowhead.jl:31-41,89-120) --------------------------------- */
+/* BBBArrowheadMatrix(A,B,C,D): validates what the constructor asserts.  Any of
+ * Au/Al/B/C may be NULL (= zero / empty). */
+int pop_arrowhead_upload(pop_ctx *ctx, const pop_desc *desc, const double *Ad, const double *Au,
+                         const double *Al, const double *B, const double *C, const double *D,
+                         pop_arrowhead **out);
+int pop_arrowhead_desc(const pop_arrowhead *A, pop_desc *desc);
+/* copies the fields back in the layout `desc` of pop_arrowhead_desc describes
+ * (D expanded to [bands][q][m] unless expand_uniform == 0).  NULL = skip field. */
+int pop_arrowhead_download(pop_ctx *ctx, const pop_arrowhead *A, int expand_uniform, double *Ad,
+                           double *Au, double *Al, double *B, double *C, double *D);
+int pop_arrowhead_free(pop_ctx *ctx, pop_arrowhead *A);
+/* copy(A), src/arrowhead.jl:64 ; reversecholcopy, :266-272 */
+int pop_arrowhead_copy(pop_ctx *ctx, const pop_arrowhead *A, pop_arrowhead **out);
+
+/* ---- assembly on a uniform mesh (upper data, as the reference stores it) --------
+ * mass:  grammatrix(C)[KR,KR]   src/continuouspolynomial.jl:274-290, src/dirichlet.jl:180-196
+ * lap :  weaklaplacian(C)[KR,KR] src/continuouspolynomial.jl:348-357, src/dirichlet.jl:169-178
+ * KR = Block.(oneto(N)) (src/arrowhead.jl:141-149); h = step(points).  Either output may be NULL. */
+int pop_assemble(pop_ctx *ctx, int basis, int m, int N, double h, pop_arrowhead **mass,
+                 pop_arrowhead **lap);
+
+/* ---- algebra: alpha*X + beta*Y with ragged B/C and D bands (src/arrowhead.jl:392-417) */
+int pop_axpby(pop_ctx *ctx, double alpha, const pop_arrowhead *X, double beta,
+              const pop_arrowhead *Y, pop_arrowhead **out);
+
+/* ---- reverse Cholesky S = U U^T (src/arrowhead.jl:276-389) ----------------------
+ * reversecholesky(Symmetric(S)): reads the upper data of S, returns a new handle
+ * holding U (same sparsity as triu(S)) plus reciprocal pivots. */
+int pop_revchol(pop_ctx *ctx, const pop_arrowhead *S, pop_arrowhead **U);
+/* reversecholesky!(Symmetric(S)): in place */
+int pop_revchol_inplace(pop_ctx *ctx, pop_arrowhead *S);
+/* factors of alpha[i]*K + sigma[i]*M for i < nshift in ONE batched launch sequence
+ * (the per-shift `reversecholesky(Symmetric(C - B/p[j]))` of examples/adi_poisson.jl:54-55).
+ * U[i] receives nshift handles; info[i] (may be NULL) the per-shift status. */
+int pop_revchol_shifted_batch(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M,
+                              const double *alpha, const double *sigma, int nshift,
+                              pop_arrowhead **U, int32_t *info);
+
+/* ---- products (src/arrowhead.jl:191-258) -----------------------------------------
+ * side LEFT :  Y <- alpha*op(A)*X + beta*Y, X,Y are n x nrhs
+ * side RIGHT:  Y <- alpha*X*op(A) + beta*Y, X,Y are nrhs x n
+ * op(A) = A or A^T (trans); sym = POP_SYM_UPPER treats A as Symmetric(A). */
+int pop_mul(pop_ctx *ctx, const pop_arrowhead *A, int side, int sym, int trans, double alpha,
+            const double *dX, int64_t ldx, double beta, double *dY, int64_t ldy, int64_t nrhs);
+int pop_mul_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int sym, int trans, double alpha,
+                 const double *X, int64_t ldx, double beta, double *Y, int64_t ldy, int64_t nrhs);
+
+/* ---- triangular solves (src/arrowhead.jl:425-486) -------------------------------
+ * X <- op(T)^{-1} X (LEFT) or X <- X op(T)^{-1} (RIGHT) with
+ * T = UpperTriangular(A) / LowerTriangular(A) (uplo), Unit* when unit != 0. */
+int pop_trsm(pop_ctx *ctx, const pop_arrowhead *A, int side, int uplo, int trans, int unit,
+             double *dX, int64_t ldx, int64_t nrhs);
+int pop_trsm_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int uplo, int trans, int unit,
+                  double *X, int64_t ldx, int64_t nrhs);
+
+/* ---- ReverseCholesky solve:  F \ X  and  X / F  (call sites
+ * test/test_arrowhead.jl:130, examples/adi_poisson.jl:54-55): X <- U^{-T} U^{-1} X.
+ * `algo`: POP_SOLVE_AUTO picks the single-pass fused kernel when the column fits
+ * on chip, else the staged kernels. */
+int pop_solve(pop_ctx *ctx, const pop_arrowhead *U, int side, double *dX, int64_t ldx,
+              int64_t nrhs, int algo);
+int pop_solve_host(pop_ctx *ctx, const pop_arrowhead *U, int side, double *X, int64_t ldx,
+                   int64_t nrhs, int algo);
+/* nshift systems, shift i acting on the panel dX + i*stride_shift (BASELINE config 3) */
+int pop_solve_shift_batch(pop_ctx *ctx, pop_arrowhead *const *U, int nshift, double *dX,
+                          int64_t ldx, int64_t stride_shift, int64_t nrhs, int algo);
+
+/* ---- fused ADI half step (examples/adi_poisson.jl:54-55) ------------------------
+ * dR <- T * (U^{-T} U^{-1} dR) + gamma * dF, column-wise, T = Symmetric(Tm) (upper
+ * data).  T may be NULL (plain solve).  One read of R, one read of F, one write. */
+int pop_solve_mul_axpy(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *Tm, double gamma,
+                       const double *dF, int64_t ldf, double *dR, int64_t ldr, int64_t nrhs);
+
+/* out-of-place transpose dst (cols x rows, ldd) <- src^T, src rows x cols (lds) */
+int pop_transpose(pop_ctx *ctx, const double *dsrc, int64_t lds, int64_t rows, int64_t cols,
+                  double *ddst, int64_t ldd);
+
+/* ---- drivers ----------------------------------------------------------------------
+ * ADI shifts and iteration count: examples/adi_poisson.jl:11-40,47-49 (host arithmetic).
+ * p,q must hold J doubles. */
+int pop_adi_num_iterations(double a, double b, double c, double d, double tol);
+int pop_adi_shifts(int J, double a, double b, double c, double d, double *p, double *q);
+/* ADI(A=M, B=-M, C=K, F, a, b, c, d, tol) of examples/adi_poisson.jl:42-59 on one GPU:
+ * solves K X M + M X K = F for X (n x n, device, column-major).  J <= 0: derive J from tol. */
+int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, const double *dF,
+                    int64_t ldf, double *dX, int64_t ldx, double a, double b, double c, double d,
+                    double tol, int J);
+/* backward Euler with one reused factorisation, examples/heat.jl:58-63:
+ * nsteps times  U <- S^{-1} (M U)  with S = M + dt*K; dims = 1: columns of dU (n x nrhs);
+ * dims = 2: n x n field, U <- S^{-1} (M U M) S^{-1} (factored 2D extension). */
+int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt,
+                   int nsteps, int dims, double *dU, int64_t ldu, int64_t nrhs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POP_ARROWHEAD_H */

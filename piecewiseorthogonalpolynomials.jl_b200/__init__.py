@@ -1,0 +1,12 @@
+"""B200-native arrowhead hot path of PiecewiseOrthogonalPolynomials.jl behind the reference's API.
+
+All arithmetic runs in libpop_arrowhead.so (hand-written CUDA for sm_100a, C ABI in
+include/pop_arrowhead.h).  There is no CPU fallback."""
+from ._lib import (Context, DimensionMismatch, PopError, PosDefException, StructureError, build, default_context,
+                   SOLVE_AUTO, SOLVE_FUSED, SOLVE_STAGED, LIB_PATH, EXPORTED)
+from .arrowhead import (BBBArrowheadMatrix, LowerTriangular, ReverseCholesky, Symmetric, UnitLowerTriangular,
+                        UnitUpperTriangular, UpperTriangular, ldiv, mul, rdiv, reversecholesky, reversecholesky_inplace,
+                        reversecholesky_shifted)
+from .bases import Block, BlockRange, ContinuousPolynomial, DirichletPolynomial, LazyArrowhead, grammatrix, weaklaplacian
+from .drivers import (DistTranspose, adi_num_iterations, adi_poisson, adi_poisson_distributed, adi_shifts, heat_steps,
+                      shard_bounds, spectrum_bounds)

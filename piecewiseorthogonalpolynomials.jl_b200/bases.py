@@ -1,0 +1,147 @@
+"""Bases and the lazy (infinite) mass / weak-Laplacian arrowheads they assemble.
+
+Mirrors, for the hot path only, /root/reference/src/continuouspolynomial.jl:274-290,348-357 and
+src/dirichlet.jl:169-196 (closed forms on a uniform mesh) plus the truncation `M[KR,KR]` with
+`KR = Block.(oneto(N))` (src/arrowhead.jl:141-149).  The entries are generated on the device by
+pop_assemble; nothing is computed on the host.  Non-uniform meshes (generic `L'*G*L`,
+src/continuouspolynomial.jl:293-297) are a "next" row and raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .arrowhead import BBBArrowheadMatrix, Symmetric
+
+
+@dataclass(frozen=True)
+class BlockRange:
+    """Block.(oneto(N)) -- the only block range the arrowhead `sublayout` accepts
+    (src/arrowhead.jl:141-142)."""
+    N: int
+
+    def __len__(self):
+        return self.N
+
+
+class Block:
+    @staticmethod
+    def oneto(N: int) -> BlockRange:
+        if N < 1:
+            raise ValueError("Block.oneto(N) needs N >= 1")
+        return BlockRange(int(N))
+
+
+def _uniform_step(points) -> float:
+    p = np.asarray(points, dtype=np.float64)
+    if p.ndim != 1 or p.size < 2:
+        raise ValueError("points must be a 1-D grid with at least two nodes")
+    h = np.diff(p)
+    if np.any(h <= 0):
+        raise ValueError("points must be increasing")
+    if np.max(np.abs(h - h[0])) > 8 * np.finfo(float).eps * max(1.0, np.abs(p).max()):
+        raise NotImplementedError("non-uniform meshes are not on the accelerated path yet (SURVEY.md 8f-3)")
+    return float((p[-1] - p[0]) / (p.size - 1))
+
+
+class _Basis:
+    basis_id = -1
+
+    def __init__(self, points):
+        self.points = np.asarray(points, dtype=np.float64)
+        self.h = _uniform_step(self.points)
+        self.m = self.points.size - 1
+
+    def __eq__(self, o):
+        return type(self) is type(o) and np.array_equal(self.points, o.points)
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.points.tobytes()))
+
+
+class ContinuousPolynomial(_Basis):
+    """ContinuousPolynomial{1}(points): hats + bubbles, Neumann-type (src/continuouspolynomial.jl:7-15)."""
+    basis_id = L.BASIS_C1
+
+    def __init__(self, order, points=None):
+        if points is None:
+            order, points = 1, order
+        if order != 1:
+            raise NotImplementedError("only ContinuousPolynomial{1} is on the arrowhead path")
+        super().__init__(points)
+
+    @property
+    def nh(self):
+        return self.m + 1
+
+
+class DirichletPolynomial(_Basis):
+    """DirichletPolynomial(points): end hats removed (src/dirichlet.jl)."""
+    basis_id = L.BASIS_DIRICHLET
+
+    @property
+    def nh(self):
+        return self.m - 1
+
+
+class LazyArrowhead:
+    """Linear combination of the infinite mass and weak-Laplacian matrices of one basis;
+    `A[KR, KR]` materialises the truncation on the device as Symmetric(BBBArrowheadMatrix)."""
+
+    def __init__(self, basis: _Basis, cm: float, cl: float, ctx=None):
+        self.basis, self.cm, self.cl, self.ctx = basis, float(cm), float(cl), ctx
+
+    def _comb(self, o, s):
+        if not isinstance(o, LazyArrowhead) or o.basis != self.basis:
+            raise TypeError("lazy arrowheads combine only within one basis")
+        return LazyArrowhead(self.basis, self.cm + s * o.cm, self.cl + s * o.cl, self.ctx or o.ctx)
+
+    def __add__(self, o):
+        return self._comb(o, 1.0)
+
+    def __sub__(self, o):
+        return self._comb(o, -1.0)
+
+    def __neg__(self):
+        return LazyArrowhead(self.basis, -self.cm, -self.cl, self.ctx)
+
+    def __mul__(self, c):
+        return LazyArrowhead(self.basis, self.cm * c, self.cl * c, self.ctx)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, c):
+        return LazyArrowhead(self.basis, self.cm / c, self.cl / c, self.ctx)
+
+    def __getitem__(self, idx) -> Symmetric:
+        KR, JR = idx
+        if not (isinstance(KR, BlockRange) and isinstance(JR, BlockRange)) or KR.N != JR.N:
+            raise TypeError("arrowhead truncation needs [Block.oneto(N), Block.oneto(N)]")
+        ctx = self.ctx or L.default_context()
+        hm, hl = C.c_void_p(), C.c_void_p()
+        L.check(L.lib().pop_assemble(ctx.handle, self.basis.basis_id, self.basis.m, KR.N, self.basis.h,
+                                     C.byref(hm) if self.cm != 0 else None, C.byref(hl) if self.cl != 0 else None), "assemble")
+        Mh = BBBArrowheadMatrix(ctx=ctx, _handle=hm) if self.cm != 0 else None
+        Lh = BBBArrowheadMatrix(ctx=ctx, _handle=hl) if self.cl != 0 else None
+        if Mh is not None and Lh is not None:
+            return Symmetric(Mh._axpby(self.cm, Lh, self.cl))
+        if Mh is not None:
+            return Symmetric(Mh if self.cm == 1.0 else Mh * self.cm)
+        if Lh is not None:
+            return Symmetric(Lh if self.cl == 1.0 else Lh * self.cl)
+        raise ValueError("zero operator")
+
+
+def grammatrix(basis: _Basis, ctx=None) -> LazyArrowhead:
+    """M = C'C (src/continuouspolynomial.jl:274-290, src/dirichlet.jl:180-196)."""
+    return LazyArrowhead(basis, 1.0, 0.0, ctx)
+
+
+def weaklaplacian(basis: _Basis, ctx=None) -> LazyArrowhead:
+    """Delta = weaklaplacian(C), negative semi-definite (src/continuouspolynomial.jl:348-357,
+    src/dirichlet.jl:169-178)."""
+    return LazyArrowhead(basis, 0.0, 1.0, ctx)

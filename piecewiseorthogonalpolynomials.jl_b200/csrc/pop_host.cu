@@ -1,0 +1,343 @@
+// Host-buffer variants (chunked, copy/compute overlapped) and the drivers of
+// examples/adi_poisson.jl and examples/heat.jl on top of the device kernels.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "pop_internal.h"
+
+// ------------------------------------------------------------------------------------
+// chunked host panels: H2D (copy stream 0) -> kernels (ctx stream) -> D2H (copy stream 1)
+// ------------------------------------------------------------------------------------
+struct PanelOp {
+    // run on a device panel: `vec` x `cnt` region, leading dimension ldd
+    virtual int run(pop_ctx *ctx, double *d, int64_t ldd, int64_t cnt) = 0;
+    virtual ~PanelOp() {}
+};
+
+static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, double *X, int64_t ldx, PanelOp &op) {
+    if (nrhs == 0 || n == 0) return POP_OK;
+    // LEFT: panel = n x nrhs, chunks of columns.  RIGHT: panel = nrhs x n, chunks of rows.
+    const int64_t target = (int64_t)48 << 20;  // bytes per chunk
+    int64_t per = std::max<int64_t>(1, target / (n * 8));
+    if (side == POP_RIGHT) per = std::max<int64_t>(per, 32);
+    per = std::min(per, nrhs);
+    const int nbuf = 3;
+    const int64_t ldd = side == POP_LEFT ? ((n + 1) & ~(int64_t)1) : ((per + 1) & ~(int64_t)1);
+    const size_t buf_doubles = side == POP_LEFT ? (size_t)ldd * per : (size_t)ldd * n;
+    double *dbuf = nullptr;
+    cudaError_t e = cudaMalloc(&dbuf, buf_doubles * nbuf * sizeof(double));
+    if (e != cudaSuccess) {
+        pop_set_error("host panel: device buffer of %zu bytes: %s", buf_doubles * nbuf * sizeof(double), cudaGetErrorString(e));
+        return POP_ERR_ALLOC;
+    }
+    cudaEvent_t *h2d = ctx->ev, *cmp = ctx->ev + 3, *d2h = ctx->ev + 6;
+    int rc = POP_OK;
+    int64_t done = 0;
+    int it = 0;
+    // make the copy streams wait for work already queued on the compute stream
+    cudaEventRecord(ctx->ev[9], ctx->stream);
+    cudaStreamWaitEvent(ctx->s_copy[0], ctx->ev[9], 0);
+    while (done < nrhs && rc == POP_OK) {
+        const int64_t cnt = std::min(per, nrhs - done);
+        const int b = it % nbuf;
+        double *d = dbuf + (size_t)b * buf_doubles;
+        if (it >= nbuf) cudaStreamWaitEvent(ctx->s_copy[0], d2h[b], 0);
+        if (side == POP_LEFT)
+            e = cudaMemcpy2DAsync(d, ldd * 8, X + done * ldx, ldx * 8, n * 8, cnt, cudaMemcpyHostToDevice, ctx->s_copy[0]);
+        else
+            e = cudaMemcpy2DAsync(d, ldd * 8, X + done, ldx * 8, cnt * 8, n, cudaMemcpyHostToDevice, ctx->s_copy[0]);
+        if (e != cudaSuccess) { pop_set_error("host panel H2D: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
+        cudaEventRecord(h2d[b], ctx->s_copy[0]);
+        cudaStreamWaitEvent(ctx->stream, h2d[b], 0);
+        rc = op.run(ctx, d, ldd, cnt);
+        if (rc) break;
+        cudaEventRecord(cmp[b], ctx->stream);
+        cudaStreamWaitEvent(ctx->s_copy[1], cmp[b], 0);
+        if (side == POP_LEFT)
+            e = cudaMemcpy2DAsync(X + done * ldx, ldx * 8, d, ldd * 8, n * 8, cnt, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+        else
+            e = cudaMemcpy2DAsync(X + done, ldx * 8, d, ldd * 8, cnt * 8, n, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+        if (e != cudaSuccess) { pop_set_error("host panel D2H: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
+        cudaEventRecord(d2h[b], ctx->s_copy[1]);
+        done += cnt;
+        ++it;
+    }
+    cudaStreamSynchronize(ctx->s_copy[0]);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaStreamSynchronize(ctx->s_copy[1]);
+    cudaFree(dbuf);
+    if (rc == POP_OK && e != cudaSuccess) { pop_set_error("host panel: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
+    return rc;
+}
+
+struct SolveOp : PanelOp {
+    const pop_arrowhead *U; int side, algo;
+    int run(pop_ctx *ctx, double *d, int64_t ldd, int64_t cnt) override { return pop_solve(ctx, U, side, d, ldd, cnt, algo); }
+};
+struct TrsmOp : PanelOp {
+    const pop_arrowhead *A; int side, uplo, trans, unit;
+    int run(pop_ctx *ctx, double *d, int64_t ldd, int64_t cnt) override { return pop_trsm(ctx, A, side, uplo, trans, unit, d, ldd, cnt); }
+};
+
+static int check_host_panel(const pop_arrowhead *A, int side, const double *X, int64_t ldx, int64_t nrhs, const char *who) {
+    POP_REQUIRE(side == POP_LEFT || side == POP_RIGHT, POP_ERR_ARG, "%s: bad side", who);
+    POP_REQUIRE(nrhs >= 0, POP_ERR_DIM, "%s: negative nrhs", who);
+    POP_REQUIRE(X || nrhs == 0, POP_ERR_ARG, "%s: null matrix", who);
+    const int64_t rows = side == POP_LEFT ? A->n() : nrhs;
+    POP_REQUIRE(ldx >= std::max<int64_t>(rows, 1), POP_ERR_DIM, "%s: DimensionMismatch: leading dimension %lld < %lld", who, (long long)ldx, (long long)rows);
+    return POP_OK;
+}
+
+extern "C" int pop_solve_host(pop_ctx *ctx, const pop_arrowhead *U, int side, double *X, int64_t ldx, int64_t nrhs, int algo) {
+    POP_REQUIRE(ctx && U, POP_ERR_ARG, "pop_solve_host: null argument");
+    POP_REQUIRE(U->is_factor, POP_ERR_ARG, "pop_solve_host: handle is not a reverse-Cholesky factor");
+    int rc = check_host_panel(U, side, X, ldx, nrhs, "pop_solve_host");
+    if (rc) return rc;
+    SolveOp op; op.U = U; op.side = side; op.algo = algo;
+    return run_host_panels(ctx, side, U->n(), nrhs, X, ldx, op);
+}
+
+extern "C" int pop_trsm_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int uplo, int trans, int unit, double *X, int64_t ldx, int64_t nrhs) {
+    POP_REQUIRE(ctx && A, POP_ERR_ARG, "pop_trsm_host: null argument");
+    int rc = check_host_panel(A, side, X, ldx, nrhs, "pop_trsm_host");
+    if (rc) return rc;
+    TrsmOp op; op.A = A; op.side = side; op.uplo = uplo; op.trans = trans; op.unit = unit;
+    return run_host_panels(ctx, side, A->n(), nrhs, X, ldx, op);
+}
+
+extern "C" int pop_mul_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int sym, int trans, double alpha, const double *X, int64_t ldx,
+                            double beta, double *Y, int64_t ldy, int64_t nrhs) {
+    POP_REQUIRE(ctx && A, POP_ERR_ARG, "pop_mul_host: null argument");
+    int rc = check_host_panel(A, side, X, ldx, nrhs, "pop_mul_host");
+    if (rc) return rc;
+    rc = check_host_panel(A, side, Y, ldy, nrhs, "pop_mul_host");
+    if (rc || nrhs == 0) return rc;
+    const int64_t n = A->n();
+    const int64_t rows = side == POP_LEFT ? n : nrhs, cols = side == POP_LEFT ? nrhs : n;
+    const int64_t ldd = (rows + 1) & ~(int64_t)1;
+    double *dX = nullptr;
+    cudaError_t e = cudaMalloc(&dX, (size_t)ldd * cols * 2 * sizeof(double));
+    if (e != cudaSuccess) { pop_set_error("pop_mul_host: device buffer: %s", cudaGetErrorString(e)); return POP_ERR_ALLOC; }
+    double *dY = dX + (size_t)ldd * cols;
+    e = cudaMemcpy2DAsync(dX, ldd * 8, X, ldx * 8, rows * 8, cols, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && beta != 0.0) e = cudaMemcpy2DAsync(dY, ldd * 8, Y, ldy * 8, rows * 8, cols, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rc = pop_mul(ctx, A, side, sym, trans, alpha, dX, ldd, beta, dY, ldd, nrhs);
+        if (rc == POP_OK) e = cudaMemcpy2DAsync(Y, ldy * 8, dY, ldd * 8, rows * 8, cols, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dX);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { pop_set_error("pop_mul_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return POP_ERR_CUDA; }
+    return POP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// ADI shifts (examples/adi_poisson.jl:11-40): host arithmetic
+// ------------------------------------------------------------------------------------
+static double mobius(double z, double a, double b, double c, double d, double al) {  // :11-18
+    const double t1 = a * (-al * b + b + al * c + c) - 2 * b * c;
+    const double t2 = a * (al * (b + c) - b + c) - 2 * al * b * c;
+    const double t3 = 2 * a - (al + 1) * b + (al - 1) * c;
+    const double t4 = -al * (-2 * a + b + c) - b + c;
+    return (t1 * z + t2) / (t3 * z + t4);
+}
+
+// Complete elliptic integral K(m) and Jacobi dn(u|m), m = 1 - m1, by the arithmetic-geometric
+// mean / descending Landen recurrence (Abramowitz & Stegun 16.4, 17.6); the reference calls
+// Elliptic.K and Elliptic.Jacobi.dn (:30-31).
+static void agm_setup(double m1, double *a, double *cc, int *N) {
+    double an = 1.0, bn = std::sqrt(m1), cn = std::sqrt(1.0 - m1);
+    a[0] = an; cc[0] = cn;
+    int n = 0;
+    while (std::fabs(cn) > 1e-17 * an && n < 60) {
+        const double a1 = 0.5 * (an + bn);
+        cn = 0.5 * (an - bn);
+        bn = std::sqrt(an * bn);
+        an = a1;
+        ++n;
+        a[n] = an; cc[n] = cn;
+    }
+    *N = n;
+}
+static double ellip_K_m1(double m1) {
+    double a[64], c[64]; int N;
+    agm_setup(m1, a, c, &N);
+    return M_PI / (2.0 * a[N]);
+}
+static double jacobi_dn_m1(double u, double m1) {
+    double a[64], c[64]; int N;
+    agm_setup(m1, a, c, &N);
+    double phi = std::ldexp(a[N] * u, N), phi_prev = phi;
+    for (int n = N; n >= 1; --n) {
+        phi_prev = phi;
+        phi = 0.5 * (phi + std::asin(c[n] * std::sin(phi) / a[n]));
+    }
+    if (N == 0) return 1.0;  // m = 0
+    return std::cos(phi) / std::cos(phi_prev - phi);
+}
+
+extern "C" int pop_adi_num_iterations(double a, double b, double c, double d, double tol) {
+    const double gamma = (c - a) * (d - b) / ((c - b) * (d - a));   // :47
+    return (int)std::ceil(std::log(16 * gamma) * std::log(4 / tol) / (M_PI * M_PI));  // :48
+}
+
+extern "C" int pop_adi_shifts(int J, double a, double b, double c, double d, double *p, double *q) {
+    POP_REQUIRE(J >= 1 && p && q, POP_ERR_ARG, "pop_adi_shifts: bad argument");
+    const double gamma = (c - a) * (d - b) / ((c - b) * (d - a));   // :24
+    const double alpha = -1 + 2 * gamma + 2 * std::sqrt(gamma * gamma - gamma);   // :25
+    POP_REQUIRE(std::isfinite(alpha) && alpha >= 1, POP_ERR_ARG, "pop_adi_shifts: invalid spectral intervals (alpha=%g)", alpha);
+    const double m1 = 1.0 / (alpha * alpha);
+    for (int i = 0; i < J; ++i) {
+        double dn;
+        if (alpha < 1e7) {                                          // :29-31
+            const double K = ellip_K_m1(m1);
+            dn = jacobi_dn_m1((2.0 * i + 1.0) * K / (2.0 * J), m1);
+        } else {                                                    // :32-37
+            const double K = 2 * std::log(2.0) + std::log(alpha) + (-1 + 2 * std::log(2.0) + std::log(alpha)) / (alpha * alpha) / 4;
+            const double u = (i + 0.5) * K / J;
+            const double sech = 1.0 / std::cosh(u);
+            dn = sech + m1 / 4 * (std::sinh(u) * std::cosh(u) + u) * std::tanh(u) * sech;
+        }
+        p[i] = mobius(-alpha * dn, a, b, c, d, alpha);              // :39
+        q[i] = mobius(alpha * dn, a, b, c, d, alpha);
+    }
+    return POP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// ADI Poisson driver (examples/adi_poisson.jl:42-59), one GPU
+// ------------------------------------------------------------------------------------
+__global__ void k_scale_copy(const double *__restrict__ src, int64_t lds, double *__restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, double s) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) dst[c * ldd + r] = s * src[c * lds + r];
+}
+
+static int scale_copy(pop_ctx *ctx, const double *src, int64_t lds, double *dst, int64_t ldd, int64_t rows, int64_t cols, double s) {
+    dim3 grid((unsigned)((rows + 255) / 256), (unsigned)std::min<int64_t>(cols, 32768));
+    k_scale_copy<<<grid, 256, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols, s);
+    ctx->launches++;
+    POP_CUDA(cudaGetLastError());
+    return POP_OK;
+}
+
+static void free_handles(pop_ctx *ctx, std::vector<pop_arrowhead *> &v) {
+    for (auto *h : v) pop_arrowhead_free(ctx, h);
+    v.clear();
+}
+
+extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, const double *dF, int64_t ldf, double *dX,
+                               int64_t ldx, double a, double b, double c, double d, double tol, int J) {
+    POP_REQUIRE(ctx && K && M && dF && dX, POP_ERR_ARG, "pop_adi_poisson: null argument");
+    POP_REQUIRE(K->d.m == M->d.m && K->d.nh == M->d.nh && K->d.q == M->d.q, POP_ERR_DIM, "pop_adi_poisson: K and M differ in size");
+    const int64_t n = K->n();
+    POP_REQUIRE(ldf >= n && ldx >= n, POP_ERR_DIM, "pop_adi_poisson: leading dimensions too small");
+    if (J <= 0) J = pop_adi_num_iterations(a, b, c, d, tol);
+    POP_REQUIRE(J >= 1 && J <= 2000, POP_ERR_ARG, "pop_adi_poisson: iteration count %d out of range", J);
+    std::vector<double> p(J), q(J);
+    int rc = pop_adi_shifts(J, a, b, c, d, p.data(), q.data());
+    if (rc) return rc;
+    // factors of S1_j = K + M/p_j, S2_j = K - M/q_j  and products T1_j = M/p_j - K, T2_j = -M/q_j - K
+    std::vector<double> al(2 * J), sg(2 * J), ta(2 * J), tb(2 * J);
+    for (int j = 0; j < J; ++j) {
+        al[2 * j] = 1.0; sg[2 * j] = 1.0 / p[j];
+        al[2 * j + 1] = 1.0; sg[2 * j + 1] = -1.0 / q[j];
+        ta[2 * j] = -1.0; tb[2 * j] = 1.0 / p[j];
+        ta[2 * j + 1] = -1.0; tb[2 * j + 1] = -1.0 / q[j];
+    }
+    std::vector<pop_arrowhead *> fac(2 * J, nullptr), top(2 * J, nullptr);
+    rc = pop_revchol_shifted_batch(ctx, K, M, al.data(), sg.data(), 2 * J, fac.data(), nullptr);
+    if (rc) { free_handles(ctx, fac); return rc; }
+    {
+        pop_arrowhead Ku = *K, Mu = *M;   // upper data (Symmetric views)
+        Ku.d.nC = 0; Mu.d.nC = 0;
+        Ku.p.D = K->p.D + (size_t)K->d.lD * K->d.q * K->mD; Ku.d.lD = 0;
+        Mu.p.D = M->p.D + (size_t)M->d.lD * M->d.q * M->mD; Mu.d.lD = 0;
+        rc = pop_launch_axpby_batch(ctx, &Ku, &Mu, ta.data(), tb.data(), 2 * J, top.data());
+        if (rc) { free_handles(ctx, fac); free_handles(ctx, top); return rc; }
+    }
+    const int64_t ld = (n + 1) & ~(int64_t)1;
+    double *buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)ld * n * 3 * sizeof(double));
+    if (e != cudaSuccess) {
+        free_handles(ctx, fac); free_handles(ctx, top);
+        pop_set_error("pop_adi_poisson: %zu bytes of workspace: %s", (size_t)ld * n * 3 * 8, cudaGetErrorString(e));
+        return POP_ERR_ALLOC;
+    }
+    double *W = buf, *V = buf + (size_t)ld * n, *Ft = buf + (size_t)2 * ld * n;
+    do {
+        if ((rc = pop_transpose(ctx, dF, ldf, n, n, Ft, ld))) break;
+        // X0 = 0  =>  R1 = -F/p_1 ; W holds R1^T
+        if ((rc = scale_copy(ctx, Ft, ld, W, ld, n, n, -1.0 / p[0]))) break;
+        for (int j = 0; j < J && rc == POP_OK; ++j) {
+            // W <- T2_j (S1_j^{-1} W) - F^T/q_j      (= R2^T)
+            if ((rc = pop_solve_mul_axpy(ctx, fac[2 * j], top[2 * j + 1], -1.0 / q[j], Ft, ld, W, ld, n))) break;
+            if ((rc = pop_transpose(ctx, W, ld, n, n, V, ld))) break;
+            if (j + 1 < J) {
+                // V <- T1_{j+1} (S2_j^{-1} V) - F/p_{j+1}   (= R1 of the next iteration)
+                if ((rc = pop_solve_mul_axpy(ctx, fac[2 * j + 1], top[2 * j + 2], -1.0 / p[j + 1], dF, ldf, V, ld, n))) break;
+                if ((rc = pop_transpose(ctx, V, ld, n, n, W, ld))) break;
+            } else {
+                if ((rc = pop_solve(ctx, fac[2 * j + 1], POP_LEFT, V, ld, n, POP_SOLVE_AUTO))) break;
+            }
+        }
+        if (rc) break;
+        e = cudaMemcpy2DAsync(dX, ldx * 8, V, ld * 8, n * 8, n, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { pop_set_error("pop_adi_poisson: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    free_handles(ctx, fac);
+    free_handles(ctx, top);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------
+// heat stepping (examples/heat.jl:58-63): A = factorize(M - h*Delta); u <- A \ (M*u)
+// ------------------------------------------------------------------------------------
+extern "C" int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt, int nsteps, int dims, double *dU,
+                              int64_t ldu, int64_t nrhs) {
+    POP_REQUIRE(ctx && K && M && dU, POP_ERR_ARG, "pop_heat_steps: null argument");
+    POP_REQUIRE(dims == 1 || dims == 2, POP_ERR_ARG, "pop_heat_steps: dims must be 1 or 2");
+    POP_REQUIRE(nsteps >= 0 && dt > 0, POP_ERR_ARG, "pop_heat_steps: need nsteps >= 0, dt > 0");
+    const int64_t n = K->n();
+    if (dims == 2) nrhs = n;
+    POP_REQUIRE(ldu >= n && nrhs >= 0, POP_ERR_DIM, "pop_heat_steps: DimensionMismatch");
+    if (nsteps == 0 || nrhs == 0) return POP_OK;
+    pop_arrowhead *U = nullptr;
+    double one = 1.0;
+    int rc = pop_revchol_shifted_batch(ctx, M, K, &one, &dt, 1, &U, nullptr);   // S = M + dt*K
+    if (rc) return rc;
+    const int64_t ld = (n + 1) & ~(int64_t)1;
+    double *buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)ld * nrhs * sizeof(double));
+    if (e != cudaSuccess) { pop_arrowhead_free(ctx, U); pop_set_error("pop_heat_steps: workspace: %s", cudaGetErrorString(e)); return POP_ERR_ALLOC; }
+    MulView mv;
+    pop_make_mulview(M, POP_SYM_UPPER, 0, &mv);
+    do {
+        if (dims == 1) {
+            // v = M u;  (nsteps-1) x  v <- M (S^{-1} v)  in one pass each;  u = S^{-1} v
+            if ((rc = pop_launch_mul(ctx, mv, 1.0, dU, 1, ldu, 0.0, buf, 1, ld, nrhs))) break;
+            for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, M, 0.0, buf, ld, buf, ld, nrhs);
+            if (rc) break;
+            if ((rc = pop_solve(ctx, U, POP_LEFT, buf, ld, nrhs, POP_SOLVE_AUTO))) break;
+            e = cudaMemcpy2DAsync(dU, ldu * 8, buf, ld * 8, n * 8, nrhs, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) { pop_set_error("pop_heat_steps: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
+        } else {
+            // U <- S^{-1} M U M S^{-1}: apply G = S^{-1} M along columns, transpose, again, transpose
+            double *cur = dU; int64_t ldc = ldu;
+            double *oth = buf; int64_t ldo = ld;
+            for (int s = 0; s < 2 * nsteps && rc == POP_OK; ++s) {
+                if ((rc = pop_launch_mul(ctx, mv, 1.0, cur, 1, ldc, 0.0, oth, 1, ldo, n))) break;
+                if ((rc = pop_solve(ctx, U, POP_LEFT, oth, ldo, n, POP_SOLVE_AUTO))) break;
+                if ((rc = pop_transpose(ctx, oth, ldo, n, n, cur, ldc))) break;
+            }
+        }
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    pop_arrowhead_free(ctx, U);
+    return rc;
+}

@@ -1,0 +1,202 @@
+"""Drivers of the reference's examples on the accelerated path.
+
+  adi_poisson : examples/adi_poisson.jl:42-59   ADI(A=M, B=-M, C=K, F, a, b, c, d, tol)
+  heat_steps  : examples/heat.jl:58-63          A = factorize(M - h*Delta); u <- A \\ (M*u)
+  spectrum_bounds : replaces the dense eigmin/eigmax of examples/adi_poisson.jl:91-94 by power /
+                    inverse iteration on the arrowhead kernels.
+
+Multi-GPU (one process per GPU, torch.distributed): X is distributed by column blocks; the
+x<->y switch between the two half steps is one all-to-all (NCCL over NVLink) of locally
+transposed tiles.  Shift computation and the 2J small factorisations are replicated.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from .arrowhead import BBBArrowheadMatrix, Symmetric, _Panel, _bind_stream, _new_like
+
+
+def _base(S):
+    return S.data if isinstance(S, Symmetric) else S
+
+
+def adi_num_iterations(a, b, c, d, tol=1e-15) -> int:
+    return int(L.lib().pop_adi_num_iterations(a, b, c, d, tol))
+
+
+def adi_shifts(J, a, b, c, d):
+    p = np.zeros(J)
+    q = np.zeros(J)
+    L.check(L.lib().pop_adi_shifts(int(J), a, b, c, d, p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p)), "ADI_shifts")
+    return p, q
+
+
+def adi_poisson(M, K, F, a, b, c=None, d=None, tol=1e-15, J=0):
+    """Solve K X M + M X K = F by the reference's ADI iteration on ONE GPU.  F: CUDA torch tensor
+    (n x n, column-major) or NumPy array; returns X of the same kind.  (a,b) enclose the spectrum
+    of K^{-1}M; c,d default to -b,-a as in examples/adi_poisson.jl:107."""
+    Mb, Kb = _base(M), _base(K)
+    c = -b if c is None else c
+    d = -a if d is None else d
+    host = not hasattr(F, "data_ptr")
+    if host:
+        import torch
+        Fd = torch.from_numpy(np.asfortranarray(F).T.copy()).to(f"cuda:{Mb.ctx.device}").t()
+    else:
+        Fd = F
+    pf = _Panel(Fd, False)
+    X = _new_like(Fd, tuple(Fd.shape))
+    px = _Panel(X, True)
+    _bind_stream(Mb.ctx)
+    L.check(L.lib().pop_adi_poisson(Mb.ctx.handle, Kb._h, Mb._h, pf.ptr, pf.ld, px.ptr, px.ld, a, b, c, d, tol, int(J)), "ADI")
+    if host:
+        return np.asfortranarray(X.cpu().numpy())
+    return X
+
+
+def heat_steps(M, K, U, dt, nsteps, dims=1):
+    """In place: nsteps of backward Euler with one factorisation of M + dt*K (K = -Delta)."""
+    Mb, Kb = _base(M), _base(K)
+    p = _Panel(U, True)
+    if not p.torch:
+        raise TypeError("heat_steps works on device-resident (CUDA torch) fields")
+    _bind_stream(Mb.ctx)
+    L.check(L.lib().pop_heat_steps(Mb.ctx.handle, Kb._h, Mb._h, float(dt), int(nsteps), int(dims), p.ptr, p.ld, p.cols), "heat")
+    return U
+
+
+def spectrum_bounds(M, K, iters=200, seed=0):
+    """(a, b) with a <= lambda(K^{-1} M) <= b: b by power iteration on K^{-1}M, a = 1/lambda_max(M^{-1}K)
+    by power iteration on M^{-1}K, both through reverse-Cholesky solves on the device; widened by 1e-6
+    relative so the interval encloses the spectrum (ADI converges for any enclosing interval)."""
+    import torch
+    from .arrowhead import ldiv, mul, reversecholesky
+    Ms, Ks = (M if isinstance(M, Symmetric) else Symmetric(M)), (K if isinstance(K, Symmetric) else Symmetric(K))
+    FM, FK = reversecholesky(Ms), reversecholesky(Ks)
+    n = Ms.n
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = f"cuda:{_base(M).ctx.device}"
+
+    def power(applyA, solveB):
+        x = torch.randn(n, generator=g, dtype=torch.float64).to(dev)
+        lam = 0.0
+        for _ in range(iters):
+            y = ldiv(solveB, mul(applyA, x))
+            lam = float(torch.dot(x, y) / torch.dot(x, x))
+            x = y / torch.linalg.norm(y)
+        return lam
+
+    b = power(Ms, FK)          # lambda_max(K^{-1} M)
+    lmax = power(Ks, FM)       # lambda_max(M^{-1} K)
+    return (1.0 / lmax) * (1 - 1e-6), b * (1 + 1e-6)
+
+
+# --------------------------------------------------------------------------------------
+# multi-GPU ADI: column-block distribution, all-to-all transposes (torch.distributed)
+# --------------------------------------------------------------------------------------
+def shard_bounds(n: int, world: int):
+    """Column ranges [lo, hi) per rank: near-equal split, first n % world ranks one larger."""
+    base, rem = divmod(n, world)
+    lo = [r * base + min(r, rem) for r in range(world)]
+    return [(lo[r], lo[r] + base + (1 if r < rem else 0)) for r in range(world)]
+
+
+class DistTranspose:
+    """Distributed transpose of an n x n matrix held as column blocks: rank r owns columns
+    [lo_r, hi_r).  Afterwards rank r owns the same column range of the TRANSPOSED matrix.
+    Tile (rows of block s, my columns) is transposed locally by pop_transpose into the send
+    buffer; one all_to_all_single exchanges the tiles; received tiles are already column-major
+    slices of the destination and are placed with one strided copy each."""
+
+    def __init__(self, n, group=None, ctx=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n = n
+        self.bounds = shard_bounds(n, self.world)
+        self.lo, self.hi = self.bounds[self.rank]
+        self.w = self.hi - self.lo
+        self.ctx = ctx
+        self.device = device
+        self.send_counts = [(hi - lo) * self.w for lo, hi in self.bounds]
+        self.recv_counts = list(self.send_counts)
+        self.sendbuf = torch.empty(sum(self.send_counts), dtype=torch.float64, device=device)
+        self.recvbuf = torch.empty(sum(self.recv_counts), dtype=torch.float64, device=device)
+
+    def __call__(self, src, dst):
+        """src, dst: column-major (n x w) CUDA tensors (views with stride(0) == 1)."""
+        import torch
+        ps, pd = _Panel(src, False), _Panel(dst, True)
+        if self.ctx is not None and src.is_cuda:
+            _bind_stream(self.ctx)
+        off = 0
+        for s, (lo, hi) in enumerate(self.bounds):
+            rows = hi - lo
+            # tile = src[lo:hi, :] (rows x w) -> its transpose (w x rows), column-major, packed
+            if src.is_cuda:
+                L.check(L.lib().pop_transpose(self.ctx.handle, ps.ptr + 8 * lo, ps.ld, rows, self.w,
+                                              self.sendbuf.data_ptr() + 8 * off, self.w), "transpose")
+            else:
+                self.sendbuf[off: off + rows * self.w].view(rows, self.w).copy_(src[lo:hi, :])
+            off += rows * self.w
+        if self.world > 1:
+            self.dist.all_to_all_single(self.recvbuf, self.sendbuf, self.recv_counts, self.send_counts, group=self.group)
+            rb = self.recvbuf
+        else:
+            rb = self.sendbuf
+        # the tile received from rank s is (w_s x w) column-major = dst[lo_s:hi_s, :]
+        off = 0
+        for s, (lo, hi) in enumerate(self.bounds):
+            rows = hi - lo
+            tile = rb[off: off + rows * self.w].view(self.w, rows).t()
+            dst[lo:hi, :].copy_(tile)
+            off += rows * self.w
+        return dst
+
+
+def adi_poisson_distributed(M, K, F_local, Ft_local, a, b, c=None, d=None, tol=1e-15, J=0, group=None):
+    """Multi-GPU ADI.  F_local = F[:, lo:hi], Ft_local = F^T[:, lo:hi] (column blocks of F and of its
+    transpose, column-major CUDA tensors).  Returns X[:, lo:hi].  Same operator sequence as
+    pop_adi_poisson (csrc/pop_host.cu) with the local transposes replaced by DistTranspose."""
+    import torch
+    from .arrowhead import reversecholesky_shifted
+    Mb, Kb = _base(M), _base(K)
+    ctx = Mb.ctx
+    c = -b if c is None else c
+    d = -a if d is None else d
+    n = Mb.n
+    if J <= 0:
+        J = adi_num_iterations(a, b, c, d, tol)
+    p, q = adi_shifts(J, a, b, c, d)
+    al = np.ones(2 * J)
+    sg = np.empty(2 * J)
+    sg[0::2] = 1.0 / p
+    sg[1::2] = -1.0 / q
+    facs = reversecholesky_shifted(Kb, Mb, al, sg)
+    tops = [Mb._axpby(s, Kb, -1.0) for s in sg]          # T1_j = M/p_j - K (even), T2_j = -M/q_j - K (odd)
+    tr = DistTranspose(n, group=group, ctx=ctx, device=F_local.device)
+    w = tr.w
+    W = _new_like(F_local, (n, w))
+    V = _new_like(F_local, (n, w))
+    lib = L.lib()
+    pF, pFt = _Panel(F_local, False), _Panel(Ft_local, False)
+    pW, pV = _Panel(W, True), _Panel(V, True)
+    W.copy_(Ft_local)
+    W.mul_(-1.0 / p[0])
+    _bind_stream(ctx)
+    for j in range(J):
+        L.check(lib.pop_solve_mul_axpy(ctx.handle, facs[2 * j].factor._h, tops[2 * j + 1]._h, -1.0 / q[j], pFt.ptr, pFt.ld, pW.ptr, pW.ld, w), "ADI half step")
+        tr(W, V)
+        if j + 1 < J:
+            L.check(lib.pop_solve_mul_axpy(ctx.handle, facs[2 * j + 1].factor._h, tops[2 * j + 2]._h, -1.0 / p[j + 1], pF.ptr, pF.ld, pV.ptr, pV.ld, w), "ADI half step")
+            tr(V, W)
+        else:
+            L.check(lib.pop_solve(ctx.handle, facs[2 * j + 1].factor._h, L.LEFT, pV.ptr, pV.ld, w, L.SOLVE_AUTO), "ADI final solve")
+    return V

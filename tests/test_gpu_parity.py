@@ -1,0 +1,405 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the host mirror of the reference API)
+against the CPU oracle on the same seeded inputs.  Tolerances: the north star asks for a relative
+solution difference and residual <= 1e-12 in Float64; each assert states its bound.
+
+Testsets of /root/reference/test/test_arrowhead.jl are restated one by one (line numbers cited)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import pop_b200 as P  # noqa: E402
+from oracle import arrowhead_oracle as O  # noqa: E402
+from tests.util import packed_to_product, product_to_packed, random_general, relerr, to_product  # noqa: E402
+
+TOL = 1e-12
+
+
+def dev(x):
+    """NumPy (any order) -> column-major CUDA tensor with an even leading dimension."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        return torch.from_numpy(x.copy()).cuda()
+    rows, cols = x.shape
+    ld = (rows + 1) & ~1
+    buf = torch.zeros((cols, ld), dtype=torch.float64, device="cuda")
+    buf[:, :rows] = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    return buf.t()[:rows]
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(autouse=True)
+def _fused_env():
+    old = {k: os.environ.get(k) for k in ("POP_FUSED_CS", "POP_DISABLE_FUSED")}
+    yield
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+# --------------------------------------------------------------------------------------
+# test_arrowhead.jl testsets
+# --------------------------------------------------------------------------------------
+def test_constructor_and_dense_roundtrip():
+    # :9-15
+    rng = np.random.default_rng(0)
+    for lower in (True, False):
+        Ao = random_general(rng, 5, 5, nB=2, nC=3, lower_B=lower, same_D=False)
+        A = to_product(P, Ao)
+        assert isinstance(A, P.BBBArrowheadMatrix)
+        assert A.shape == (Ao.n, Ao.n)
+        assert np.array_equal(A.to_dense(), Ao.to_dense())
+        assert A.blockaxes() == (Ao.nh,) + (Ao.m,) * Ao.q
+
+
+def test_algebra():
+    # :17-37  (exact equalities, as in the reference)
+    rng = np.random.default_rng(1)
+    Ao = random_general(rng, 4, 5)
+    A = to_product(P, Ao)
+    S = Ao.to_dense()
+    assert np.array_equal((2 * A).to_dense(), 2 * S)
+    assert np.array_equal((A * 2).to_dense(), 2 * S)
+    assert np.array_equal((A + A).to_dense(), 2 * S)
+    assert np.all((A - A).to_dense() == 0)
+    assert np.array_equal((A / 2).to_dense(), S / 2)
+    At = to_product(P, Ao.transpose())
+    assert np.array_equal((A + At).to_dense(), S + S.T)
+    assert np.array_equal((A - At).to_dense(), S - S.T)
+    assert np.array_equal((-A).to_dense(), -S)
+    # ragged B tuples (tupleop, :392-398): Laplacian (no B) + mass (two B blocks)
+    C = P.ContinuousPolynomial(1, np.linspace(-1, 1, 4))
+    KR = P.Block.oneto(6)
+    M = P.grammatrix(C)[KR, KR]
+    Lp = P.weaklaplacian(C)[KR, KR]
+    Hm = (-Lp + M).to_dense()
+    np.testing.assert_array_equal(Hm, -Lp.to_dense() + M.to_dense())
+
+
+def test_mul():
+    # :39-54
+    rng = np.random.default_rng(2)
+    Ao = random_general(rng, 4, 5)
+    A = to_product(P, Ao)
+    S = Ao.to_dense()
+    n = Ao.n
+    x = rng.standard_normal(n)
+    X = rng.standard_normal((n, n))
+    Xt = rng.standard_normal((n, 5))
+    for wrap in (dev, np.asfortranarray):          # device pointers and host buffers
+        get = host if wrap is dev else np.asarray
+        assert relerr(get(A @ wrap(x)), S @ x) < TOL                 # A*x
+        assert relerr(get(A.T @ wrap(x)), S.T @ x) < TOL             # A'*x
+        assert relerr(get(A @ wrap(X)), S @ X) < TOL                 # A*X
+        assert relerr(get(A @ wrap(Xt)), S @ Xt) < TOL               # A*X~
+        assert relerr(get(wrap(X) @ A), X @ S) < TOL                 # X*A
+    Y0 = rng.standard_normal((n, 5))
+    out = dev(Y0)
+    P.mul(A, dev(Xt), alpha=0.7, beta=-1.3, out=out)                 # mul!(Y, A, X, alpha, beta)
+    assert relerr(host(out), 0.7 * S @ Xt - 1.3 * Y0) < TOL
+    Sy = P.Symmetric(A)
+    assert relerr(host(Sy @ dev(Xt)), Sy.to_dense() @ Xt) < TOL
+    assert relerr(host(dev(X) @ Sy), X @ Sy.to_dense()) < TOL
+    with pytest.raises(P.DimensionMismatch):
+        A @ dev(rng.standard_normal(n + 1))
+
+
+@pytest.mark.parametrize("lower_B", [True, False])
+def test_triangular(lower_B):
+    # :56-81
+    rng = np.random.default_rng(3)
+    Ao = random_general(rng, 5, 5, nB=2, nC=2, lower_B=lower_B, same_D=False)
+    A = to_product(P, Ao)
+    n = Ao.n
+    c = rng.standard_normal(n)
+    Cm = rng.standard_normal((n, 7))
+    R = rng.standard_normal((6, n))
+    for T in (P.UpperTriangular(A), P.UnitUpperTriangular(A), P.LowerTriangular(A), P.UnitLowerTriangular(A), P.UpperTriangular(A).T):
+        Td = T.to_dense()
+        assert relerr(host(P.ldiv(T, dev(c))), np.linalg.solve(Td, c)) < 1e-11        # T \ c
+        assert relerr(host(P.rdiv(dev(c), T)), np.linalg.solve(Td.T, c)) < 1e-11      # c' / T
+        assert relerr(host(P.ldiv(T, dev(Cm))), np.linalg.solve(Td, Cm)) < 1e-11
+        assert relerr(host(P.rdiv(dev(R), T)), np.linalg.solve(Td.T, R.T).T) < 1e-11  # X / T
+        assert relerr(P.ldiv(T, np.asfortranarray(Cm)), np.linalg.solve(Td, Cm)) < 1e-11
+
+
+@pytest.mark.parametrize("diag1", [False, True])
+def test_reversecholesky_lower_B(diag1):
+    # :83-100
+    rng = np.random.default_rng(4)
+    Ao = random_general(rng, 3, 5, nB=2, nC=0, lD=0, diag1=diag1)
+    A = to_product(P, Ao)
+    Uw = O.dense_reversecholesky(O.symmetric_from_upper(Ao).to_dense())
+    F = P.reversecholesky(P.Symmetric(A))
+    assert relerr(F.U.to_dense(), Uw) < TOL
+    F2 = P.reversecholesky_inplace(P.Symmetric(A.copy()))
+    assert relerr(F2.U.to_dense(), Uw) < TOL
+    assert relerr(F.L.to_dense(), Uw.T) < TOL
+
+
+def test_reversecholesky_dirichlet_upper_B():
+    # :137-146
+    rng = np.random.default_rng(5)
+    Ao = random_general(rng, 5, 5, nB=2, nC=0, lower_B=False, lD=0)
+    A = to_product(P, Ao)
+    Ssym = O.symmetric_from_upper(Ao).to_dense()
+    U = P.reversecholesky(P.Symmetric(A)).U.to_dense()
+    assert relerr(U, O.dense_reversecholesky(Ssym)) < TOL
+    assert relerr(U @ U.T, Ssym) < TOL
+
+
+def test_helmholtz_reference_golden():
+    # :117-135 -- the reference's known-answer value
+    r = np.linspace(-1, 1, 4)
+    C = P.ContinuousPolynomial(1, r)
+    Delta = P.weaklaplacian(C)
+    M = P.grammatrix(C)
+    KR = P.Block.oneto(100)
+    F = P.reversecholesky((-Delta + M)[KR, KR])
+    cexp = O.c1_expand(np.exp, np.exp, r, 100)            # transform(C, exp)[KR] (out-of-scope transform: oracle)
+    x = M[KR, KR] @ cexp
+    c = P.ldiv(F, x)
+    assert abs(O.c1_evaluate(c, r, 100, 0.1) - 1.1952730862177243) < 5e-13
+    cd = host(P.ldiv(F, dev(x)))
+    assert relerr(cd, c) < TOL
+
+
+def test_not_positive_definite_and_structure_errors():
+    rng = np.random.default_rng(6)
+    Ao = random_general(rng, 4, 5, nB=2, nC=0, lD=0)
+    Ao.D[1][2, 2] = -5.0
+    with pytest.raises(P.PosDefException) as ei:
+        P.reversecholesky(P.Symmetric(to_product(P, Ao)))
+    assert ei.value.code == Ao.nh + 2 * Ao.m + 1 + 1         # 1-based global index of the bad pivot
+    Ao = random_general(rng, 4, 5, nB=2, nC=0, lD=0)
+    Ao.A[1, 1] = -100.0
+    with pytest.raises(P.PosDefException) as ei:
+        P.reversecholesky(P.Symmetric(to_product(P, Ao)))
+    assert ei.value.code == 2
+    F = P.reversecholesky(P.Symmetric(to_product(P, random_general(rng, 4, 5, nB=2, nC=0, lD=0))))
+    with pytest.raises(P.DimensionMismatch):
+        P.ldiv(F, dev(np.zeros(7)))
+
+
+# --------------------------------------------------------------------------------------
+# assembly + factor + solve against the oracle (staged and fused kernels, all cluster sizes)
+# --------------------------------------------------------------------------------------
+def _assemble(basis, m, N):
+    h = 2.0 / m
+    if basis == "c1":
+        B = P.ContinuousPolynomial(1, np.linspace(-1, 1, m + 1))
+        bo = O.C1
+    else:
+        B = P.DirichletPolynomial(np.linspace(-1, 1, m + 1))
+        bo = O.DIRICHLET
+    KR = P.Block.oneto(N)
+    M = P.grammatrix(B)[KR, KR]
+    Lp = P.weaklaplacian(B)[KR, KR]
+    return M, Lp, O.assemble_mass(bo, m, N, h), O.assemble_weaklaplacian(bo, m, N, h)
+
+
+@pytest.mark.parametrize("basis,m,N", [("c1", 3, 10), ("dirichlet", 4, 12), ("c1", 7, 5), ("dirichlet", 9, 3), ("c1", 5, 2), ("c1", 4, 1)])
+def test_assembly_matches_oracle(basis, m, N):
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    np.testing.assert_allclose(M.data.to_dense(), O.unpack(Mo).to_dense(), rtol=2e-16, atol=0)
+    np.testing.assert_allclose(Lp.data.to_dense(), O.unpack(Lo).to_dense(), rtol=2e-16, atol=0)
+
+
+def test_readme_case_goldens():
+    """BASELINE config 1: README case, survey goldens."""
+    M, Lp, Mo, Lo = _assemble("c1", 3, 10)
+    F = P.reversecholesky(-Lp + M)
+    Lf = F.L.to_dense()
+    for (i, j), v in {(1, 1): 0.9818490617583832, (2, 1): -0.8671084871570119, (5, 5): 1.4452827020171803, (8, 1): -0.020179587355387243,
+                      (11, 5): -0.006841062695774555, (31, 25): -0.0002447828624173438, (31, 31): 0.5621263590512574}.items():
+        assert abs(Lf[i - 1, j - 1] - v) < 1e-14
+    b = np.arange(1, 32) / 31
+    for algo in (P.SOLVE_STAGED, P.SOLVE_AUTO):
+        x = host(P.ldiv(F, dev(b), algo=algo))
+        for i, v in {1: 0.11098908536056581, 4: 0.18024989943421074, 5: 0.06638120377479541, 31: 3.1655746467356325}.items():
+            assert abs(x[i - 1] - v) < 1e-13 * max(1, abs(v))
+    Uo = O.packed_revchol(O.packed_axpby(-1.0, Lo, 1.0, Mo))
+    assert relerr(F.U.to_dense(), O.unpack(Uo).to_dense()) < TOL
+
+
+SHAPES = [("c1", 16, 12), ("dirichlet", 8, 9), ("dirichlet", 16, 24), ("c1", 13, 7), ("dirichlet", 11, 6), ("c1", 64, 40), ("dirichlet", 32, 64),
+          ("c1", 2, 3), ("dirichlet", 2, 4), ("c1", 1, 6)]
+
+
+@pytest.mark.parametrize("basis,m,N", SHAPES)
+@pytest.mark.parametrize("sigma", [1.0, 1e4])
+def test_solve_staged_and_fused_vs_oracle(basis, m, N, sigma):
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    S = -Lp + sigma * M
+    So = O.packed_axpby(-1.0, Lo, sigma, Mo)
+    Uo = O.packed_revchol(So)
+    F = P.reversecholesky(S)
+    assert relerr(F.U.to_dense(), O.unpack(Uo).to_dense()) < TOL
+    n = So.n
+    rng = np.random.default_rng(7)
+    Bm = rng.standard_normal((n, 37))
+    want = O.packed_solve(Uo, Bm.copy())
+    os.environ.pop("POP_FUSED_CS", None)
+    got = {"staged": host(P.ldiv(F, dev(Bm), algo=P.SOLVE_STAGED))}
+    for cs in (1, 2, 4, 8):
+        if cs > m:
+            continue
+        os.environ["POP_FUSED_CS"] = str(cs)
+        got[f"fused cs={cs}"] = host(P.ldiv(F, dev(Bm), algo=P.SOLVE_FUSED))
+    os.environ.pop("POP_FUSED_CS", None)
+    got["auto"] = host(P.ldiv(F, dev(Bm)))
+    got["host"] = P.ldiv(F, np.asfortranarray(Bm))
+    got["vector"] = host(P.ldiv(F, dev(Bm[:, 0])))[:, None]
+    Sd = O.unpack(O.packed_symmetrize(So)).to_dense()
+    for name, x in got.items():
+        ref = want if name != "vector" else want[:, :1]
+        rhs = Bm if name != "vector" else Bm[:, :1]
+        assert relerr(x, ref) < TOL, name
+        assert np.linalg.norm(Sd @ x - rhs) / (np.linalg.norm(Sd, 2) * np.linalg.norm(x)) < TOL, name
+    # X / F on rows (examples/adi_poisson.jl:54)
+    R = rng.standard_normal((9, n))
+    assert relerr(host(P.rdiv(dev(R), F)), O.packed_solve(Uo, R.T.copy()).T) < TOL
+
+
+def test_solve_per_element_blocks_general_bands():
+    """Distinct D_k per element and a non-zero first superdiagonal (test_arrowhead.jl:96)."""
+    rng = np.random.default_rng(8)
+    for lower in (True, False):
+        Ao = random_general(rng, 19, 11, nB=2, nC=0, lower_B=lower, lD=0, diag1=True, same_D=False)
+        for k in range(Ao.m):      # make S comfortably positive definite
+            Ao.D[k] += 5 * np.eye(Ao.q)
+        A = to_product(P, Ao)
+        F = P.reversecholesky(P.Symmetric(A))
+        Ssym = O.symmetric_from_upper(Ao).to_dense()
+        assert relerr(F.U.to_dense(), O.dense_reversecholesky(Ssym)) < TOL
+        Bm = rng.standard_normal((Ao.n, 21))
+        want = np.linalg.solve(Ssym, Bm)
+        for algo in (P.SOLVE_STAGED, P.SOLVE_FUSED):
+            for cs in ("1", "2"):
+                os.environ["POP_FUSED_CS"] = cs
+                assert relerr(host(P.ldiv(F, dev(Bm), algo=algo)), want) < 1e-11
+
+
+def test_shifted_batch_factor_and_solve():
+    """BASELINE config 3 in miniature: Dirichlet, many shifts sigma, batched factor + solve."""
+    m, N = 16, 16
+    M, Lp, Mo, Lo = _assemble("dirichlet", m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    sig = np.logspace(np.log10(np.pi ** 2 / 4), 8, 12)
+    facs = P.reversecholesky_shifted(K, M, np.ones_like(sig), sig)
+    assert len(facs) == len(sig)
+    rng = np.random.default_rng(9)
+    Bm = rng.standard_normal((Ko.n, 16))
+    for s, F in zip(sig, facs):
+        Uo = O.packed_revchol(O.packed_axpby(1.0, Ko, s, Mo))
+        assert relerr(F.U.to_dense(), O.unpack(Uo).to_dense()) < TOL
+        assert relerr(host(P.ldiv(F, dev(Bm))), O.packed_solve(Uo, Bm.copy())) < TOL
+    with pytest.raises(P.PosDefException):
+        P.reversecholesky_shifted(K, M, np.ones(3), np.array([1.0, -1e9, 2.0]))
+
+
+@pytest.mark.parametrize("basis,m,N", [("dirichlet", 8, 12), ("c1", 16, 9), ("dirichlet", 32, 20)])
+def test_fused_solve_mul_axpy(basis, m, N):
+    """One ADI half step R <- T (S^{-1} R) + gamma F (examples/adi_poisson.jl:54-55), fused and staged."""
+    import ctypes as C
+    from pop_b200 import _lib as L
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    sigma, gamma = 3.7, -0.4
+    S, T = -Lp + sigma * M, (0.5 * M + Lp)
+    F = P.reversecholesky(S)
+    n = S.n
+    rng = np.random.default_rng(10)
+    R0, Fm = rng.standard_normal((n, 19)), rng.standard_normal((n, 19))
+    Uo = O.packed_revchol(O.packed_axpby(-1.0, Lo, sigma, Mo))
+    To = O.packed_symmetrize(O.packed_axpby(0.5, Mo, 1.0, Lo))
+    Xo = O.packed_solve(Uo, R0.copy())
+    want = np.zeros_like(Xo)
+    O.packed_mul_left(1.0, To, Xo, 0.0, want)
+    want += gamma * Fm
+    for disable in ("0", "1"):
+        os.environ["POP_DISABLE_FUSED"] = disable
+        R, Fd = dev(R0), dev(Fm)
+        L.check(L.lib().pop_solve_mul_axpy(F.ctx.handle, F.factor._h, T.data._h, gamma, Fd.data_ptr(), Fd.stride(1), R.data_ptr(), R.stride(1), 19))
+        torch.cuda.synchronize()
+        assert relerr(host(R), want) < TOL, disable
+
+
+def test_adi_small_vs_oracle():
+    """examples/adi_poisson.jl:42-59 at m=4, N=12 (J=42)."""
+    m, N = 4, 12
+    M, Lp, Mo, Lo = _assemble("dirichlet", m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    n = Mo.n
+    Y = np.random.default_rng(1).standard_normal((n, n))
+    Fm = Kd @ Y @ Md + Md @ Y @ Kd
+    lam = np.linalg.eigvals(np.linalg.solve(Kd, Md)).real
+    a, b = lam.min(), lam.max()
+    X = host(P.adi_poisson(M, K, dev(Fm), a, b))
+    Xo = O.adi_packed(Mo, Ko, Fm, a, b, -b, -a)
+    assert np.abs(X - Xo).max() <= 1e-11 * np.abs(Xo).max()
+    Yg = np.linalg.solve(Kd, X.T).T
+    assert relerr(Yg, Y) < 1e-12
+    res = Kd @ Yg @ Md + Md @ Yg @ Kd - Fm
+    assert np.linalg.norm(res) / np.linalg.norm(Fm) < 1e-12
+    # spectrum bounds by power iteration on the device kernels enclose the dense ones
+    a2, b2 = P.spectrum_bounds(M, K, iters=300)
+    assert a2 <= a * (1 + 1e-9) and b2 >= b * (1 - 1e-9) and a2 > 0.5 * a and b2 < 1.5 * b
+
+
+def test_heat_steps_vs_oracle():
+    # examples/heat.jl:58-63 (1D) and its factored 2D extension
+    m, N = 6, 10
+    M, Lp, Mo, Lo = _assemble("c1", m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    n = Mo.n
+    rng = np.random.default_rng(11)
+    u0 = rng.standard_normal((n, 5))
+    U = dev(u0)
+    P.heat_steps(M, K, U, 1e-3, 7, dims=1)
+    want = O.heat_steps_packed(Mo, Ko, u0, 1e-3, 7)
+    assert relerr(host(U), want) < TOL
+    U0 = rng.standard_normal((n, n))
+    U = dev(U0)
+    P.heat_steps(M, K, U, 1e-3, 3, dims=2)
+    assert relerr(host(U), O.heat2d_steps_packed(Mo, Ko, U0, 1e-3, 3)) < TOL
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE shapes: size-independent properties at (near) full size
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("basis,m,N,ncols", [("c1", 1024, 40, 192), ("dirichlet", 256, 128, 160), ("dirichlet", 128, 64, 300), ("dirichlet", 256, 64, 150)])
+def test_baseline_shapes_residual_and_linearity(basis, m, N, ncols):
+    """cfg 2/3/4/5 column shapes: fused == staged, oracle agreement on a column sample,
+    residual ||S X - B|| through the independent product kernel, linearity."""
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    S = -Lp + M
+    F = P.reversecholesky(S)
+    n = S.n
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ld = (n + 1) & ~1
+    Bt = torch.randn((ncols, ld), generator=g, dtype=torch.float64, device="cuda").t()[:n]
+    Xf = P.ldiv(F, Bt)                                   # auto -> fused
+    Xs = P.ldiv(F, Bt, algo=P.SOLVE_STAGED)
+    assert float(torch.linalg.norm(Xf - Xs) / torch.linalg.norm(Xs)) < TOL
+    R = S @ Xf
+    assert float(torch.linalg.norm(R - Bt) / torch.linalg.norm(Bt)) < TOL
+    Uo = O.packed_revchol(O.packed_axpby(-1.0, Lo, 1.0, Mo))
+    sample = host(Bt[:, :8])
+    assert relerr(host(Xf[:, :8]), O.packed_solve(Uo, sample.copy())) < TOL
+    X2 = P.ldiv(F, 2.0 * Bt[:, :16] - 3.0 * Bt[:, 16:32])
+    assert float(torch.linalg.norm(X2 - (2.0 * Xf[:, :16] - 3.0 * Xf[:, 16:32])) / torch.linalg.norm(X2)) < TOL
