@@ -82,6 +82,7 @@ const char *pop_last_error(void);
  * let the context create its own non-blocking stream. */
 int pop_create(pop_ctx **ctx, int device, void *stream);
 int pop_destroy(pop_ctx *ctx);
+/* use `stream` from now on, exactly as given: NULL (0) is the CUDA legacy default stream */
 int pop_set_stream(pop_ctx *ctx, void *stream);
 int pop_sync(pop_ctx *ctx);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */

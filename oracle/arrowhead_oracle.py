@@ -564,7 +564,9 @@ def packed_revchol(P: Packed) -> Packed:
         B[b] *= (1.0 / Dd[0, b])[None, :]
     Ad, Au = P.Ad.copy(), P.Au.copy()
     ks = np.arange(m)
-    for b in range(P.nB):
+    # only blocks inside the truncation take part (the reference's loop over all of A.B at :378 is
+    # the same thing whenever length(A.B) <= N-1, which its own callers guarantee)
+    for b in range(nb):
         for t in range(3):
             i = ks + t - 1
             ok = (i >= 0) & (i < nh)

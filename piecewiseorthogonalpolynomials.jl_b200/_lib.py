@@ -133,7 +133,8 @@ class Context:
         return self._h
 
     def set_stream(self, stream):
-        check(lib().pop_set_stream(self._h, vp(stream) if stream else None))
+        """Bind to a raw cudaStream_t handle; 0/None is the CUDA legacy default stream (torch's default)."""
+        check(lib().pop_set_stream(self._h, vp(int(stream)) if stream else None))
 
     def sync(self):
         check(lib().pop_sync(self._h))

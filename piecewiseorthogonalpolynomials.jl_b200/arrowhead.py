@@ -94,6 +94,8 @@ class BBBArrowheadMatrix:
     BBBArrowheadMatrix(A, B, C, D): A (nh x nh, bandwidths <= (1,1)), B tuple of nh x m blocks,
     C tuple of m x nh blocks, D list of m banded q x q blocks (all the same bandwidths)."""
 
+    __array_ufunc__ = None      # let `ndarray @ A` reach __rmatmul__
+
     def __init__(self, A=None, B=(), C=(), D=None, *, ctx: Optional[Context] = None, _handle=None):
         self.ctx = ctx or default_context()
         if _handle is not None:
@@ -224,6 +226,7 @@ class BBBArrowheadMatrix:
 class _Wrapper:
     sym = L.GENERAL
     trans = 0
+    __array_ufunc__ = None
 
     def __init__(self, data: BBBArrowheadMatrix):
         self.data = data

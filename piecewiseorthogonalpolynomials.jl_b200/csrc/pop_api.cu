@@ -74,17 +74,15 @@ extern "C" int pop_destroy(pop_ctx *ctx) {
 
 extern "C" int pop_set_stream(pop_ctx *ctx, void *stream) {
     POP_REQUIRE(ctx, POP_ERR_ARG, "pop_set_stream: null ctx");
+    if ((cudaStream_t)stream == ctx->stream && !ctx->own_stream) return POP_OK;
     if (ctx->own_stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
         ctx->own_stream = false;
     }
-    if (stream) {
-        ctx->stream = (cudaStream_t)stream;
-    } else {
-        POP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    }
+    // the handle is used as given; NULL is the CUDA (legacy) default stream, which is also what
+    // torch.cuda.current_stream().cuda_stream reports for torch's default stream
+    ctx->stream = (cudaStream_t)stream;
     return POP_OK;
 }
 

@@ -255,6 +255,8 @@ def test_solve_staged_and_fused_vs_oracle(basis, m, N, sigma):
     for cs in (1, 2, 4, 8):
         if cs > m:
             continue
+        if (cs - 1) * -(-m // cs) >= m:
+            continue                  # an empty trailing rank: not a valid partition
         os.environ["POP_FUSED_CS"] = str(cs)
         got[f"fused cs={cs}"] = host(P.ldiv(F, dev(Bm), algo=P.SOLVE_FUSED))
     os.environ.pop("POP_FUSED_CS", None)
@@ -397,7 +399,13 @@ def test_baseline_shapes_residual_and_linearity(basis, m, N, ncols):
     Xs = P.ldiv(F, Bt, algo=P.SOLVE_STAGED)
     assert float(torch.linalg.norm(Xf - Xs) / torch.linalg.norm(Xs)) < TOL
     R = S @ Xf
-    assert float(torch.linalg.norm(R - Bt) / torch.linalg.norm(Bt)) < TOL
+    v = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
+    for _ in range(30):                                                     # power iteration: ||S||_2 from below
+        v = S @ v
+        normS = float(torch.linalg.norm(v))
+        v = v / normS
+    # normwise backward error  ||S X - B|| / (||S|| ||X|| + ||B||)
+    assert float(torch.linalg.norm(R - Bt) / (normS * torch.linalg.norm(Xf) + torch.linalg.norm(Bt))) < TOL
     Uo = O.packed_revchol(O.packed_axpby(-1.0, Lo, 1.0, Mo))
     sample = host(Bt[:, :8])
     assert relerr(host(Xf[:, :8]), O.packed_solve(Uo, sample.copy())) < TOL
