@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the arrowhead hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+Workload at N=1 (config 2 of BASELINE.json): 1D Helmholtz -Delta+M, ContinuousPolynomial{1},
+m=1024 elements, p=40 blocks (n=40961 unknowns), 4096 synthetic right-hand sides; one "step" is one
+ReverseCholesky solve X <- S^{-1} X of the whole 1.34 GB panel (one launch of the fused kernel).
+N>1: every rank solves its own 4096-column panel (columns are independent: weak scaling, no
+collective on the data path).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(basis="c1", m=1024, N=40, nrhs=4096)
+METRIC = "arrowhead_solve_unknowns_rhs_per_s"
+UNIT = "unknown*RHS/s"
+BYTES_PER_UNIT = 16.0   # one read + one write of X per unknown*RHS
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst, of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_problem():
+    from oracle import arrowhead_oracle as O
+    from oracle import c_oracle as CO
+    m, N = CFG["m"], CFG["N"]
+    h = 2.0 / m
+    S = O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.C1, m, N, h), 1.0, O.assemble_mass(O.C1, m, N, h))
+    U = CO.revchol(S)
+    return O, CO, U
+
+
+def cpu_rate(CO, U, ncols, reps=1):
+    """unknown*RHS/s of the C/OpenMP restatement of the reference algorithm on `ncols` columns."""
+    n = U.n
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.standard_normal((n, ncols)))
+    best = None
+    for _ in range(reps):
+        Y = X.copy(order="F")
+        t0 = time.perf_counter()
+        CO.solve(U, Y)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n * ncols / best, best
+
+
+def cpu_baseline_sample():
+    O, CO, U = oracle_problem()
+    cpu_rate(CO, U, 32)                                   # warm up threads / page in
+    r, dt = cpu_rate(CO, U, 128)
+    ncols = int(min(4096, max(128, 12.0 * r / U.n)))     # ~12 s of CPU work
+    r, dt = cpu_rate(CO, U, ncols)
+    return {"value": r, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
+            "sample": f"{ncols} of {CFG['nrhs']} columns of the same workload, C/OpenMP restatement of src/arrowhead.jl:425-486 (oracle/pop_oracle.c), {dt:.2f} s"}
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's own CPU algorithm (its C restatement; Julia is absent) on the
+    box's host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    O, CO, U = oracle_problem()
+    cpu_rate(CO, U, 32)
+    r, _ = cpu_rate(CO, U, 64)
+    budget = 60.0 / max(1, args.steps + args.warmup)      # keep the whole run around a minute
+    ncols = int(min(CFG["nrhs"], max(64, budget * r / U.n)))
+    for _ in range(args.warmup):
+        cpu_rate(CO, U, ncols)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_rate(CO, U, ncols)
+        t += dt
+    value = U.n * ncols * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
+                             "sample": f"{ncols} of {CFG['nrhs']} columns per step; C/OpenMP restatement of the reference algorithm (Julia not installed)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    n = CFG["m"] + 1 + CFG["m"] * (CFG["N"] - 1)
+    return {"workload": "BASELINE config 2: 1D Helmholtz -Delta+M, ContinuousPolynomial{1}, m=1024, p=40 (n=40961), 4096 RHS columns per GPU, ReverseCholesky solve F\\X",
+            "n": n, "nrhs_per_gpu": CFG["nrhs"], "panel_bytes": n * CFG["nrhs"] * 8,
+            "l2": "panel (1.34 GB) is 10x larger than L2; it is also rewritten from a pristine copy between timed steps",
+            "timing": "CUDA events around each step on the launching stream, summed over K steps; max over ranks"}
+
+
+def adi_case(P, torch, dist, rank, world, dev):
+    """BASELINE config 4: 2D ADI Poisson, Dirichlet, m=128, p=64 (n=8191), J from tol=1e-15."""
+    m, N = 128, 64
+    Q = P.DirichletPolynomial(np.linspace(-1, 1, m + 1))
+    KR = P.Block.oneto(N)
+    M = P.grammatrix(Q)[KR, KR]
+    K = -P.weaklaplacian(Q)[KR, KR]
+    n = M.n
+    b = 4 / np.pi ** 2 * (1 + 1e-9)
+    a = 3.1e-10                      # 1/lambda_max(K,M) for this mesh (gamma ~ 3.1e9, J = 90)
+    J = P.adi_num_iterations(a, b, -b, -a, 1e-15)
+    lo, hi = P.shard_bounds(n, world)[rank]
+    w = hi - lo
+    ld = (n + 1) & ~1
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    F = torch.randn((w, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
+    Ft = torch.randn((w, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
+    out = {"workload": "BASELINE config 4: 2D ADI Poisson, DirichletPolynomial m=128, p=64 (n=8191), synthetic F", "n": n, "J": J}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for it in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        if world == 1:
+            P.adi_poisson(M, K, F, a, b, J=J)
+        else:
+            P.adi_poisson_distributed(M, K, F, Ft, a, b, J=J)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    t = torch.tensor([times[-1]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t.item())
+    out["s_per_solve"] = s
+    out["unknown_rhs_per_s"] = 2.0 * J * n * n / s
+    out["hbm_gbs_per_gpu_algorithmic"] = 48.0 * n * n * J / world / s / 1e9
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-adi", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pop_b200 as P
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    m, N, nrhs = CFG["m"], CFG["N"], CFG["nrhs"]
+    C = P.ContinuousPolynomial(1, np.linspace(-1, 1, m + 1))
+    KR = P.Block.oneto(N)
+    S = (-P.weaklaplacian(C) + P.grammatrix(C))[KR, KR]
+    F = P.reversecholesky(S)
+    n = S.n
+    ld = (n + 1) & ~1
+    g = torch.Generator(device=dev).manual_seed(rank)
+    B = torch.randn((nrhs, ld), generator=g, dtype=torch.float64, device=dev)     # pristine right-hand sides
+    Xbuf = torch.empty_like(B)
+    X = Xbuf.t()[:n]
+    ctx = F.ctx
+
+    def step(timed_events=None):
+        Xbuf.copy_(B)                                    # untimed restore (also sweeps L2)
+        if timed_events is not None:
+            timed_events[0].record()
+        P.ldiv(F, X, overwrite=True)
+        if timed_events is not None:
+            timed_events[1].record()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # parity spot check against the oracle on a few columns of the real panel (not timed)
+    if rank == 0:
+        from oracle import arrowhead_oracle as O
+        h = 2.0 / m
+        Uo = O.packed_revchol(O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.C1, m, N, h), 1.0, O.assemble_mass(O.C1, m, N, h)))
+        want = O.packed_solve(Uo, B[:4, :n].t().cpu().numpy().copy())
+        got = X[:, :4].cpu().numpy()
+        parity = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        assert parity < 1e-12, f"parity check failed: {parity}"
+    else:
+        parity = None
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        step(evs[i])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    units = float(n) * nrhs * args.steps * world
+    value = units / (t_ms * 1e-3)
+
+    # end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside)
+    e2e = None
+    if not args.no_e2e:
+        ksteps = min(args.steps, 5)
+        hB = torch.randn((nrhs, n), dtype=torch.float64).pin_memory()
+        hX = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
+        Xh = hX.numpy().T                                 # Fortran-ordered (n x nrhs) view
+        hX.copy_(hB)
+        P.ldiv(F, Xh, overwrite=True)                     # warm-up
+        te = 0.0
+        for _ in range(ksteps):
+            hX.copy_(hB)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            P.ldiv(F, Xh, overwrite=True)                 # pop_solve_host: returns after the D2H copy
+            te += time.perf_counter() - t0
+        tte = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tte, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(n) * nrhs * ksteps * world / float(tte.item()), "unit": UNIT, "h2d_bytes_per_step": n * nrhs * 8,
+               "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps, "api": "pop_solve_host (ldiv(F, numpy array)), pinned host panel, chunked H2D/compute/D2H overlap"}
+        del hB, hX
+
+    adi = None
+    if not args.no_adi:
+        try:
+            adi = adi_case(P, torch, dist, rank, world, dev)
+        except Exception as ex:  # keep the headline line even if the secondary case fails
+            adi = {"error": f"{type(ex).__name__}: {ex}"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_kernel = t_ms / args.steps
+        achieved = BYTES_PER_UNIT * n * nrhs / (ms_kernel * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "k_fused_solve<2,false>", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
+                "parity_rel_err_vs_oracle": parity, "adi_poisson": adi}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
