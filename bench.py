@@ -251,12 +251,18 @@ def main():
         from oracle import arrowhead_oracle as O
         h = 2.0 / m
         Uo = O.packed_revchol(O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.C1, m, N, h), 1.0, O.assemble_mass(O.C1, m, N, h)))
-        want = O.packed_solve(Uo, B[:4, :n].t().cpu().numpy().copy())
+        sample = np.asfortranarray(B[:4, :n].t().cpu().numpy())
+        want = O.packed_solve(Uo, sample.copy())
         got = X[:, :4].cpu().numpy()
         parity = float(np.linalg.norm(got - want) / np.linalg.norm(want))
-        assert parity < 1e-12, f"parity check failed: {parity}"
+        # noise floor of this shape: NumPy vs C restatement of the same algorithm (1.4e-12 at n=40961)
+        from oracle import c_oracle as CO
+        So = O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.C1, m, N, h), 1.0, O.assemble_mass(O.C1, m, N, h))
+        xc = CO.solve(CO.revchol(So), sample.copy(order="F"))
+        parity_floor = float(np.linalg.norm(xc - want) / np.linalg.norm(want))
+        assert parity < max(1e-12, 3 * parity_floor), f"parity check failed: {parity} (floor {parity_floor})"
     else:
-        parity = None
+        parity = parity_floor = None
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -322,7 +328,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "kernel": "k_fused_solve<2,false>", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
-                "parity_rel_err_vs_oracle": parity, "adi_poisson": adi}
+                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         else:

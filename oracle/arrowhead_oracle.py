@@ -579,7 +579,7 @@ def packed_revchol(P: Packed) -> Packed:
         s = Ad[i] - (Au[i] ** 2 if i < nh - 1 else 0.0)
         if not s > 0:
             raise np.linalg.LinAlgError("non-positive pivot in hat block")
-        Ad[i] = math.sqrt(s)
+        Ad[i] = np.sqrt(s)              # np.sqrt keeps the dtype (extended-precision runs of the oracle)
         if i > 0:
             Au[i - 1] = Au[i - 1] / Ad[i]
     return Packed(m, nh, q, 0, u, Ad, Au, np.zeros_like(Au), B, np.zeros((0, 3, m)), Dd)
@@ -631,9 +631,15 @@ def packed_trsm(U: Packed, X, upper=True, unit=False):
     return X
 
 
+def packed_astype(P: Packed, dtype) -> Packed:
+    """Same arrowhead in another floating type (np.longdouble gives the noise-floor reference)."""
+    f = lambda a: np.asarray(a).astype(dtype)
+    return Packed(P.m, P.nh, P.q, P.lD, P.uD, f(P.Ad), f(P.Au), f(P.Al), f(P.B), f(P.C), f(P.D))
+
+
 def packed_transpose(P: Packed) -> Packed:
     q, m = P.q, P.m
-    D = np.zeros((P.lD + P.uD + 1, q, m))
+    D = np.zeros((P.lD + P.uD + 1, q, m), dtype=P.D.dtype)
     # new lD = old uD ; D'[j, j+d] = D[j+d, j] -> old band -d at row j+d
     for d in range(-P.uD, P.lD + 1):
         src = P.D[P.lD - d]          # old band -d : D[r, r-d]
