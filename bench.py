@@ -39,7 +39,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix=".csv")
@@ -50,7 +50,10 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock of the samples taken between wall-clock times t0 and t1 (all samples of
+        the run -- warm-up included -- when the window is shorter than the sampling period)."""
+        import datetime
         if self.p is not None:
             self.p.terminate()
             try:
@@ -58,26 +61,32 @@ class ClockSampler:
             except Exception:
                 self.p.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 c = [x.strip() for x in line.split(",")]
                 if len(c) < 9:
                     continue
                 try:
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(c[1]), float(c[2]), [v.lower().startswith("active") for v in c[5:9]]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        window = "timed region" if len(inside) >= 3 else "warm-up + timed region"
+        use = inside if len(inside) >= 3 else rows
+        reasons = set()
+        for r in use:
+            for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if on:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)), "reasons": sorted(reasons),
+                "samples": len(use), "window": window}
 
 
 def oracle_problem():
@@ -243,6 +252,8 @@ def main():
         if timed_events is not None:
             timed_events[1].record()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -265,11 +276,11 @@ def main():
         parity = parity_floor = None
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = ctx.launches
+    t_epoch0 = time.time()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         step(evs[i])
@@ -278,7 +289,7 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_epoch0, time.time()) if sampler else None
     t_ms = sum(a.elapsed_time(b) for a, b in evs)
     tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
     if world > 1:

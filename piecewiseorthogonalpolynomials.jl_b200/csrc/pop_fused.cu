@@ -77,6 +77,9 @@ struct Smem {
     double *hloc;   // [mloc + 2]    hats k0-1 .. k1 seen by this CTA
     double *part;   // [mloc + 2]    partial sums for hats k0-1 .. k1
     double *tab;    // [(1 + nd) * q] rd, W1, W2 of the shared block
+    double *hrd;    // [nh] reciprocal hat pivots
+    double *hoff;   // [nh] hat super-diagonal of U (0 in the last slot)
+    double *wagg;   // [128] warp aggregates of the block-wide hat scan (2 directions x (t, P) x 32)
     uint64_t *bar;
 };
 
@@ -88,12 +91,15 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *base, int q, int pitch
     s.hloc = p; p += (mloc + 3) & ~1;
     s.part = p; p += (mloc + 3) & ~1;
     s.tab = p; p += tabs ? (((size_t)(1 + nd) * q + 1) & ~(size_t)1) : 0;
+    s.hrd = p; p += (nh + 1) & ~1;
+    s.hoff = p; p += (nh + 1) & ~1;
+    s.wagg = p; p += 128;
     s.bar = reinterpret_cast<uint64_t *>(p);
     return s;
 }
 
 static size_t fused_smem_bytes(int q, int pitch, int nh, int mloc, int nd, bool tabs) {
-    size_t d = (size_t)q * pitch + ((nh + 3) & ~1) + 2 * ((mloc + 3) & ~1);
+    size_t d = (size_t)q * pitch + ((nh + 3) & ~1) + 2 * ((mloc + 3) & ~1) + 2 * ((nh + 1) & ~1) + 128;
     if (tabs) {
         size_t t = (size_t)(1 + nd) * q;
         d += t + (t & 1);
@@ -130,6 +136,10 @@ __global__ void __launch_bounds__(512) k_fused_solve(const FusedParams P) {
 #pragma unroll
             for (int d = 1; d <= ND; ++d) s.tab[d * q + j] = (d <= tv.nd) ? tv.W[d - 1][j] : 0.0;
         }
+    }
+    for (int i = tid; i < nh; i += nthr) {
+        s.hrd[i] = tv.rdA[i];
+        s.hoff[i] = i < nh - 1 ? tv.offA[i] : 0.0;
     }
     if (cs > 1) cluster.sync(); else __syncthreads();
 
@@ -222,42 +232,56 @@ __global__ void __launch_bounds__(512) k_fused_solve(const FusedParams P) {
                 s.H[i] = v;
             }
             __syncthreads();
-            if (warp == 0) {
-                // h[i] = (H[i] - offA[i] h[i+1]) rd[i] downwards, then upwards with offA[i-1]
-                const int sg = (nh + 31) / 32;
-                const int lo = min(lane * sg, nh), hi = min(lo + sg, nh);
+            // Block-wide segmented affine scan: thread t owns hats [t*sg, (t+1)*sg).
+            //   down: h[i] = (H[i] - off[i] h[i+1]) rd[i]     (U solve,   src/arrowhead.jl:453)
+            //   up  : h[i] = (H[i] - off[i-1] h[i-1]) rd[i]   (U' solve,  src/arrowhead.jl:472)
+            // pass 1 reduces a segment to an affine map of its incoming value, warp shuffles and a
+            // short loop over the warp aggregates compose the maps, pass 2 is the reference
+            // recurrence itself with the exact incoming value.  Factor entries come from smem.
+            const int sg = (nh + nthr - 1) / nthr;
+            const int lo = min(tid * sg, nh), hi = min(lo + sg, nh);
+            const int nw = nthr >> 5;
 #pragma unroll
-                for (int dir = 0; dir < 2; ++dir) {
-                    const bool bw = dir == 0;
-                    double t = 0.0, Pm = 1.0;
-                    for (int ii = lo; ii < hi; ++ii) {
-                        const int i = bw ? (hi - 1 - (ii - lo)) : ii;
-                        const bool has = bw ? (i < nh - 1) : (i > 0);
-                        const double off = has ? tv.offA[bw ? i : i - 1] : 0.0;
-                        const double rd = tv.rdA[i];
-                        t = (s.H[i] - off * t) * rd;
-                        Pm = -off * rd * Pm;
-                    }
+            for (int dir = 0; dir < 2; ++dir) {
+                const bool bw = dir == 0;
+                double t = 0.0, Pm = 1.0;
+                for (int ii = lo; ii < hi; ++ii) {
+                    const int i = bw ? (hi - 1 - (ii - lo)) : ii;
+                    const double off = bw ? s.hoff[i] : (i > 0 ? s.hoff[i - 1] : 0.0);
+                    const double rd = s.hrd[i];
+                    t = (s.H[i] - off * t) * rd;
+                    Pm = -off * rd * Pm;
+                }
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double t2 = bw ? __shfl_down_sync(FULL, t, o) : __shfl_up_sync(FULL, t, o);
-                        const double P2 = bw ? __shfl_down_sync(FULL, Pm, o) : __shfl_up_sync(FULL, Pm, o);
-                        const bool ok = bw ? (lane + o < 32) : (lane - o >= 0);
-                        if (ok) {
-                            t = t + Pm * t2;
-                            Pm = Pm * P2;
-                        }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t2 = bw ? __shfl_down_sync(FULL, t, o) : __shfl_up_sync(FULL, t, o);
+                    const double P2 = bw ? __shfl_down_sync(FULL, Pm, o) : __shfl_up_sync(FULL, Pm, o);
+                    const bool ok = bw ? (lane + o < 32) : (lane - o >= 0);
+                    if (ok) {
+                        t = t + Pm * t2;
+                        Pm = Pm * P2;
                     }
-                    double hin = bw ? __shfl_down_sync(FULL, t, 1) : __shfl_up_sync(FULL, t, 1);
-                    if (bw ? (lane == 31) : (lane == 0)) hin = 0.0;
-                    for (int ii = lo; ii < hi; ++ii) {
-                        const int i = bw ? (hi - 1 - (ii - lo)) : ii;
-                        const bool has = bw ? (i < nh - 1) : (i > 0);
-                        const double off = has ? tv.offA[bw ? i : i - 1] : 0.0;
-                        hin = (s.H[i] - off * hin) * tv.rdA[i];
-                        s.H[i] = hin;
-                    }
-                    __syncwarp();
+                }
+                // lane now holds the composite of lanes lane..31 (down) / 0..lane (up)
+                if (lane == (bw ? 0 : 31)) {
+                    s.wagg[dir * 64 + warp] = t;
+                    s.wagg[dir * 64 + 32 + warp] = Pm;
+                }
+                __syncthreads();
+                double G = 0.0;   // value entering this warp from the warps after (down) / before (up) it
+                if (bw) {
+                    for (int w2 = nw - 1; w2 > warp; --w2) G = s.wagg[w2] + s.wagg[32 + w2] * G;
+                } else {
+                    for (int w2 = 0; w2 < warp; ++w2) G = s.wagg[64 + w2] + s.wagg[96 + w2] * G;
+                }
+                const double tn = bw ? __shfl_down_sync(FULL, t, 1) : __shfl_up_sync(FULL, t, 1);
+                const double Pn = bw ? __shfl_down_sync(FULL, Pm, 1) : __shfl_up_sync(FULL, Pm, 1);
+                double hin = (bw ? (lane == 31) : (lane == 0)) ? G : tn + Pn * G;
+                for (int ii = lo; ii < hi; ++ii) {
+                    const int i = bw ? (hi - 1 - (ii - lo)) : ii;
+                    const double off = bw ? s.hoff[i] : (i > 0 ? s.hoff[i - 1] : 0.0);
+                    hin = (s.H[i] - off * hin) * s.hrd[i];
+                    s.H[i] = hin;
                 }
             }
         }
