@@ -171,6 +171,7 @@ int pop_alloc_handles(pop_ctx *ctx, const pop_desc &d, int mD, int count, pop_ar
         h->has_recip = false;
         h->is_factor = false;
         h->bmask = 0;
+        h->band1_zero = false;
         carve(h, (double *)slab->dptr + (size_t)i * std::max<size_t>(s.total, 2));
         out[i] = h;
     }
@@ -328,6 +329,7 @@ extern "C" int pop_arrowhead_copy(pop_ctx *ctx, const pop_arrowhead *A, pop_arro
     h->has_recip = A->has_recip;
     h->is_factor = A->is_factor;
     h->bmask = A->bmask;
+    h->band1_zero = A->band1_zero;
     *out = h;
     return POP_OK;
 }
@@ -649,7 +651,7 @@ extern "C" int pop_revchol_shifted_batch(pop_ctx *ctx, const pop_arrowhead *K, c
     Mu.p.D = M->p.D + (size_t)M->d.lD * M->d.q * M->mD; Mu.d.lD = 0;
     int done = 0, first_bad = 0;
     while (done < nshift) {
-        int cnt = std::min(nshift - done, 4096);
+        int cnt = std::min(nshift - done, 2048);
         int rc = pop_launch_axpby_batch(ctx, &Ku, &Mu, alpha + done, sigma + done, cnt, U + done);
         if (rc) return rc;
         rc = check_factor_structure(U[done]);

@@ -13,7 +13,7 @@ struct FactorBatch {
 
 // Per-element banded reverse Cholesky of D_k (the `Threads.@threads for B in A.D` loop, :277-279).
 // thread <-> element k (or the single shared block when mD == 1); blockIdx.y <-> shift.
-__global__ void k_factor_D(const FactorBatch *batch, int *info, int m, int nh, int q, int uD, int mD) {
+__global__ void k_factor_D(const FactorBatch *batch, int *info, int *band1, int m, int nh, int q, int uD, int mD) {
     const int s = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= mD) return;
@@ -45,6 +45,11 @@ __global__ void k_factor_D(const FactorBatch *batch, int *info, int m, int nh, i
                 acc -= Dd[(c - i) * plane + (size_t)i * mD + k] * Dd[(c - j) * plane + (size_t)j * mD + k];
             Dd[d * plane + (size_t)i * mD + k] = acc / r;
         }
+    }
+    if (uD >= 1) {   // structurally decoupled even/odd chains (mass + Laplacian): remember it
+        bool nz = false;
+        for (int j = 0; j + 1 < q; ++j) nz |= Dd[plane + (size_t)j * mD + k] != 0.0;
+        if (nz) band1[s] = 1;
     }
 }
 
@@ -129,22 +134,26 @@ int pop_launch_factor(pop_ctx *ctx, pop_arrowhead **S, int count, int32_t *info_
     int rc = pop_ctx_scratch(ctx, sizeof(FactorBatch) * count, &dscr);
     if (rc) return rc;
     POP_CUDA(cudaMemcpyAsync(dscr, host.data(), sizeof(FactorBatch) * count, cudaMemcpyHostToDevice, ctx->stream));
+    POP_REQUIRE(count <= 2048, POP_ERR_ARG, "factor batch size %d out of range", count);
     k_fill_int<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_info, count, INT_MAX);
-    ctx->launches++;
+    k_fill_int<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_info + 2048, count, 0);
+    ctx->launches += 2;
     const int nb = d.nB < d.q ? d.nB : d.q;
     if (d.q > 0) {
         dim3 grid((mD + 127) / 128, count);
-        k_factor_D<<<grid, 128, 0, ctx->stream>>>((const FactorBatch *)dscr, ctx->d_info, d.m, d.nh, d.q, d.uD, mD);
+        k_factor_D<<<grid, 128, 0, ctx->stream>>>((const FactorBatch *)dscr, ctx->d_info, ctx->d_info + 2048, d.m, d.nh, d.q, d.uD, mD);
         ctx->launches++;
     }
     k_factor_hat<<<count, 256, 0, ctx->stream>>>((const FactorBatch *)dscr, ctx->d_info, d.m, d.nh, d.q, nb, d.uD, mD);
     ctx->launches++;
     POP_CUDA(cudaGetLastError());
     POP_CUDA(cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    POP_CUDA(cudaMemcpyAsync(ctx->h_info + 2048, ctx->d_info + 2048, sizeof(int) * count, cudaMemcpyDeviceToHost, ctx->stream));
     POP_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < count; ++i) {
         S[i]->has_recip = true;
         S[i]->is_factor = true;
+        S[i]->band1_zero = d.uD >= 1 && ctx->h_info[2048 + i] == 0;
         if (info_out) info_out[i] = ctx->h_info[i] == INT_MAX ? 0 : ctx->h_info[i];
     }
     return POP_OK;

@@ -52,6 +52,7 @@ struct pop_arrowhead {
     bool has_recip;   // rdA/rdD are up to date
     bool is_factor;   // produced by reverse Cholesky (upper data hold U)
     int bmask;        // bit t set: slot t of some B block may be non-zero
+    bool band1_zero;  // factor only: the first super-diagonal of every D block is identically zero
     int64_t n() const { return (int64_t)d.nh + (int64_t)d.m * d.q; }
 };
 
