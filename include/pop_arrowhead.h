@@ -60,7 +60,9 @@ enum { POP_BASIS_C1 = 0, POP_BASIS_DIRICHLET = 1 }; /* ContinuousPolynomial{1} /
 enum { POP_LEFT = 0, POP_RIGHT = 1 };               /* A*X, A\X  vs  X*A, X/A */
 enum { POP_GENERAL = 0, POP_SYM_UPPER = 1 };        /* Symmetric(P) reads upper data, src/arrowhead.jl:154-167 */
 enum { POP_UPPER = 0, POP_LOWER = 1 };
-enum { POP_SOLVE_AUTO = 0, POP_SOLVE_STAGED = 1, POP_SOLVE_FUSED = 2 }; /* kernel choice for pop_solve */
+enum { POP_SOLVE_AUTO = 0, POP_SOLVE_STAGED = 1, POP_SOLVE_FUSED = 2,
+       POP_SOLVE_FUSED_SMEM = 3 }; /* kernel choice for pop_solve: FUSED = best single-pass kernel,
+                                       FUSED_SMEM = the shared-memory-resident variant */
 
 typedef struct pop_ctx pop_ctx;
 typedef struct pop_arrowhead pop_arrowhead; /* device-resident packed arrowhead or factor */

@@ -3,7 +3,7 @@
 All arithmetic runs in libpop_arrowhead.so (hand-written CUDA for sm_100a, C ABI in
 include/pop_arrowhead.h).  There is no CPU fallback."""
 from ._lib import (Context, DimensionMismatch, PopError, PosDefException, StructureError, build, default_context,
-                   SOLVE_AUTO, SOLVE_FUSED, SOLVE_STAGED, LIB_PATH, EXPORTED)
+                   SOLVE_AUTO, SOLVE_FUSED, SOLVE_FUSED_SMEM, SOLVE_STAGED, LIB_PATH, EXPORTED)
 from .arrowhead import (BBBArrowheadMatrix, LowerTriangular, ReverseCholesky, Symmetric, UnitLowerTriangular,
                         UnitUpperTriangular, UpperTriangular, ldiv, mul, rdiv, reversecholesky, reversecholesky_inplace,
                         reversecholesky_shifted)

@@ -15,7 +15,7 @@ BASIS_C1, BASIS_DIRICHLET = 0, 1
 LEFT, RIGHT = 0, 1
 GENERAL, SYM_UPPER = 0, 1
 UPPER, LOWER = 0, 1
-SOLVE_AUTO, SOLVE_STAGED, SOLVE_FUSED = 0, 1, 2
+SOLVE_AUTO, SOLVE_STAGED, SOLVE_FUSED, SOLVE_FUSED_SMEM = 0, 1, 2, 3
 
 
 class PopError(RuntimeError):

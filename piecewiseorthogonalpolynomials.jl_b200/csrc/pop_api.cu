@@ -259,6 +259,11 @@ extern "C" int pop_arrowhead_upload(pop_ctx *ctx, const pop_desc *desc, const do
         for (int t = 0; t < 3; ++t)
             for (int k = 0; k < m; ++k)
                 if (B[((size_t)b * 3 + t) * m + k] != 0.0) h->bmask |= 1 << t;
+    h->band1_zero = true;
+    for (int dd = -1; dd <= 1; dd += 2)
+        if (dd >= -desc->lD && dd <= desc->uD)
+            for (size_t r = 0; r < (size_t)q * mD_in; ++r)
+                if (D[(size_t)(desc->lD + dd) * q * mD_in + r] != 0.0) h->band1_zero = false;
     cudaError_t e = cudaMemcpyAsync(h->slab->dptr, stage.data(), s.total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -483,8 +488,8 @@ extern "C" int pop_assemble(pop_ctx *ctx, int basis, int m, int N, double h, pop
     k_assemble<<<(nthr + 255) / 256, 256, 0, ctx->stream>>>(pm, pl, basis, m, nh, q, h);
     LAUNCH_COUNT(ctx);
     POP_CUDA(cudaGetLastError());
-    if (mass) { hm->bmask = basis == POP_BASIS_C1 ? 6 : 3; *mass = hm; }
-    if (lap) *lap = hl;
+    if (mass) { hm->bmask = basis == POP_BASIS_C1 ? 6 : 3; hm->band1_zero = true; *mass = hm; }
+    if (lap) { hl->band1_zero = true; *lap = hl; }
     return POP_OK;
 }
 
@@ -536,6 +541,10 @@ int pop_launch_axpby_batch(pop_ctx *ctx, const pop_arrowhead *X, const pop_arrow
     d.uniform = mD == 1;
     int rc = pop_alloc_handles(ctx, d, mD, count, out);
     if (rc) return rc;
+    for (int i = 0; i < count; ++i) {
+        out[i]->band1_zero = X->band1_zero && Y->band1_zero;
+        out[i]->bmask = X->bmask | Y->bmask;
+    }
     // stage [alpha | beta | BatchPtrs] in scratch
     size_t bytes = (size_t)count * (2 * sizeof(double) + sizeof(BatchPtrs));
     std::vector<char> host(bytes);

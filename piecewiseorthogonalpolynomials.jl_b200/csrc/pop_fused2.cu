@@ -1,0 +1,212 @@
+// Fused ReverseCholesky solve, register-resident ("v2"):  X <- U^{-T} U^{-1} X, optionally followed
+// by the ADI product  R <- T X + gamma F, in ONE pass over HBM (16 B per unknown, 24 B with F).
+//
+// Replaces, for matrix right-hand sides, the column loop over
+//   materialize!(::MatLdivVec{TriangularLayout{'U'}}) (src/arrowhead.jl:425-457) and
+//   materialize!(::MatLdivVec{TriangularLayout{'L'}}) (src/arrowhead.jl:458-486),
+// and with the product one half step of examples/adi_poisson.jl:54-55.
+//
+// Mapping (sm_100a):
+//   * a cluster of CS CTAs owns one column at a time; CTA r owns elements [k0,k1).  One CONSUMER
+//     thread per element (two when the even/odd degree chains are split, NPAR = 2) keeps the whole
+//     degree chain of its element in REGISTERS between the backward and the forward sweep: the
+//     register file is the on-chip home of the column (src/arrowhead.jl:439-441 and :480-482 run
+//     back to back without touching memory).
+//   * the columns stream into a shared-memory ring of row chunks by TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), in the order the backward sweep consumes them.
+//     Once a column sits in registers (first block barrier of the column) warp 0 refills the
+//     whole ring, so the loads of column c+1 (and the start of c+2) overlap the hat solve, the
+//     forward sweep and the stores of column c.
+//   * hats: every CTA reduces its elements' couplings to per-hat partial sums, sends them to its
+//     peers with one shared->peer-shared bulk copy each (complete_tx on the peer's mbarrier: no
+//     cluster barrier in the steady state) and then solves the bidiagonal hat systems redundantly
+//     with a block-wide segmented affine scan (src/arrowhead.jl:449-453, :472-477).
+//   * the forward sweep streams x (or T x + gamma F) to global memory straight from registers;
+//     lanes run over elements, so every warp store is one run of consecutive doubles.
+#include <cstdlib>
+
+#include "pop_fused2.cuh"
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+struct F2Plan {
+    bool ok;
+    int rows, npar, variant;
+    int threads, occ;
+    size_t smem;
+    f2_kernel_t kern;
+    F2Params p;
+};
+
+static f2_kernel_t f2_kernel(int rows, int npar, int variant, bool mul) {
+    switch (rows) {
+        case 8: return f2_kernel_r8(npar, variant, mul);
+        case 16: return f2_kernel_r16(npar, variant, mul);
+        case 24: return f2_kernel_r24(npar, variant, mul);
+        case 32: return f2_kernel_r32(npar, variant, mul);
+        case 40: return f2_kernel_r40(npar, variant, mul);
+        case 48: return f2_kernel_r48(npar, variant, mul);
+        case 56: return f2_kernel_r56(npar, variant, mul);
+        case 64: return f2_kernel_r64(npar, variant, mul);
+    }
+    return nullptr;
+}
+
+static inline int ev2i(int x) { return (x + 1) & ~1; }
+
+static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T) {
+    F2Plan pl = {};
+    const pop_desc &d = U->d;
+    if (!U->is_factor || U->mD != 1 || d.uD > 2 || d.q < 1) return pl;
+    if (std::min(d.nB, d.q) > F2_NBMAX) return pl;
+    if (T && (T->mD != 1 || T->d.uD > 2 || std::min(T->d.nB, T->d.q) > F2_NBMAX)) return pl;
+    const int nd = d.uD;
+    const bool skip1 = nd == 2 && U->band1_zero;
+    const int tu = T ? T->d.uD : 0;
+    const bool t_even = !T || tu == 0 || (tu == 2 && T->band1_zero);   // the product never couples j and j+1
+    if (nd == 0 && tu == 0) pl.variant = 0;
+    else if ((nd == 0 || skip1) && t_even) pl.variant = 1;
+    else pl.variant = 2;
+    const int q = d.q;
+    if (q <= 64) {
+        pl.npar = 1;
+        pl.rows = ((q + F2_CLASS - 1) / F2_CLASS) * F2_CLASS;
+    } else if (q <= 128 && !T && (nd == 0 || skip1)) {
+        pl.npar = 2;                                         // even / odd degree chains on two threads
+        pl.rows = ((q + 2 * F2_CLASS - 1) / (2 * F2_CLASS)) * F2_CLASS;
+    } else {
+        return pl;
+    }
+    const int jmax = pl.rows * pl.npar;
+    const int maxthreads = f2_tmax(pl.rows);
+    int force_cs = 0, force_occ = 0, force_slots = 0;
+    if (const char *e = getenv("POP_F2_CS")) force_cs = atoi(e);
+    if (const char *e = getenv("POP_F2_OCC")) force_occ = atoi(e);
+    if (const char *e = getenv("POP_F2_SLOTS")) force_slots = atoi(e);
+    const size_t limit = (size_t)ctx->max_smem_optin;
+    pl.kern = f2_kernel(pl.rows, pl.npar, pl.variant, T != nullptr);
+    if (!pl.kern) return pl;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, pl.kern) != cudaSuccess) {
+        cudaGetLastError();
+        return pl;
+    }
+    for (int cs = 1; cs <= 8; cs *= 2) {
+        if (T && cs > 1) break;
+        if (force_cs && cs != force_cs) continue;
+        const int mloc = (d.m + cs - 1) / cs;
+        if ((int64_t)(cs - 1) * mloc >= d.m) continue;
+        const int ncE = ((mloc + 31) / 32) * 32;
+        const int threads = ncE * pl.npar;
+        if (threads > maxthreads) continue;
+        F2Params &p = pl.p;
+        p.cs = cs; p.mloc = mloc; p.ncE = ncE;
+        p.contiguous = cs == 1 ? 1 : 0;
+        p.rp = cs == 1 ? d.m : ev2i(mloc + 2);
+        p.slot_stride = ev2i(F2_G * p.rp + 2);
+        p.nch = jmax / F2_G;
+        p.pstride = ev2i(mloc + 2) + 2;
+        p.hstride = ev2i(d.nh) + 2;
+        const size_t slot_bytes = (size_t)p.slot_stride * 8;
+        const size_t tail = 512;
+        // registers decide how many CTAs an SM can hold; shared memory is then split between them
+        const int occ_regs = (int)(65536 / ((size_t)threads * ((fa.numRegs + 7) & ~7)));
+        if (occ_regs < 1) continue;
+        bool found = false;
+        for (int occ = std::min(occ_regs, 4); occ >= 1 && !found; --occ) {
+            if (force_occ && occ != force_occ) continue;
+            const size_t budget = std::min(limit, (size_t)(233472 / occ) - 1024);
+            for (int hat_tabs = 1; hat_tabs >= 0 && !found; --hat_tabs) {
+                int o = 0;
+                p.o_tab = o; o += 2 * (jmax + 2);
+                p.o_tab1 = o; o += ev2i(jmax + 2);
+                p.o_tT = o; o += T ? ev2i(3 * (jmax + 2)) : 0;
+                p.o_hrd = o; o += hat_tabs ? ev2i(d.nh) : 0;
+                p.o_hoff = o; o += hat_tabs ? ev2i(d.nh) : 0;
+                p.o_H = o; o += 2 * p.hstride;
+                p.o_ct = o; o += 3 * pl.npar * ncE;
+                p.o_xb = o; o += T ? F2_NBMAX * ncE : 0;
+                p.o_part = o; o += 2 * cs * p.pstride;
+                p.o_wagg = o; o += 128;
+                o = (o + 15) & ~15;
+                p.o_ring = o;
+                p.hat_tabs = hat_tabs;
+                const size_t fixed = F2_BAR_BYTES + (size_t)o * 8;
+                if (budget < fixed + tail + slot_bytes * (size_t)p.nch) continue;
+                int slots = (int)((budget - fixed - tail) / slot_bytes);
+                slots = std::min(slots, std::min(F2_MAXSLOTS, 2 * p.nch));
+                // prefer the highest occupancy whose ring still holds a whole column plus a chunk
+                if (slots < p.nch + 1 && occ > 1 && !force_occ) continue;
+                if (force_slots >= p.nch && force_slots <= slots) slots = force_slots;
+                p.nslots = slots;
+                pl.occ = occ;
+                pl.threads = threads;
+                pl.smem = fixed + tail + slot_bytes * (size_t)slots;
+                found = true;
+            }
+        }
+        if (!found) continue;
+        pl.ok = true;
+        break;
+    }
+    return pl;
+}
+
+bool pop_fused2_supported(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, int64_t ldx, const double *X) {
+    if (const char *e = getenv("POP_DISABLE_FUSED2"))
+        if (atoi(e)) return false;
+    if ((ldx & 1) || ((uintptr_t)X & 15)) return false;   // TMA bulk copies need 16 B aligned column starts
+    return plan_f2(ctx, U, T).ok;
+}
+
+int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *F, int64_t ldf,
+                            double *X, int64_t ldx, int64_t nrhs) {
+    F2Plan pl = plan_f2(ctx, U, T);
+    POP_REQUIRE(pl.ok, POP_ERR_DIM, "fused solve v2: shape not supported (n=%lld, q=%d, uD=%d)", (long long)U->n(), U->d.q, U->d.uD);
+    POP_REQUIRE(!(ldx & 1) && !((uintptr_t)X & 15), POP_ERR_DIM, "fused solve v2 needs an even leading dimension and a 16-byte aligned panel");
+    if (nrhs == 0) return POP_OK;
+    const pop_desc &d = U->d;
+    F2Params &p = pl.p;
+    const size_t plane = (size_t)d.q;   // mD == 1
+    p.rdD = U->p.rdD;
+    p.W1 = d.uD >= 1 ? U->p.D + (size_t)(d.lD + 1) * plane : nullptr;
+    p.W2 = d.uD >= 2 ? U->p.D + (size_t)(d.lD + 2) * plane : nullptr;
+    p.Sb = U->p.B;
+    p.rdA = U->p.rdA;
+    p.offA = U->p.Au;
+    p.m = d.m; p.nh = d.nh; p.q = d.q; p.nb = std::min(d.nB, d.q);
+    if (T) {
+        const pop_desc &t = T->d;
+        const size_t tpl = (size_t)t.q;
+        p.Td0 = T->p.D + (size_t)t.lD * tpl;
+        p.Td1 = t.uD >= 1 ? T->p.D + (size_t)(t.lD + 1) * tpl : nullptr;
+        p.Td2 = t.uD >= 2 ? T->p.D + (size_t)(t.lD + 2) * tpl : nullptr;
+        p.Trow = T->p.B;
+        p.TAd = T->p.Ad;
+        p.TAu = T->p.Au;
+        p.nbT = std::min(t.nB, t.q);
+    }
+    p.gamma = gamma;
+    p.F = F ? F : X;
+    p.ldf = F ? ldf : ldx;
+    p.X = X; p.ldx = ldx; p.nrhs = nrhs;
+    POP_CUDA(cudaFuncSetAttribute(pl.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int64_t nclusters = std::min<int64_t>(nrhs, (int64_t)ctx->sm_count * pl.occ / p.cs);
+    if (nclusters < 1) nclusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nclusters * p.cs));
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    POP_CUDA(cudaLaunchKernelEx(&cfg, pl.kern, p));
+    ctx->launches++;
+    return POP_OK;
+}

@@ -1,0 +1,490 @@
+// Kernel template of the register-resident fused solve (see pop_fused2.cu for the design notes).
+// Instantiated per row class in pop_fused2_rNN.cu so the classes compile in parallel.
+#pragma once
+#include "pop_internal.h"
+#include "pop_ptx.cuh"
+
+#define F2_NBMAX 4        // coupling blocks B handled in registers
+#define F2_BAR_BYTES 1152 // 144 mbarrier words at the start of shared memory
+#define F2_MAXSLOTS 32
+#define F2_G 8            // rows per ring chunk
+#define F2_CLASS 8        // a row class covers q in (ROWS*NPAR - F2_CLASS*NPAR, ROWS*NPAR]
+
+struct F2Params {
+    // factor U (upper data; D block shared by all elements)
+    const double *rdD, *W1, *W2;   // [q] reciprocal pivots, first / second super-diagonal (may be null)
+    const double *Sb;              // [nb][3][m] hat <-> bubble coupling
+    const double *rdA, *offA;      // [nh], [nh-1]
+    int m, nh, q, nb;
+    // optional product operator T = Symmetric(upper data), D block shared
+    const double *Td0, *Td1, *Td2; // [q] diagonal, first, second super-diagonal (may be null)
+    const double *Trow;            // [nbT][3][m]
+    const double *TAd, *TAu;       // [nh], [nh-1]
+    int nbT;
+    double gamma;
+    const double *F;
+    int64_t ldf;
+    // panel
+    double *X;
+    int64_t ldx, nrhs;
+    // plan
+    int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, pstride, hstride, hat_tabs;
+    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_part, o_wagg, o_ring;   // offsets in doubles
+};
+
+typedef void (*f2_kernel_t)(const F2Params);
+// variant: 0 -> no D coupling, 1 -> second super-diagonal only (even/odd chains decoupled), 2 -> general (<= 2 bands)
+f2_kernel_t f2_kernel_r8(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r16(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r24(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r32(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r40(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r48(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r56(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r64(int npar, int variant, bool mul);
+// largest block of a row class (registers: the chain of an element lives in 2*ROWS registers)
+__host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : rows <= 48 ? 384 : 256; }
+
+#ifdef __CUDACC__
+// h[i] = (H[i] - off[i] h[i+1]) rd[i], i = nh-1..0 (BW, src/arrowhead.jl:453) or
+// h[i] = (H[i] - off[i-1] h[i-1]) rd[i], i = 0..nh-1 (src/arrowhead.jl:472) as a block-wide segmented
+// affine scan: thread t owns hats [lo,hi).  Pass 1 reduces a segment to an affine map of its incoming
+// value, shuffles compose the maps inside a warp and across the warp aggregates, pass 2 is the
+// reference recurrence itself with the exact incoming value.
+template <bool BW>
+__device__ __forceinline__ void f2_scan_dir(double *H, const double *hrd, const double *hoff, const int lo, const int hi, const int lane,
+                                            const int warp, const int nw, double *wagg) {
+    double t = 0.0, Pm = 1.0;
+    for (int ii = lo; ii < hi; ++ii) {
+        const int i = BW ? (hi - 1 - (ii - lo)) : ii;
+        const double off = BW ? hoff[i] : (i > 0 ? hoff[i - 1] : 0.0);
+        const double rd = hrd[i];
+        t = (H[i] - off * t) * rd;
+        Pm = -off * rd * Pm;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t2 = BW ? __shfl_down_sync(POP_FULL_MASK, t, o) : __shfl_up_sync(POP_FULL_MASK, t, o);
+        const double P2 = BW ? __shfl_down_sync(POP_FULL_MASK, Pm, o) : __shfl_up_sync(POP_FULL_MASK, Pm, o);
+        const bool ok = BW ? (lane + o < 32) : (lane - o >= 0);
+        if (ok) {
+            t = fma(Pm, t2, t);
+            Pm = Pm * P2;
+        }
+    }
+    // lane now holds the composite of lanes lane..31 (BW) / 0..lane (forward)
+    if (lane == (BW ? 0 : 31)) {
+        wagg[warp] = t;
+        wagg[32 + warp] = Pm;
+    }
+    __syncthreads();
+    // compose the warp aggregates (every warp redundantly, by shuffles)
+    double at = lane < nw ? wagg[lane] : 0.0, aP = lane < nw ? wagg[32 + lane] : 1.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t2 = BW ? __shfl_down_sync(POP_FULL_MASK, at, o) : __shfl_up_sync(POP_FULL_MASK, at, o);
+        const double P2 = BW ? __shfl_down_sync(POP_FULL_MASK, aP, o) : __shfl_up_sync(POP_FULL_MASK, aP, o);
+        const bool ok = BW ? (lane + o < 32) : (lane - o >= 0);
+        if (ok) {
+            at = fma(aP, t2, at);
+            aP = aP * P2;
+        }
+    }
+    // value entering this warp: composite of the warps after (BW) / before (forward) it applied to 0
+    const int src = BW ? warp + 1 : warp - 1;
+    double Gin = __shfl_sync(POP_FULL_MASK, at, src & 31);
+    if (BW ? (warp + 1 >= nw || warp + 1 > 31) : (warp == 0)) Gin = 0.0;
+    const double tn = BW ? __shfl_down_sync(POP_FULL_MASK, t, 1) : __shfl_up_sync(POP_FULL_MASK, t, 1);
+    const double Pn = BW ? __shfl_down_sync(POP_FULL_MASK, Pm, 1) : __shfl_up_sync(POP_FULL_MASK, Pm, 1);
+    double hin = (BW ? (lane == 31) : (lane == 0)) ? Gin : fma(Pn, Gin, tn);
+    for (int ii = lo; ii < hi; ++ii) {
+        const int i = BW ? (hi - 1 - (ii - lo)) : ii;
+        const double off = BW ? hoff[i] : (i > 0 ? hoff[i - 1] : 0.0);
+        hin = (H[i] - off * hin) * hrd[i];
+        H[i] = hin;
+    }
+}
+
+// Ring bookkeeping: chunk number g of this cluster's sequence is chunk `ch` (counted from the top
+// of the degree chain) of local column `it`, held in slot `slot` in mbarrier phase `ph`.
+struct F2Cursor {
+    int64_t it;
+    int ch, slot;
+    uint32_t ph;
+    __device__ __forceinline__ void step(const int nch, const int nslots) {
+        if (++ch == nch) {
+            ch = 0;
+            ++it;
+        }
+        if (++slot == nslots) {
+            slot = 0;
+            ph ^= 1;
+        }
+    }
+};
+
+// TMA loads of one chunk (rows j0 .. j0+nr-1 of column xcol) into its ring slot; one warp.
+__device__ __forceinline__ void f2_issue_chunk(const F2Params &P, uint64_t *full, double *ring, const int lane, const int k0, const int ml,
+                                               const double *xcol, const int chunk_from_top, const int slot) {
+    const int ch = P.nch - 1 - chunk_from_top;
+    const int j0 = ch * F2_G;
+    const int nr = min(F2_G, P.q - j0);
+    double *dst = ring + (size_t)slot * P.slot_stride;
+    if (nr <= 0) {   // a chunk above the last row (wide classes of the even/odd split): nothing to load
+        if (lane == 0) mbar_expect_tx(full + slot, 0);
+    } else if (P.contiguous) {
+        if (lane == 0) {
+            const int64_t gs = (int64_t)P.nh + (int64_t)j0 * P.m;
+            const int64_t a0 = gs & ~(int64_t)1, a1 = (gs + (int64_t)nr * P.m + 1) & ~(int64_t)1;
+            const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
+            mbar_expect_tx(full + slot, bytes);
+            tma_load_1d(dst, xcol + a0, bytes, full + slot);
+        }
+    } else {
+        const int64_t g0 = (int64_t)P.nh + (int64_t)(j0 + lane) * P.m + k0;
+        const int64_t a0 = g0 & ~(int64_t)1, a1 = (g0 + ml + 1) & ~(int64_t)1;
+        const uint32_t bytes = lane < nr ? (uint32_t)(a1 - a0) * 8u : 0u;
+        const uint32_t total = __reduce_add_sync(POP_FULL_MASK, bytes);
+        if (lane == 0) mbar_expect_tx(full + slot, total);
+        __syncwarp();
+        if (lane < nr) tma_load_1d(dst + (size_t)lane * P.rp, xcol + a0, bytes, full + slot);
+    }
+}
+
+template <int ROWS, int NPAR, int ND, bool SKIP1, bool MUL>
+__global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_constant__ F2Params P) {
+    static_assert(NPAR == 1 || (ND != 1 && (ND == 0 || SKIP1)), "the even/odd split needs decoupled chains");
+    static_assert(!(MUL && NPAR != 1), "fused product: one thread per element");
+    static_assert(ROWS % F2_G == 0, "row classes are multiples of the chunk height");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int JMAX = ROWS * NPAR;
+    constexpr int G = F2_G;
+    constexpr int NCH = JMAX / G;                    // chunks per column of this class (the top one may be partial)
+    constexpr int JSAFE = JMAX - F2_CLASS * NPAR;    // rows j <= JSAFE exist for every q of the class
+    constexpr int NBI = (F2_NBMAX + NPAR - 1) / NPAR;
+
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *full = bars, *hfull = bars + F2_MAXSLOTS, *hx = hfull + 2;
+    double *sm = reinterpret_cast<double *>(smem_raw + F2_BAR_BYTES);
+    double2 *tab = reinterpret_cast<double2 *>(sm + P.o_tab);   // (rd_j, w2_j), zero beyond q
+    double *tab1 = sm + P.o_tab1;                               // w1_j
+    double *tT = sm + P.o_tT;                                   // [3][JMAX+2] product bands
+    double *Hb = sm + P.o_H;
+    double *ct = sm + P.o_ct;
+    double *xb = sm + P.o_xb;   // x of the coupled bubbles (fused product)
+    double *part = sm + P.o_part;
+    double *wagg = sm + P.o_wagg;
+    double *ring = sm + P.o_ring;
+    // reciprocal hat pivots / hat super-diagonal: staged in shared memory when it has room
+    const double *hrd = P.hat_tabs ? sm + P.o_hrd : P.rdA;
+    const double *hoff = P.hat_tabs ? sm + P.o_hoff : P.offA;
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+    const int cs = P.cs;
+    const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const int m = P.m, nh = P.nh, q = P.q, nb = P.nb;
+    const int ncE = P.ncE;
+    const int k0 = rank * P.mloc;
+    const int ml = min(m, k0 + P.mloc) - k0;
+    const int nslots = P.nslots;
+    const int64_t ncl = gridDim.x / cs;
+    const int64_t c_first = blockIdx.x / cs;
+    const int64_t ncols = c_first < P.nrhs ? (P.nrhs - c_first + ncl - 1) / ncl : 0;   // columns of this cluster
+    const uint32_t hbytes = (uint32_t)((nh + 1) & ~1) * 8u;
+    const int64_t colstep = ncl * P.ldx;
+
+    // ---- one-time setup ----------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < nslots; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(hfull + s, 1);
+            mbar_init(hx + s, 1);
+        }
+        fence_mbar_init();
+    }
+    for (int j = tid; j < JMAX + 2; j += nthr) {
+        const bool in = j < q;
+        tab[j] = make_double2(in ? P.rdD[j] : 0.0, (in && P.W2 && j + 2 < q) ? P.W2[j] : 0.0);
+        tab1[j] = (in && P.W1 && j + 1 < q) ? P.W1[j] : 0.0;
+        if (MUL) {
+            tT[j] = in ? P.Td0[j] : 0.0;
+            tT[(JMAX + 2) + j] = (in && P.Td1 && j + 1 < q) ? P.Td1[j] : 0.0;
+            tT[2 * (JMAX + 2) + j] = (in && P.Td2 && j + 2 < q) ? P.Td2[j] : 0.0;
+        }
+    }
+    if (P.hat_tabs)
+        for (int i = tid; i < nh; i += nthr) {
+            sm[P.o_hrd + i] = P.rdA[i];
+            sm[P.o_hoff + i] = i < nh - 1 ? P.offA[i] : 0.0;
+        }
+    __syncthreads();
+    if (cs > 1) {
+        cluster_arrive();
+        cluster_wait();
+    }
+    // The ring is refilled by all warps: chunk g of the issue sequence is handled by warp g % nw.
+    // `iss` is the next chunk to issue (every thread tracks it), `rd` the next chunk to consume.
+    F2Cursor iss = {0, 0, 0, 0}, rd = {0, 0, 0, 0};
+    const double *xbase = P.X + c_first * P.ldx;
+    if (ncols > 0) {
+        if (tid == 0) {
+            mbar_expect_tx(hfull, hbytes);
+            tma_load_1d(Hb, xbase, hbytes, hfull);
+        }
+        for (int g = 0; g < nslots && iss.it < ncols; ++g) {
+            if ((g % nw) == warp) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase + iss.it * colstep, iss.ch, iss.slot);
+            iss.step(NCH, nslots);
+        }
+    }
+
+    const int par = NPAR == 1 ? 0 : tid / ncE;            // warp-uniform
+    const int e = NPAR == 1 ? tid : tid - par * ncE;
+    const bool active = e < ml;
+    const int el = min(e, ml - 1);
+    const int k = k0 + el;
+    // cs > 1: rows were loaded as 16 B aligned supersets; element e of row j sits at offset
+    // e + (par0 ^ (j & modd)).  cs == 1: a chunk is one contiguous run starting at parity par0.
+    const int par0 = P.contiguous ? (nh & 1) : ((nh + k0) & 1);
+    const int modd = P.contiguous ? 0 : (m & 1);
+    const int off_even = el + par0, off_odd = el + (par0 ^ modd);
+    const int rp = P.rp;
+    const double2 *tabp = tab + par;
+    const double *tab1p = tab1 + par;
+    // hats this thread owns in the scans
+    const int sg = (nh + nthr - 1) / nthr;
+    const int lo = min(tid * sg, nh), hi = min(lo + sg, nh);
+    const int pstride = P.pstride;
+    // coupling entries of this element (rows b = NPAR*i + par), reloaded per use from L1/L2
+    const double *sbk = P.Sb + k;
+
+    for (int64_t it = 0; it < ncols; ++it) {
+        double *xcol = P.X + (c_first + it * ncl) * P.ldx;
+        const int hb = (int)(it & 1);
+        const uint32_t hph = (uint32_t)(it >> 1) & 1;
+        double *H = Hb + (size_t)hb * P.hstride;
+        double *pmine = part + ((size_t)hb * cs + rank) * pstride;
+
+        // ---- column -> registers (ring order = backward-sweep order) --------------------------
+        double z[ROWS];
+#pragma unroll
+        for (int cc = NCH - 1; cc >= 0; --cc) {
+            mbar_wait(full + rd.slot, rd.ph);
+            const double *sp = ring + (size_t)rd.slot * P.slot_stride;
+#pragma unroll
+            for (int r = G - 1; r >= 0; --r) {
+                const int j = cc * G + r;
+                const double *src = sp + r * rp + ((j & 1) ? off_odd : off_even);
+                if (NPAR == 1) {
+                    z[j] = (j <= JSAFE || j < q) ? *src : 0.0;
+                } else {
+                    if (par == (j & 1)) z[j >> 1] = (j <= JSAFE || j < q) ? *src : 0.0;
+                }
+            }
+            rd.step(NCH, nslots);
+        }
+        // ---- backward sweep  z_j = (b_j - W1(j) z_{j+1} - W2(j) z_{j+2}) rd_j  (:439-441) --------
+#pragma unroll
+        for (int i = ROWS - 1; i >= 0; --i) {
+            const double2 cf = tabp[NPAR * i];
+            double v = z[i];
+            if (NPAR == 1) {
+                if (ND >= 1 && !SKIP1 && i + 1 < ROWS) v = fma(-tab1p[i], z[i + 1], v);
+                if (ND >= 2 && i + 2 < ROWS) v = fma(-cf.y, z[i + 2], v);
+            } else {
+                if (ND >= 2 && i + 1 < ROWS) v = fma(-cf.y, z[i + 1], v);
+            }
+            z[i] = v * cf.x;
+        }
+        // ---- coupling to the hats: per-element contributions (:449-451) -----------------------
+        {
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NBI; ++i) {
+                const int b = NPAR * i + par;
+                if (i < ROWS && b < nb) {
+                    const double *sb = sbk + (size_t)b * 3 * m;
+                    c0 = fma(__ldg(sb), z[i], c0);
+                    c1 = fma(__ldg(sb + m), z[i], c1);
+                    c2 = fma(__ldg(sb + 2 * m), z[i], c2);
+                }
+            }
+            ct[(par * 3 + 0) * ncE + e] = active ? c0 : 0.0;
+            ct[(par * 3 + 1) * ncE + e] = active ? c1 : 0.0;
+            ct[(par * 3 + 2) * ncE + e] = active ? c2 : 0.0;
+        }
+        fence_proxy_async();   // this thread's earlier writes to the hat buffer vs. the TMA refill below
+        __syncthreads();
+        // every row of this column is in registers: refill the ring (and the other hat buffer)
+        if (tid == 0 && it + 1 < ncols) {
+            mbar_expect_tx(hfull + (hb ^ 1), hbytes);
+            tma_load_1d(Hb + (size_t)(hb ^ 1) * P.hstride, xcol + colstep, hbytes, hfull + (hb ^ 1));
+        }
+        for (int g = 0; g < NCH && iss.it < ncols; ++g) {
+            if ((g % nw) == warp) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase + iss.it * colstep, iss.ch, iss.slot);
+            iss.step(NCH, nslots);
+        }
+        // partial sums for hats k0-1 .. k1 (index u = hat - (k0-1))
+        for (int u = tid; u < ml + 2; u += nthr) {
+            double v = 0.0;
+#pragma unroll
+            for (int pp = 0; pp < NPAR; ++pp)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int ee = u - t;
+                    if (ee >= 0 && ee < ml) v += ct[(pp * 3 + t) * ncE + ee];
+                }
+            pmine[u] = v;
+        }
+        if (cs > 1) fence_proxy_async();   // the partial sums are read by the peer copies (async proxy)
+        __syncthreads();
+        if (cs > 1) {
+            if (tid == 0) {
+                uint32_t expect = 0;
+                for (int r = 0; r < cs; ++r) {
+                    if (r == rank) continue;
+                    const int mlr = min(m, (r + 1) * P.mloc) - r * P.mloc;
+                    expect += (uint32_t)((mlr + 3) & ~1) * 8u;
+                    dsmem_bulk_copy(mapa_u32(pmine, r), pmine, (uint32_t)((ml + 3) & ~1) * 8u, mapa_u32(hx + hb, r));
+                }
+                mbar_expect_tx(hx + hb, expect);
+            }
+            mbar_wait(hx + hb, hph);
+        }
+        mbar_wait(hfull + hb, hph);
+        // ---- hat right-hand sides of this thread's segment, then the two bidiagonal solves --------
+        for (int i = lo; i < hi; ++i) {
+            double v = H[i];
+            const int rlo = max(0, (i - 1) / P.mloc), rhi = min(cs - 1, (i + 1) / P.mloc);
+            for (int r = rlo; r <= rhi; ++r) {
+                const int mlr = min(m, (r + 1) * P.mloc) - r * P.mloc;
+                const int u = i - r * P.mloc + 1;
+                if (u >= 0 && u < mlr + 2) v -= part[((size_t)hb * cs + r) * pstride + u];
+            }
+            H[i] = v;
+        }
+        f2_scan_dir<true>(H, hrd, hoff, lo, hi, lane, warp, nw, wagg);
+        f2_scan_dir<false>(H, hrd, hoff, lo, hi, lane, warp, nw, wagg + 64);
+        __syncthreads();
+        // ---- correct the coupled bubbles (:475-477) ----------------------------------------------
+        const double h0 = (k - 1 >= 0 && k - 1 < nh) ? H[k - 1] : 0.0;
+        const double h1 = k < nh ? H[k] : 0.0;
+        const double h2 = k + 1 < nh ? H[k + 1] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NBI; ++i) {
+            const int b = NPAR * i + par;
+            if (i < ROWS && b < nb) {
+                const double *sb = sbk + (size_t)b * 3 * m;
+                double v = z[i];
+                v = fma(-__ldg(sb), h0, v);
+                v = fma(-__ldg(sb + m), h1, v);
+                v = fma(-__ldg(sb + 2 * m), h2, v);
+                z[i] = v;
+            }
+        }
+        // ---- forward sweep  x_j = (z_j - W1(j-1) x_{j-1} - W2(j-2) x_{j-2}) rd_j  (:480-482) --------
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const double2 cf = tabp[NPAR * i];
+            double v = z[i];
+            if (NPAR == 1) {
+                if (ND >= 1 && !SKIP1 && i >= 1) v = fma(-tab1p[i - 1], z[i - 1], v);
+                if (ND >= 2 && i >= 2) v = fma(-tabp[i - 2].y, z[i - 2], v);
+            } else {
+                if (ND >= 2 && i >= 1) v = fma(-tabp[NPAR * (i - 1)].y, z[i - 1], v);
+            }
+            z[i] = v * cf.x;
+        }
+        if (!MUL) {
+            if (rank == 0)
+                for (int i = tid; i < nh; i += nthr) xcol[i] = H[i];
+            if (active) {
+                double *xo = xcol + nh + k + (NPAR == 2 ? (int64_t)par * m : 0);
+                const int64_t xs = (int64_t)NPAR * m;
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) {
+                    const int jj = NPAR * i;                       // row j = jj + par
+                    if (jj + NPAR - 1 <= JSAFE || jj + par < q) *xo = z[i];
+                    xo += xs;
+                }
+            }
+        } else {
+            // ---- fused product  r = T x + gamma f,  T = Symmetric(upper data) ------------------
+            const bool useF = P.gamma != 0.0;
+            const double *fcol = P.F + (c_first + it * ncl) * P.ldf;
+            const double *t0 = tT, *t1 = tT + (JMAX + 2), *t2 = tT + 2 * (JMAX + 2);
+            // the hat rows of the product read x of the coupled bubbles
+#pragma unroll
+            for (int b = 0; b < F2_NBMAX; ++b)
+                if (b < ROWS && b < P.nbT) xb[b * ncE + e] = active ? z[b] : 0.0;
+            constexpr int BLK = 8;
+            const double *fo = fcol + nh + k;
+            double *xo = xcol + nh + k;
+#pragma unroll
+            for (int i0 = 0; i0 < ROWS; i0 += BLK) {
+                double fq[BLK];
+#pragma unroll
+                for (int u = 0; u < BLK; ++u) {
+                    const int j = i0 + u;
+                    fq[u] = (useF && active && (j <= JSAFE || j < q)) ? __ldg(fo) : 0.0;
+                    fo += m;
+                }
+#pragma unroll
+                for (int u = 0; u < BLK; ++u) {
+                    const int j = i0 + u;
+                    double acc = t0[j] * z[j];
+                    if (!SKIP1) {
+                        if (j + 1 < ROWS) acc = fma(t1[j], z[j + 1], acc);
+                        if (j >= 1) acc = fma(t1[j - 1], z[j - 1], acc);
+                    }
+                    if (j + 2 < ROWS) acc = fma(t2[j], z[j + 2], acc);
+                    if (j >= 2) acc = fma(t2[j - 2], z[j - 2], acc);
+                    if (j < F2_NBMAX && j < P.nbT) {
+                        const double *sb = P.Trow + (size_t)j * 3 * m + k;
+                        acc = fma(__ldg(sb), h0, acc);
+                        acc = fma(__ldg(sb + m), h1, acc);
+                        acc = fma(__ldg(sb + 2 * m), h2, acc);
+                    }
+                    if (active && (j <= JSAFE || j < q)) *xo = fma(P.gamma, fq[u], acc);
+                    xo += m;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < nh; i += nthr) {
+                double acc = P.TAd[i] * H[i];
+                if (i + 1 < nh) acc = fma(P.TAu[i], H[i + 1], acc);
+                if (i > 0) acc = fma(P.TAu[i - 1], H[i - 1], acc);
+                for (int b = 0; b < P.nbT; ++b)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const int kk = i - t + 1;
+                        if (kk >= 0 && kk < m) acc = fma(__ldg(P.Trow + ((size_t)b * 3 + t) * m + kk), xb[b * ncE + kk], acc);
+                    }
+                xcol[i] = useF ? fma(P.gamma, fcol[i], acc) : acc;
+            }
+        }
+    }
+    if (cs > 1) {
+        cluster_arrive();
+        cluster_wait();
+    }
+}
+
+// one translation unit per row class: NPAR = 1 for every class, NPAR = 2 (q up to 128) for 40..64
+template <int ROWS>
+static f2_kernel_t f2_pick(int npar, int variant, bool mul) {
+    if (npar == 2) {
+        if constexpr (ROWS >= 40) {
+            if (variant == 0) return k_fused2<ROWS, 2, 0, false, false>;
+            return k_fused2<ROWS, 2, 2, true, false>;
+        } else {
+            return nullptr;
+        }
+    }
+    if (variant == 0) return mul ? k_fused2<ROWS, 1, 0, false, true> : k_fused2<ROWS, 1, 0, false, false>;
+    if (variant == 1) return mul ? k_fused2<ROWS, 1, 2, true, true> : k_fused2<ROWS, 1, 2, true, false>;
+    return mul ? k_fused2<ROWS, 1, 2, false, true> : k_fused2<ROWS, 1, 2, false, false>;
+}
+#define F2_DEFINE_CLASS(ROWS) \
+    f2_kernel_t f2_kernel_r##ROWS(int npar, int variant, bool mul) { return f2_pick<ROWS>(npar, variant, mul); }
+#endif  // __CUDACC__

@@ -1,0 +1,3 @@
+// Row class 32 of the register-resident fused solve (kernel template: pop_fused2.cuh).
+#include "pop_fused2.cuh"
+F2_DEFINE_CLASS(32)

@@ -52,7 +52,7 @@ struct pop_arrowhead {
     bool has_recip;   // rdA/rdD are up to date
     bool is_factor;   // produced by reverse Cholesky (upper data hold U)
     int bmask;        // bit t set: slot t of some B block may be non-zero
-    bool band1_zero;  // factor only: the first super-diagonal of every D block is identically zero
+    bool band1_zero;  // the first super-/sub-diagonal of every D block is identically zero (or absent)
     int64_t n() const { return (int64_t)d.nh + (int64_t)d.m * d.q; }
 };
 
@@ -116,6 +116,10 @@ int pop_launch_mul(pop_ctx *ctx, const MulView &mv, double alpha, const double *
 bool pop_fused_supported(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T);
 int pop_launch_solve_fused(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, double gamma,
                            const double *F, int64_t ldf, double *X, int64_t ldx, int64_t nrhs);
+// register-resident single-pass kernel (pop_fused2.cu): LEFT only, shared D block, q <= 128
+bool pop_fused2_supported(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, int64_t ldx, const double *X);
+int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *F, int64_t ldf,
+                            double *X, int64_t ldx, int64_t nrhs);
 int pop_launch_factor(pop_ctx *ctx, pop_arrowhead **S, int count, int32_t *info_out);
 int pop_launch_axpby_batch(pop_ctx *ctx, const pop_arrowhead *X, const pop_arrowhead *Y,
                            const double *h_alpha, const double *h_beta, int count, pop_arrowhead **out);

@@ -287,10 +287,12 @@ extern "C" int pop_solve(pop_ctx *ctx, const pop_arrowhead *U, int side, double 
     if (rc) return rc;
     if (nrhs == 0) return POP_OK;
     if (side == POP_LEFT && algo != POP_SOLVE_STAGED) {
+        if (algo != POP_SOLVE_FUSED_SMEM && pop_fused2_supported(ctx, U, nullptr, ldx, dX))
+            return pop_launch_solve_fused2(ctx, U, nullptr, 0.0, nullptr, 0, dX, ldx, nrhs);
         if (pop_fused_supported(ctx, U, nullptr)) return pop_launch_solve_fused(ctx, U, nullptr, 0.0, nullptr, 0, dX, ldx, nrhs);
-        POP_REQUIRE(algo != POP_SOLVE_FUSED, POP_ERR_DIM, "pop_solve: fused kernel does not support this shape (n=%lld)", (long long)U->n());
+        POP_REQUIRE(algo != POP_SOLVE_FUSED && algo != POP_SOLVE_FUSED_SMEM, POP_ERR_DIM, "pop_solve: fused kernel does not support this shape (n=%lld)", (long long)U->n());
     }
-    POP_REQUIRE(!(side == POP_RIGHT && algo == POP_SOLVE_FUSED), POP_ERR_ARG, "pop_solve: the fused kernel acts on columns only");
+    POP_REQUIRE(!(side == POP_RIGHT && (algo == POP_SOLVE_FUSED || algo == POP_SOLVE_FUSED_SMEM)), POP_ERR_ARG, "pop_solve: the fused kernel acts on columns only");
     TriView up, lo;
     pop_make_triview(U, POP_UPPER, 0, 0, &up);
     pop_make_triview(U, POP_UPPER, 1, 0, &lo);
@@ -320,6 +322,8 @@ extern "C" int pop_solve_mul_axpy(pop_ctx *ctx, const pop_arrowhead *U, const po
         POP_REQUIRE(gamma == 0.0 || (dF != nullptr && ldf >= U->n()), POP_ERR_DIM, "pop_solve_mul_axpy: F panel missing or too small");
     }
     if (nrhs == 0) return POP_OK;
+    if ((!Tm || gamma == 0.0 || !(ldf & 1)) && pop_fused2_supported(ctx, U, Tm, ldr, dR))
+        return pop_launch_solve_fused2(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
     if (pop_fused_supported(ctx, U, Tm)) return pop_launch_solve_fused(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
     // staged fallback: solve, then R <- T*X + gamma*F through a scratch copy
     TriView up, lo;

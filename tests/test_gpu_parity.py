@@ -39,7 +39,7 @@ def host(t):
 
 @pytest.fixture(autouse=True)
 def _fused_env():
-    old = {k: os.environ.get(k) for k in ("POP_FUSED_CS", "POP_DISABLE_FUSED")}
+    old = {k: os.environ.get(k) for k in ("POP_FUSED_CS", "POP_DISABLE_FUSED", "POP_F2_CS", "POP_F2_OCC", "POP_F2_SLOTS", "POP_DISABLE_FUSED2")}
     yield
     for k, v in old.items():
         if v is None:
@@ -234,7 +234,8 @@ def test_readme_case_goldens():
 
 
 SHAPES = [("c1", 16, 12), ("dirichlet", 8, 9), ("dirichlet", 16, 24), ("c1", 13, 7), ("dirichlet", 11, 6), ("c1", 64, 40), ("dirichlet", 32, 64),
-          ("c1", 2, 3), ("dirichlet", 2, 4), ("c1", 1, 6)]
+          ("c1", 2, 3), ("dirichlet", 2, 4), ("c1", 1, 6),
+          ("dirichlet", 12, 100), ("c1", 6, 129), ("c1", 4, 140), ("dirichlet", 70, 17), ("c1", 33, 65)]
 
 
 @pytest.mark.parametrize("basis,m,N", SHAPES)
@@ -251,6 +252,7 @@ def test_solve_staged_and_fused_vs_oracle(basis, m, N, sigma):
     Bm = rng.standard_normal((n, 37))
     want = O.packed_solve(Uo, Bm.copy())
     os.environ.pop("POP_FUSED_CS", None)
+    os.environ.pop("POP_F2_CS", None)
     got = {"staged": host(P.ldiv(F, dev(Bm), algo=P.SOLVE_STAGED))}
     for cs in (1, 2, 4, 8):
         if cs > m:
@@ -258,8 +260,11 @@ def test_solve_staged_and_fused_vs_oracle(basis, m, N, sigma):
         if (cs - 1) * -(-m // cs) >= m:
             continue                  # an empty trailing rank: not a valid partition
         os.environ["POP_FUSED_CS"] = str(cs)
-        got[f"fused cs={cs}"] = host(P.ldiv(F, dev(Bm), algo=P.SOLVE_FUSED))
+        got[f"fused-smem cs={cs}"] = host(P.ldiv(F, dev(Bm), algo=P.SOLVE_FUSED_SMEM))
+        os.environ["POP_F2_CS"] = str(cs)
+        got[f"fused-reg cs={cs}"] = host(P.ldiv(F, dev(Bm), algo=P.SOLVE_FUSED))
     os.environ.pop("POP_FUSED_CS", None)
+    os.environ.pop("POP_F2_CS", None)
     got["auto"] = host(P.ldiv(F, dev(Bm)))
     got["host"] = P.ldiv(F, np.asfortranarray(Bm))
     got["vector"] = host(P.ldiv(F, dev(Bm[:, 0])))[:, None]
@@ -287,7 +292,7 @@ def test_solve_per_element_blocks_general_bands():
         assert relerr(F.U.to_dense(), O.dense_reversecholesky(Ssym)) < TOL
         Bm = rng.standard_normal((Ao.n, 21))
         want = np.linalg.solve(Ssym, Bm)
-        for algo in (P.SOLVE_STAGED, P.SOLVE_FUSED):
+        for algo in (P.SOLVE_STAGED, P.SOLVE_FUSED, P.SOLVE_FUSED_SMEM):
             for cs in ("1", "2"):
                 os.environ["POP_FUSED_CS"] = cs
                 assert relerr(host(P.ldiv(F, dev(Bm), algo=algo)), want) < 1e-11
@@ -330,12 +335,13 @@ def test_fused_solve_mul_axpy(basis, m, N):
     want = np.zeros_like(Xo)
     O.packed_mul_left(1.0, To, Xo, 0.0, want)
     want += gamma * Fm
-    for disable in ("0", "1"):
+    for disable2, disable in (("0", "0"), ("1", "0"), ("1", "1")):      # register kernel, shared-memory kernel, staged
+        os.environ["POP_DISABLE_FUSED2"] = disable2
         os.environ["POP_DISABLE_FUSED"] = disable
         R, Fd = dev(R0), dev(Fm)
         L.check(L.lib().pop_solve_mul_axpy(F.ctx.handle, F.factor._h, T.data._h, gamma, Fd.data_ptr(), Fd.stride(1), R.data_ptr(), R.stride(1), 19))
         torch.cuda.synchronize()
-        assert relerr(host(R), want) < TOL, disable
+        assert relerr(host(R), want) < TOL, (disable2, disable)
 
 
 def test_adi_small_vs_oracle():
@@ -398,6 +404,8 @@ def test_baseline_shapes_residual_and_linearity(basis, m, N, ncols):
     Xf = P.ldiv(F, Bt)                                   # auto -> fused
     Xs = P.ldiv(F, Bt, algo=P.SOLVE_STAGED)
     assert float(torch.linalg.norm(Xf - Xs) / torch.linalg.norm(Xs)) < TOL
+    Xm = P.ldiv(F, Bt, algo=P.SOLVE_FUSED_SMEM)          # shared-memory-resident single-pass kernel
+    assert float(torch.linalg.norm(Xm - Xs) / torch.linalg.norm(Xs)) < TOL
     R = S @ Xf
     v = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
     for _ in range(30):                                                     # power iteration: ||S||_2 from below
