@@ -80,10 +80,9 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
     }
     const int jmax = pl.rows * pl.npar;
     const int maxthreads = f2_tmax(pl.rows);
-    int force_cs = 0, force_occ = 0, force_slots = 0;
+    int force_cs = 0, force_occ = 0;
     if (const char *e = getenv("POP_F2_CS")) force_cs = atoi(e);
     if (const char *e = getenv("POP_F2_OCC")) force_occ = atoi(e);
-    if (const char *e = getenv("POP_F2_SLOTS")) force_slots = atoi(e);
     const size_t limit = (size_t)ctx->max_smem_optin;
     pl.kern = f2_kernel(pl.rows, pl.npar, pl.variant, T != nullptr);
     if (!pl.kern) return pl;
@@ -100,16 +99,30 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         const int ncE = ((mloc + 31) / 32) * 32;
         const int threads = ncE * pl.npar;
         if (threads > maxthreads) continue;
+        if (cs > 1 && (d.m & 1)) continue;   // row parities would alternate inside a CTA's slab
         F2Params &p = pl.p;
         p.cs = cs; p.mloc = mloc; p.ncE = ncE;
         p.contiguous = cs == 1 ? 1 : 0;
         p.rp = cs == 1 ? d.m : ev2i(mloc + 2);
         p.slot_stride = ev2i(F2_G * p.rp + 2);
         p.nch = jmax / F2_G;
-        p.pstride = ev2i(mloc + 2) + 2;
-        p.hstride = ev2i(d.nh) + 2;
+        p.hcap = ev2i(mloc + 1) + 8;
         const size_t slot_bytes = (size_t)p.slot_stride * 8;
         const size_t tail = 512;
+        int o = 0;
+        p.o_tab = o; o += 2 * (jmax + 2);
+        p.o_tab1 = o; o += ev2i(jmax + 2);
+        p.o_tT = o; o += T ? ev2i(3 * (jmax + 2)) : 0;
+        p.o_hrd = o; o += p.hcap;
+        p.o_hoff = o; o += p.hcap;
+        p.o_H = o; o += 2 * p.hcap;
+        p.o_ct = o; o += 3 * pl.npar * ncE;
+        p.o_xb = o; o += T ? F2_NBMAX * ncE : 0;
+        p.o_inb = o; o += F2_INB_SIZE;
+        p.o_wagg = o; o += 128;
+        o = (o + 15) & ~15;
+        p.o_ring = o;
+        const size_t fixed = F2_BAR_BYTES + (size_t)o * 8;
         // registers decide how many CTAs an SM can hold; shared memory is then split between them
         const int occ_regs = (int)(65536 / ((size_t)threads * ((fa.numRegs + 7) & ~7)));
         if (occ_regs < 1) continue;
@@ -117,34 +130,12 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         for (int occ = std::min(occ_regs, 4); occ >= 1 && !found; --occ) {
             if (force_occ && occ != force_occ) continue;
             const size_t budget = std::min(limit, (size_t)(233472 / occ) - 1024);
-            for (int hat_tabs = 1; hat_tabs >= 0 && !found; --hat_tabs) {
-                int o = 0;
-                p.o_tab = o; o += 2 * (jmax + 2);
-                p.o_tab1 = o; o += ev2i(jmax + 2);
-                p.o_tT = o; o += T ? ev2i(3 * (jmax + 2)) : 0;
-                p.o_hrd = o; o += hat_tabs ? ev2i(d.nh) : 0;
-                p.o_hoff = o; o += hat_tabs ? ev2i(d.nh) : 0;
-                p.o_H = o; o += 2 * p.hstride;
-                p.o_ct = o; o += 3 * pl.npar * ncE;
-                p.o_xb = o; o += T ? F2_NBMAX * ncE : 0;
-                p.o_part = o; o += 2 * cs * p.pstride;
-                p.o_wagg = o; o += 128;
-                o = (o + 15) & ~15;
-                p.o_ring = o;
-                p.hat_tabs = hat_tabs;
-                const size_t fixed = F2_BAR_BYTES + (size_t)o * 8;
-                if (budget < fixed + tail + slot_bytes * (size_t)p.nch) continue;
-                int slots = (int)((budget - fixed - tail) / slot_bytes);
-                slots = std::min(slots, std::min(F2_MAXSLOTS, 2 * p.nch));
-                // prefer the highest occupancy whose ring still holds a whole column plus a chunk
-                if (slots < p.nch + 1 && occ > 1 && !force_occ) continue;
-                if (force_slots >= p.nch && force_slots <= slots) slots = force_slots;
-                p.nslots = slots;
-                pl.occ = occ;
-                pl.threads = threads;
-                pl.smem = fixed + tail + slot_bytes * (size_t)slots;
-                found = true;
-            }
+            if (budget < fixed + tail + slot_bytes * (size_t)p.nch) continue;
+            p.nslots = p.nch;   // the ring holds exactly one column (static chunk <-> slot mapping)
+            pl.occ = occ;
+            pl.threads = threads;
+            pl.smem = fixed + tail + slot_bytes * (size_t)p.nch;
+            found = true;
         }
         if (!found) continue;
         pl.ok = true;

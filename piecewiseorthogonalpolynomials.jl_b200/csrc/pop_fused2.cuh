@@ -28,8 +28,8 @@ struct F2Params {
     double *X;
     int64_t ldx, nrhs;
     // plan
-    int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, pstride, hstride, hat_tabs;
-    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_part, o_wagg, o_ring;   // offsets in doubles
+    int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap;
+    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_ring;   // offsets in doubles
 };
 
 typedef void (*f2_kernel_t)(const F2Params);
@@ -45,21 +45,34 @@ f2_kernel_t f2_kernel_r64(int npar, int variant, bool mul);
 // largest block of a row class (registers: the chain of an element lives in 2*ROWS registers)
 __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : rows <= 48 ? 384 : 256; }
 
+// layout of the small cluster mailboxes (doubles, relative to o_inb)
+#define F2_INB_A 0     // [2 buffers][2 sides][2 parities]  boundary couplings of the neighbours' edge elements
+#define F2_INB_B 8     // [2 buffers][8 ranks]              segment maps of the downward hat sweep
+#define F2_INB_C 24    // [2 buffers][8 ranks]              segment maps of the upward hat sweep
+#define F2_INB_P 40    // [2 directions][8 ranks]           multipliers of the segment maps (constants of the factor)
+#define F2_INB_SIZE 56
+
 #ifdef __CUDACC__
-// h[i] = (H[i] - off[i] h[i+1]) rd[i], i = nh-1..0 (BW, src/arrowhead.jl:453) or
-// h[i] = (H[i] - off[i-1] h[i-1]) rd[i], i = 0..nh-1 (src/arrowhead.jl:472) as a block-wide segmented
-// affine scan: thread t owns hats [lo,hi).  Pass 1 reduces a segment to an affine map of its incoming
-// value, shuffles compose the maps inside a warp and across the warp aggregates, pass 2 is the
-// reference recurrence itself with the exact incoming value.
+// The hats are DISTRIBUTED over the cluster: CTA r owns hats [hA,hB) (hA = first element of the CTA).
+//   down: y[i] = (H[i] - off[i] y[i+1]) rd[i], i = nh-1..0   (U solve,   src/arrowhead.jl:453)
+//   up  : h[i] = (y[i] - off[i-1] h[i-1]) rd[i], i = 0..nh-1 (U' solve,  src/arrowhead.jl:472)
+// Each is a segmented affine scan: pass 1 reduces a thread's hats to the map  out = t + Pm * in ;
+// shuffles compose the maps over a warp and over the warp aggregates; the CTA's map (its additive
+// part; the multipliers are constants of the factor) goes to the peers that need it through
+// st.async + mbarrier; pass 2 is the reference recurrence itself with the exact incoming value.
+// hoffl[u] couples local hats u-1 and u (hoffl[0]: the left neighbour's last hat).
+// Returns the value that entered this CTA's segment.
+#define F2_SCAN_WARPS 4   // warps that run the hat scans (the others wait at the block barrier)
 template <bool BW>
-__device__ __forceinline__ void f2_scan_dir(double *H, const double *hrd, const double *hoff, const int lo, const int hi, const int lane,
-                                            const int warp, const int nw, double *wagg) {
+__device__ __forceinline__ double f2_scan_dir(double *Hs, const double *hrd, const double *hoffl, const int lo, const int hi, const int tid,
+                                              const int lane, const int warp, const int nsw, double *wagg, const int cs, const int rank,
+                                              uint64_t *xbar, const uint32_t xph, double *inb, const double *Pc, double &hlast) {
     double t = 0.0, Pm = 1.0;
     for (int ii = lo; ii < hi; ++ii) {
-        const int i = BW ? (hi - 1 - (ii - lo)) : ii;
-        const double off = BW ? hoff[i] : (i > 0 ? hoff[i - 1] : 0.0);
-        const double rd = hrd[i];
-        t = (H[i] - off * t) * rd;
+        const int u = BW ? (hi - 1 - (ii - lo)) : ii;
+        const double off = BW ? hoffl[u + 1] : hoffl[u];
+        const double rd = hrd[u];
+        t = (Hs[u] - off * t) * rd;
         Pm = -off * rd * Pm;
     }
 #pragma unroll
@@ -73,55 +86,67 @@ __device__ __forceinline__ void f2_scan_dir(double *H, const double *hrd, const 
         }
     }
     // lane now holds the composite of lanes lane..31 (BW) / 0..lane (forward)
-    if (lane == (BW ? 0 : 31)) {
-        wagg[warp] = t;
-        wagg[32 + warp] = Pm;
-    }
-    __syncthreads();
-    // compose the warp aggregates (every warp redundantly, by shuffles)
-    double at = lane < nw ? wagg[lane] : 0.0, aP = lane < nw ? wagg[32 + lane] : 1.0;
+    double at = t, aP = Pm;
+    if (nsw > 1) {
+        if (lane == (BW ? 0 : 31)) {
+            wagg[warp] = t;
+            wagg[32 + warp] = Pm;
+        }
+        named_bar_sync(1, nsw * 32);
+        // compose the warp aggregates (every scan warp redundantly, by shuffles)
+        at = lane < nsw ? wagg[lane] : 0.0;
+        aP = lane < nsw ? wagg[32 + lane] : 1.0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t2 = BW ? __shfl_down_sync(POP_FULL_MASK, at, o) : __shfl_up_sync(POP_FULL_MASK, at, o);
-        const double P2 = BW ? __shfl_down_sync(POP_FULL_MASK, aP, o) : __shfl_up_sync(POP_FULL_MASK, aP, o);
-        const bool ok = BW ? (lane + o < 32) : (lane - o >= 0);
-        if (ok) {
-            at = fma(aP, t2, at);
-            aP = aP * P2;
+        for (int o = 1; o < F2_SCAN_WARPS; o <<= 1) {
+            const double t2 = BW ? __shfl_down_sync(POP_FULL_MASK, at, o) : __shfl_up_sync(POP_FULL_MASK, at, o);
+            const double P2 = BW ? __shfl_down_sync(POP_FULL_MASK, aP, o) : __shfl_up_sync(POP_FULL_MASK, aP, o);
+            const bool ok = BW ? (lane + o < 32) : (lane - o >= 0);
+            if (ok) {
+                at = fma(aP, t2, at);
+                aP = aP * P2;
+            }
+        }
+    } else {
+        // one scan warp: its own composite sits in lane 0 (BW) / lane 31 (forward)
+        at = __shfl_sync(POP_FULL_MASK, t, BW ? 0 : 31);
+        aP = 1.0;
+    }
+    // cluster level: my segment's map goes to the ranks below (BW) / above (forward) me
+    double Gc = 0.0;
+    if (cs > 1) {
+        const int nfrom = BW ? cs - 1 - rank : rank;      // peers whose maps I need
+        if (tid == (BW ? 0 : (nsw > 1 ? nsw - 1 : 0))) {  // this lane holds the composite of all scan warps
+            for (int r = BW ? 0 : rank + 1; r < (BW ? rank : cs); ++r) st_async_f64(mapa_u32(inb + rank, r), at, mapa_u32(xbar, r));
+        }
+        if (nfrom > 0) {
+            if (tid == 0) mbar_expect_tx(xbar, (uint32_t)nfrom * 8u);
+            mbar_wait(xbar, xph);
+            if (BW) {
+                for (int r = cs - 1; r > rank; --r) Gc = fma(Pc[r], Gc, inb[r]);
+            } else {
+                for (int r = 0; r < rank; ++r) Gc = fma(Pc[r], Gc, inb[r]);
+            }
         }
     }
-    // value entering this warp: composite of the warps after (BW) / before (forward) it applied to 0
-    const int src = BW ? warp + 1 : warp - 1;
-    double Gin = __shfl_sync(POP_FULL_MASK, at, src & 31);
-    if (BW ? (warp + 1 >= nw || warp + 1 > 31) : (warp == 0)) Gin = 0.0;
+    // value entering this warp: composite of the scan warps after (BW) / before (forward) it applied to Gc
+    double Gin = Gc;
+    if (nsw > 1) {
+        const int src = BW ? warp + 1 : warp - 1;
+        const double ats = __shfl_sync(POP_FULL_MASK, at, src & 31), aPs = __shfl_sync(POP_FULL_MASK, aP, src & 31);
+        if (BW ? (warp + 1 < nsw) : (warp > 0)) Gin = fma(aPs, Gc, ats);
+    }
     const double tn = BW ? __shfl_down_sync(POP_FULL_MASK, t, 1) : __shfl_up_sync(POP_FULL_MASK, t, 1);
     const double Pn = BW ? __shfl_down_sync(POP_FULL_MASK, Pm, 1) : __shfl_up_sync(POP_FULL_MASK, Pm, 1);
     double hin = (BW ? (lane == 31) : (lane == 0)) ? Gin : fma(Pn, Gin, tn);
     for (int ii = lo; ii < hi; ++ii) {
-        const int i = BW ? (hi - 1 - (ii - lo)) : ii;
-        const double off = BW ? hoff[i] : (i > 0 ? hoff[i - 1] : 0.0);
-        hin = (H[i] - off * hin) * hrd[i];
-        H[i] = hin;
+        const int u = BW ? (hi - 1 - (ii - lo)) : ii;
+        const double off = BW ? hoffl[u + 1] : hoffl[u];
+        hin = (Hs[u] - off * hin) * hrd[u];
+        Hs[u] = hin;
     }
+    hlast = hin;   // the last hat this thread wrote
+    return Gc;
 }
-
-// Ring bookkeeping: chunk number g of this cluster's sequence is chunk `ch` (counted from the top
-// of the degree chain) of local column `it`, held in slot `slot` in mbarrier phase `ph`.
-struct F2Cursor {
-    int64_t it;
-    int ch, slot;
-    uint32_t ph;
-    __device__ __forceinline__ void step(const int nch, const int nslots) {
-        if (++ch == nch) {
-            ch = 0;
-            ++it;
-        }
-        if (++slot == nslots) {
-            slot = 0;
-            ph ^= 1;
-        }
-    }
-};
 
 // TMA loads of one chunk (rows j0 .. j0+nr-1 of column xcol) into its ring slot; one warp.
 __device__ __forceinline__ void f2_issue_chunk(const F2Params &P, uint64_t *full, double *ring, const int lane, const int k0, const int ml,
@@ -159,25 +184,24 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int JMAX = ROWS * NPAR;
     constexpr int G = F2_G;
-    constexpr int NCH = JMAX / G;                    // chunks per column of this class (the top one may be partial)
+    constexpr int NCH = JMAX / G;                    // chunks per column of this class (the top ones may be partial)
     constexpr int JSAFE = JMAX - F2_CLASS * NPAR;    // rows j <= JSAFE exist for every q of the class
     constexpr int NBI = (F2_NBMAX + NPAR - 1) / NPAR;
 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    uint64_t *full = bars, *hfull = bars + F2_MAXSLOTS, *hx = hfull + 2;
+    uint64_t *full = bars, *hfull = bars + F2_MAXSLOTS, *hxA = hfull + 2, *hxB = hfull + 4, *hxC = hfull + 6;
     double *sm = reinterpret_cast<double *>(smem_raw + F2_BAR_BYTES);
     double2 *tab = reinterpret_cast<double2 *>(sm + P.o_tab);   // (rd_j, w2_j), zero beyond q
     double *tab1 = sm + P.o_tab1;                               // w1_j
     double *tT = sm + P.o_tT;                                   // [3][JMAX+2] product bands
+    double *hrd = sm + P.o_hrd;                                 // [nhl+1] reciprocal pivots of my hats (+ the right neighbour's first)
+    double *hoffl = sm + P.o_hoff;                              // [nhl+1] hoffl[u] couples local hats u-1 and u
     double *Hb = sm + P.o_H;
     double *ct = sm + P.o_ct;
-    double *xb = sm + P.o_xb;   // x of the coupled bubbles (fused product)
-    double *part = sm + P.o_part;
+    double *xb = sm + P.o_xb;                                   // x of the coupled bubbles (fused product)
+    double *inb = sm + P.o_inb;
     double *wagg = sm + P.o_wagg;
     double *ring = sm + P.o_ring;
-    // reciprocal hat pivots / hat super-diagonal: staged in shared memory when it has room
-    const double *hrd = P.hat_tabs ? sm + P.o_hrd : P.rdA;
-    const double *hoff = P.hat_tabs ? sm + P.o_hoff : P.offA;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
@@ -187,11 +211,14 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     const int ncE = P.ncE;
     const int k0 = rank * P.mloc;
     const int ml = min(m, k0 + P.mloc) - k0;
+    const int hA = k0, hB = rank == cs - 1 ? nh : min(nh, k0 + ml);   // my hats
+    const int nhl = max(hB - hA, 0);
     const int nslots = P.nslots;
     const int64_t ncl = gridDim.x / cs;
     const int64_t c_first = blockIdx.x / cs;
     const int64_t ncols = c_first < P.nrhs ? (P.nrhs - c_first + ncl - 1) / ncl : 0;   // columns of this cluster
-    const uint32_t hbytes = (uint32_t)((nh + 1) & ~1) * 8u;
+    const int hA2 = hA & ~1;
+    const uint32_t hbytes = (uint32_t)(((hB + 1) & ~1) - hA2) * 8u;
     const int64_t colstep = ncl * P.ldx;
 
     // ---- one-time setup ----------------------------------------------------------------------
@@ -199,7 +226,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         for (int s = 0; s < nslots; ++s) mbar_init(full + s, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(hfull + s, 1);
-            mbar_init(hx + s, 1);
+            mbar_init(hxA + s, 1);
+            mbar_init(hxB + s, 1);
+            mbar_init(hxC + s, 1);
         }
         fence_mbar_init();
     }
@@ -213,75 +242,100 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             tT[2 * (JMAX + 2) + j] = (in && P.Td2 && j + 2 < q) ? P.Td2[j] : 0.0;
         }
     }
-    if (P.hat_tabs)
-        for (int i = tid; i < nh; i += nthr) {
-            sm[P.o_hrd + i] = P.rdA[i];
-            sm[P.o_hoff + i] = i < nh - 1 ? P.offA[i] : 0.0;
-        }
+    for (int u = tid; u <= nhl; u += nthr) {
+        const int i = hA + u;
+        hrd[u] = i < nh ? P.rdA[i] : 0.0;
+        hoffl[u] = (i >= 1 && i < nh) ? P.offA[i - 1] : 0.0;
+    }
+    // the hat scans run on the first nsw warps: scan thread t owns hats [lo,hi)
+    const int nsw = min(nw, F2_SCAN_WARPS);
+    const int nst = nsw * 32;
+    const int sg = (nhl + nst - 1) / nst;
+    const int lo = tid < nst ? min(tid * sg, nhl) : 0, hi = tid < nst ? min(lo + sg, nhl) : 0;
     __syncthreads();
     if (cs > 1) {
+        // multipliers of every rank's segment map (constants of the factor), shared through DSMEM
+        double pd = 1.0, pu = 1.0;
+        for (int u = lo; u < hi; ++u) {
+            pd *= -hoffl[u + 1] * hrd[u];
+            pu *= -hoffl[u] * hrd[u];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pd *= __shfl_xor_sync(POP_FULL_MASK, pd, o);
+            pu *= __shfl_xor_sync(POP_FULL_MASK, pu, o);
+        }
+        if (lane == 0) {
+            wagg[warp] = pd;
+            wagg[32 + warp] = pu;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            pd = 1.0;
+            pu = 1.0;
+            for (int w = 0; w < nsw; ++w) {
+                pd *= wagg[w];
+                pu *= wagg[32 + w];
+            }
+            for (int r = 0; r < cs; ++r) {
+                st_cluster_f64(mapa_u32(inb + F2_INB_P + rank, r), pd);
+                st_cluster_f64(mapa_u32(inb + F2_INB_P + 8 + rank, r), pu);
+            }
+        }
         cluster_arrive();
         cluster_wait();
     }
-    // The ring is refilled by all warps: chunk g of the issue sequence is handled by warp g % nw.
-    // `iss` is the next chunk to issue (every thread tracks it), `rd` the next chunk to consume.
-    F2Cursor iss = {0, 0, 0, 0}, rd = {0, 0, 0, 0};
+    // The ring holds exactly one column: chunk c (counted from the top of the degree chain) lives in
+    // slot c and its mbarrier phase is the parity of the local column number.  Warp w issues chunk w.
     const double *xbase = P.X + c_first * P.ldx;
     if (ncols > 0) {
         if (tid == 0) {
             mbar_expect_tx(hfull, hbytes);
-            tma_load_1d(Hb, xbase, hbytes, hfull);
+            tma_load_1d(Hb + 2, xbase + hA2, hbytes, hfull);
         }
-        for (int g = 0; g < nslots && iss.it < ncols; ++g) {
-            if ((g % nw) == warp) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase + iss.it * colstep, iss.ch, iss.slot);
-            iss.step(NCH, nslots);
-        }
+        for (int c = warp; c < NCH; c += nw) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase, c, c);
     }
 
+    // thread <-> element: shifted so that a warp's 32 elements start on a 32 B boundary of the column
     const int par = NPAR == 1 ? 0 : tid / ncE;            // warp-uniform
-    const int e = NPAR == 1 ? tid : tid - par * ncE;
-    const bool active = e < ml;
-    const int el = min(e, ml - 1);
+    const int tp = NPAR == 1 ? tid : tid - par * ncE;
+    const bool active = tp < ml;
+    const int e = (tp + ((4 - ((nh + k0) & 3)) & 3)) % ml;
+    const int el = active ? e : ml - 1;
     const int k = k0 + el;
-    // cs > 1: rows were loaded as 16 B aligned supersets; element e of row j sits at offset
-    // e + (par0 ^ (j & modd)).  cs == 1: a chunk is one contiguous run starting at parity par0.
+    // rows were loaded as 16 B aligned supersets: element e of a row sits at offset e + par0
     const int par0 = P.contiguous ? (nh & 1) : ((nh + k0) & 1);
-    const int modd = P.contiguous ? 0 : (m & 1);
-    const int off_even = el + par0, off_odd = el + (par0 ^ modd);
+    const int off0 = el + par0;
     const int rp = P.rp;
     const double2 *tabp = tab + par;
     const double *tab1p = tab1 + par;
-    // hats this thread owns in the scans
-    const int sg = (nh + nthr - 1) / nthr;
-    const int lo = min(tid * sg, nh), hi = min(lo + sg, nh);
-    const int pstride = P.pstride;
     // coupling entries of this element (rows b = NPAR*i + par), reloaded per use from L1/L2
     const double *sbk = P.Sb + k;
+    const int expA = cs > 1 ? NPAR * 8 * ((rank > 0) + (rank < cs - 1)) : 0;
 
     for (int64_t it = 0; it < ncols; ++it) {
         double *xcol = P.X + (c_first + it * ncl) * P.ldx;
         const int hb = (int)(it & 1);
         const uint32_t hph = (uint32_t)(it >> 1) & 1;
-        double *H = Hb + (size_t)hb * P.hstride;
-        double *pmine = part + ((size_t)hb * cs + rank) * pstride;
+        double *Hs = Hb + (size_t)hb * P.hcap + 2 + (hA & 1);   // Hs[u] = hat hA + u; Hs[-1], Hs[nhl] hold the neighbours' hats
+        double *inbA = inb + F2_INB_A + hb * 4;
 
         // ---- column -> registers (ring order = backward-sweep order) --------------------------
         double z[ROWS];
 #pragma unroll
         for (int cc = NCH - 1; cc >= 0; --cc) {
-            mbar_wait(full + rd.slot, rd.ph);
-            const double *sp = ring + (size_t)rd.slot * P.slot_stride;
+            mbar_wait(full + (NCH - 1 - cc), (uint32_t)it & 1);
+            const double *pr = ring + (size_t)(NCH - 1 - cc) * P.slot_stride + off0;
 #pragma unroll
-            for (int r = G - 1; r >= 0; --r) {
+            for (int r = 0; r < G; ++r) {
                 const int j = cc * G + r;
-                const double *src = sp + r * rp + ((j & 1) ? off_odd : off_even);
                 if (NPAR == 1) {
-                    z[j] = (j <= JSAFE || j < q) ? *src : 0.0;
+                    z[j] = (j <= JSAFE || j < q) ? *pr : 0.0;
                 } else {
-                    if (par == (j & 1)) z[j >> 1] = (j <= JSAFE || j < q) ? *src : 0.0;
+                    if (par == (j & 1)) z[j >> 1] = (j <= JSAFE || j < q) ? *pr : 0.0;
                 }
+                pr += rp;
             }
-            rd.step(NCH, nslots);
         }
         // ---- backward sweep  z_j = (b_j - W1(j) z_{j+1} - W2(j) z_{j+2}) rd_j  (:439-441) --------
 #pragma unroll
@@ -309,67 +363,65 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                     c2 = fma(__ldg(sb + 2 * m), z[i], c2);
                 }
             }
-            ct[(par * 3 + 0) * ncE + e] = active ? c0 : 0.0;
-            ct[(par * 3 + 1) * ncE + e] = active ? c1 : 0.0;
-            ct[(par * 3 + 2) * ncE + e] = active ? c2 : 0.0;
+            if (active) {
+                ct[(par * 3 + 0) * ncE + e] = c0;
+                ct[(par * 3 + 1) * ncE + e] = c1;
+                ct[(par * 3 + 2) * ncE + e] = c2;
+                if (cs > 1) {
+                    // my edge elements also couple to a neighbour's hat
+                    if (e == 0 && rank > 0) st_async_f64(mapa_u32(inbA + 2 + par, rank - 1), c0, mapa_u32(hxA + hb, rank - 1));
+                    if (e == ml - 1 && rank < cs - 1) st_async_f64(mapa_u32(inbA + par, rank + 1), c2, mapa_u32(hxA + hb, rank + 1));
+                }
+            }
         }
         fence_proxy_async();   // this thread's earlier writes to the hat buffer vs. the TMA refill below
         __syncthreads();
         // every row of this column is in registers: refill the ring (and the other hat buffer)
-        if (tid == 0 && it + 1 < ncols) {
-            mbar_expect_tx(hfull + (hb ^ 1), hbytes);
-            tma_load_1d(Hb + (size_t)(hb ^ 1) * P.hstride, xcol + colstep, hbytes, hfull + (hb ^ 1));
+        if (tid == 0) {
+            if (it + 1 < ncols) {
+                mbar_expect_tx(hfull + (hb ^ 1), hbytes);
+                tma_load_1d(Hb + (size_t)(hb ^ 1) * P.hcap + 2, xcol + colstep + hA2, hbytes, hfull + (hb ^ 1));
+            }
+            if (expA) mbar_expect_tx(hxA + hb, (uint32_t)expA);
         }
-        for (int g = 0; g < NCH && iss.it < ncols; ++g) {
-            if ((g % nw) == warp) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase + iss.it * colstep, iss.ch, iss.slot);
-            iss.step(NCH, nslots);
-        }
-        // partial sums for hats k0-1 .. k1 (index u = hat - (k0-1))
-        for (int u = tid; u < ml + 2; u += nthr) {
+        if (it + 1 < ncols)
+            for (int c = warp; c < NCH; c += nw) f2_issue_chunk(P, full, ring, lane, k0, ml, xcol + colstep, c, c);
+        if (expA) mbar_wait(hxA + hb, hph);
+        mbar_wait(hfull + hb, hph);
+        // ---- right-hand sides of my hats: hat hA+u collects elements u-1 (t=2), u (t=1), u+1 (t=0) ----
+        for (int u = tid; u < nhl; u += nthr) {
             double v = 0.0;
 #pragma unroll
-            for (int pp = 0; pp < NPAR; ++pp)
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const int ee = u - t;
-                    if (ee >= 0 && ee < ml) v += ct[(pp * 3 + t) * ncE + ee];
+            for (int pp = 0; pp < NPAR; ++pp) {
+                if (u + 1 < ml) v += ct[(pp * 3 + 0) * ncE + u + 1];
+                else if (u + 1 == ml && rank < cs - 1) v += inbA[2 + pp];
+                if (u < ml) v += ct[(pp * 3 + 1) * ncE + u];
+                if (u >= 1) {
+                    if (u - 1 < ml) v += ct[(pp * 3 + 2) * ncE + u - 1];
+                } else if (rank > 0) {
+                    v += inbA[pp];
                 }
-            pmine[u] = v;
-        }
-        if (cs > 1) fence_proxy_async();   // the partial sums are read by the peer copies (async proxy)
-        __syncthreads();
-        if (cs > 1) {
-            if (tid == 0) {
-                uint32_t expect = 0;
-                for (int r = 0; r < cs; ++r) {
-                    if (r == rank) continue;
-                    const int mlr = min(m, (r + 1) * P.mloc) - r * P.mloc;
-                    expect += (uint32_t)((mlr + 3) & ~1) * 8u;
-                    dsmem_bulk_copy(mapa_u32(pmine, r), pmine, (uint32_t)((ml + 3) & ~1) * 8u, mapa_u32(hx + hb, r));
-                }
-                mbar_expect_tx(hx + hb, expect);
             }
-            mbar_wait(hx + hb, hph);
+            Hs[u] -= v;
         }
-        mbar_wait(hfull + hb, hph);
-        // ---- hat right-hand sides of this thread's segment, then the two bidiagonal solves --------
-        for (int i = lo; i < hi; ++i) {
-            double v = H[i];
-            const int rlo = max(0, (i - 1) / P.mloc), rhi = min(cs - 1, (i + 1) / P.mloc);
-            for (int r = rlo; r <= rhi; ++r) {
-                const int mlr = min(m, (r + 1) * P.mloc) - r * P.mloc;
-                const int u = i - r * P.mloc + 1;
-                if (u >= 0 && u < mlr + 2) v -= part[((size_t)hb * cs + r) * pstride + u];
-            }
-            H[i] = v;
-        }
-        f2_scan_dir<true>(H, hrd, hoff, lo, hi, lane, warp, nw, wagg);
-        f2_scan_dir<false>(H, hrd, hoff, lo, hi, lane, warp, nw, wagg + 64);
         __syncthreads();
-        // ---- correct the coupled bubbles (:475-477) ----------------------------------------------
-        const double h0 = (k - 1 >= 0 && k - 1 < nh) ? H[k - 1] : 0.0;
-        const double h1 = k < nh ? H[k] : 0.0;
-        const double h2 = k + 1 < nh ? H[k + 1] : 0.0;
+        if (warp < nsw) {
+            double hl;
+            const double Gdn = f2_scan_dir<true>(Hs, hrd, hoffl, lo, hi, tid, lane, warp, nsw, wagg, cs, rank, hxB + hb, hph,
+                                                 inb + F2_INB_B + hb * 8, inb + F2_INB_P, hl);
+            const double Gup = f2_scan_dir<false>(Hs, hrd, hoffl, lo, hi, tid, lane, warp, nsw, wagg + 64, cs, rank, hxC + hb, hph,
+                                                  inb + F2_INB_C + hb * 8, inb + F2_INB_P + 8, hl);
+            // the neighbours' hats next to my segment: hat hA-1 entered the upward sweep; hat hB follows
+            // from the value that entered the downward sweep and my last hat (both recurrences, one step)
+            if (tid == 0) Hs[-1] = rank > 0 ? Gup : 0.0;
+            if (nhl == 0 ? tid == 0 : (hi == nhl && hi > lo)) {
+                Hs[nhl] = (hB < nh && nhl > 0) ? (Gdn - hoffl[nhl] * hl) * hrd[nhl] : 0.0;
+                Hs[nhl + 1] = 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- correct the coupled bubbles (:475-477): hats k-1, k, k+1 of element k ----------------
+        const double h0 = Hs[el - 1], h1 = Hs[el], h2 = Hs[el + 1];
 #pragma unroll
         for (int i = 0; i < NBI; ++i) {
             const int b = NPAR * i + par;
@@ -396,8 +448,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             z[i] = v * cf.x;
         }
         if (!MUL) {
-            if (rank == 0)
-                for (int i = tid; i < nh; i += nthr) xcol[i] = H[i];
+            for (int u = tid; u < nhl; u += nthr) xcol[hA + u] = Hs[u];
             if (active) {
                 double *xo = xcol + nh + k + (NPAR == 2 ? (int64_t)par * m : 0);
                 const int64_t xs = (int64_t)NPAR * m;
@@ -409,14 +460,14 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 }
             }
         } else {
-            // ---- fused product  r = T x + gamma f,  T = Symmetric(upper data) ------------------
+            // ---- fused product  r = T x + gamma f,  T = Symmetric(upper data); cs == 1: all hats are mine ----
             const bool useF = P.gamma != 0.0;
             const double *fcol = P.F + (c_first + it * ncl) * P.ldf;
             const double *t0 = tT, *t1 = tT + (JMAX + 2), *t2 = tT + 2 * (JMAX + 2);
             // the hat rows of the product read x of the coupled bubbles
 #pragma unroll
             for (int b = 0; b < F2_NBMAX; ++b)
-                if (b < ROWS && b < P.nbT) xb[b * ncE + e] = active ? z[b] : 0.0;
+                if (b < ROWS && b < P.nbT && active) xb[b * ncE + e] = z[b];
             constexpr int BLK = 8;
             const double *fo = fcol + nh + k;
             double *xo = xcol + nh + k;
@@ -451,9 +502,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             }
             __syncthreads();
             for (int i = tid; i < nh; i += nthr) {
-                double acc = P.TAd[i] * H[i];
-                if (i + 1 < nh) acc = fma(P.TAu[i], H[i + 1], acc);
-                if (i > 0) acc = fma(P.TAu[i - 1], H[i - 1], acc);
+                double acc = P.TAd[i] * Hs[i];
+                if (i + 1 < nh) acc = fma(P.TAu[i], Hs[i + 1], acc);
+                if (i > 0) acc = fma(P.TAu[i - 1], Hs[i - 1], acc);
                 for (int b = 0; b < P.nbT; ++b)
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {

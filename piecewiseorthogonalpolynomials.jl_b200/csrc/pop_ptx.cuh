@@ -64,6 +64,16 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, const
                  "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr)
                  : "memory");
 }
+// 8-byte store into a peer CTA's shared memory that completes 8 bytes on the PEER's mbarrier
+__device__ __forceinline__ void st_async_f64(uint32_t dst_cluster_addr, double v, uint32_t bar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+                 "l"(__double_as_longlong(v)), "r"(bar_cluster_addr)
+                 : "memory");
+}
+// plain store into a peer CTA's shared memory (made visible by the cluster barrier)
+__device__ __forceinline__ void st_cluster_f64(uint32_t dst_cluster_addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst_cluster_addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
