@@ -55,7 +55,7 @@ static f2_kernel_t f2_kernel(int rows, int npar, int variant, bool mul) {
 
 static inline int ev2i(int x) { return (x + 1) & ~1; }
 
-static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T) {
+static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, bool gamma_nonzero = false) {
     F2Plan pl = {};
     const pop_desc &d = U->d;
     if (!U->is_factor || U->mD != 1 || d.uD > 2 || d.q < 1) return pl;
@@ -69,20 +69,26 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
     else if ((nd == 0 || skip1) && t_even) pl.variant = 1;
     else pl.variant = 2;
     const int q = d.q;
-    if (q <= 64) {
+    // two threads per element (even / odd degree chains) when the chains decouple: mandatory for
+    // q > 64, optional below (POP_F2_NPAR=2: twice the warps per column, half the registers)
+    const bool can_split = pl.variant <= 1;
+    int want_npar = 0;
+    if (const char *e = getenv("POP_F2_NPAR")) want_npar = atoi(e);
+    if (q <= 64 && !(want_npar == 2 && can_split && q >= 2)) {
         pl.npar = 1;
         pl.rows = ((q + F2_CLASS - 1) / F2_CLASS) * F2_CLASS;
-    } else if (q <= 128 && !T && (nd == 0 || skip1)) {
-        pl.npar = 2;                                         // even / odd degree chains on two threads
+    } else if (q <= 128 && can_split) {
+        pl.npar = 2;
         pl.rows = ((q + 2 * F2_CLASS - 1) / (2 * F2_CLASS)) * F2_CLASS;
     } else {
         return pl;
     }
     const int jmax = pl.rows * pl.npar;
     const int maxthreads = f2_tmax(pl.rows);
-    int force_cs = 0, force_occ = 0;
+    int force_cs = 0, force_occ = 0, force_nf = 0;
     if (const char *e = getenv("POP_F2_CS")) force_cs = atoi(e);
     if (const char *e = getenv("POP_F2_OCC")) force_occ = atoi(e);
+    if (const char *e = getenv("POP_F2_NF")) force_nf = atoi(e);
     const size_t limit = (size_t)ctx->max_smem_optin;
     pl.kern = f2_kernel(pl.rows, pl.npar, pl.variant, T != nullptr);
     if (!pl.kern) return pl;
@@ -123,6 +129,7 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         o = (o + 15) & ~15;
         p.o_ring = o;
         const size_t fixed = F2_BAR_BYTES + (size_t)o * 8;
+        const bool fring = T != nullptr && gamma_nonzero;
         // registers decide how many CTAs an SM can hold; shared memory is then split between them
         const int occ_regs = (int)(65536 / ((size_t)threads * ((fa.numRegs + 7) & ~7)));
         if (occ_regs < 1) continue;
@@ -130,11 +137,16 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         for (int occ = std::min(occ_regs, 4); occ >= 1 && !found; --occ) {
             if (force_occ && occ != force_occ) continue;
             const size_t budget = std::min(limit, (size_t)(233472 / occ) - 1024);
-            if (budget < fixed + tail + slot_bytes * (size_t)p.nch) continue;
+            // fused product: a second ring streams the F column in (at least 2 chunks, at most a column)
+            const int nf_min = fring ? std::min(2, p.nch) : 0;
+            if (budget < fixed + tail + slot_bytes * (size_t)(p.nch + nf_min)) continue;
             p.nslots = p.nch;   // the ring holds exactly one column (static chunk <-> slot mapping)
+            p.nf = fring ? (int)std::min<size_t>(std::min(p.nch, F2_MAXFSLOTS), (budget - fixed - tail) / slot_bytes - p.nch) : 0;
+            if (force_nf >= nf_min && force_nf <= p.nf) p.nf = force_nf;
+            p.o_fring = p.o_ring + p.nch * p.slot_stride;
             pl.occ = occ;
             pl.threads = threads;
-            pl.smem = fixed + tail + slot_bytes * (size_t)p.nch;
+            pl.smem = fixed + tail + slot_bytes * (size_t)(p.nch + p.nf);
             found = true;
         }
         if (!found) continue;
@@ -148,12 +160,12 @@ bool pop_fused2_supported(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowh
     if (const char *e = getenv("POP_DISABLE_FUSED2"))
         if (atoi(e)) return false;
     if ((ldx & 1) || ((uintptr_t)X & 15)) return false;   // TMA bulk copies need 16 B aligned column starts
-    return plan_f2(ctx, U, T).ok;
+    return plan_f2(ctx, U, T, T != nullptr).ok;
 }
 
 int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *F, int64_t ldf,
                             double *X, int64_t ldx, int64_t nrhs) {
-    F2Plan pl = plan_f2(ctx, U, T);
+    F2Plan pl = plan_f2(ctx, U, T, T != nullptr && gamma != 0.0);
     POP_REQUIRE(pl.ok, POP_ERR_DIM, "fused solve v2: shape not supported (n=%lld, q=%d, uD=%d)", (long long)U->n(), U->d.q, U->d.uD);
     POP_REQUIRE(!(ldx & 1) && !((uintptr_t)X & 15), POP_ERR_DIM, "fused solve v2 needs an even leading dimension and a 16-byte aligned panel");
     if (nrhs == 0) return POP_OK;
@@ -178,6 +190,8 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
         p.TAu = T->p.Au;
         p.nbT = std::min(t.nB, t.q);
     }
+    POP_REQUIRE(!(T && gamma != 0.0) || (F && !(ldf & 1) && !((uintptr_t)F & 15)), POP_ERR_DIM,
+                "fused solve+product needs an even leading dimension and a 16-byte aligned F panel");
     p.gamma = gamma;
     p.F = F ? F : X;
     p.ldf = F ? ldf : ldx;

@@ -7,6 +7,7 @@
 #define F2_NBMAX 4        // coupling blocks B handled in registers
 #define F2_BAR_BYTES 1152 // 144 mbarrier words at the start of shared memory
 #define F2_MAXSLOTS 32
+#define F2_MAXFSLOTS 16
 #define F2_G 8            // rows per ring chunk
 #define F2_CLASS 8        // a row class covers q in (ROWS*NPAR - F2_CLASS*NPAR, ROWS*NPAR]
 
@@ -28,8 +29,8 @@ struct F2Params {
     double *X;
     int64_t ldx, nrhs;
     // plan
-    int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap;
-    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_ring;   // offsets in doubles
+    int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap, nf;   // nf: slots of the F ring (fused product)
+    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_ring, o_fring;   // offsets in doubles
 };
 
 typedef void (*f2_kernel_t)(const F2Params);
@@ -176,10 +177,25 @@ __device__ __forceinline__ void f2_issue_chunk(const F2Params &P, uint64_t *full
     }
 }
 
+// TMA load of F chunk `ch` (rows 8*ch .., ascending order) of column fcol into F-ring slot `slot`; one thread.
+__device__ __forceinline__ void f2_issue_fchunk(const F2Params &P, uint64_t *ffull, double *fring, const double *fcol, const int ch, const int slot) {
+    const int j0 = ch * F2_G;
+    const int nr = min(F2_G, P.q - j0);
+    if (nr <= 0) {
+        mbar_expect_tx(ffull + slot, 0);
+        return;
+    }
+    const int64_t gs = (int64_t)P.nh + (int64_t)j0 * P.m;
+    const int64_t a0 = gs & ~(int64_t)1, a1 = (gs + (int64_t)nr * P.m + 1) & ~(int64_t)1;
+    const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
+    mbar_expect_tx(ffull + slot, bytes);
+    tma_load_1d(fring + (size_t)slot * P.slot_stride, fcol + a0, bytes, ffull + slot);
+}
+
 template <int ROWS, int NPAR, int ND, bool SKIP1, bool MUL>
 __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_constant__ F2Params P) {
     static_assert(NPAR == 1 || (ND != 1 && (ND == 0 || SKIP1)), "the even/odd split needs decoupled chains");
-    static_assert(!(MUL && NPAR != 1), "fused product: one thread per element");
+    static_assert(!(MUL && NPAR == 2 && !(ND == 0 || SKIP1)), "fused product with split chains: T must not couple j and j+1");
     static_assert(ROWS % F2_G == 0, "row classes are multiples of the chunk height");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int JMAX = ROWS * NPAR;
@@ -190,6 +206,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *full = bars, *hfull = bars + F2_MAXSLOTS, *hxA = hfull + 2, *hxB = hfull + 4, *hxC = hfull + 6;
+    uint64_t *ffull = bars + 48, *fempty = bars + 64;   // F ring of the fused product
     double *sm = reinterpret_cast<double *>(smem_raw + F2_BAR_BYTES);
     double2 *tab = reinterpret_cast<double2 *>(sm + P.o_tab);   // (rd_j, w2_j), zero beyond q
     double *tab1 = sm + P.o_tab1;                               // w1_j
@@ -202,6 +219,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     double *inb = sm + P.o_inb;
     double *wagg = sm + P.o_wagg;
     double *ring = sm + P.o_ring;
+    double *fring = sm + P.o_fring;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
@@ -224,6 +242,11 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < nslots; ++s) mbar_init(full + s, 1);
+        if (MUL)
+            for (int s = 0; s < P.nf; ++s) {
+                mbar_init(ffull + s, 1);
+                mbar_init(fempty + s, nw);
+            }
         for (int s = 0; s < 2; ++s) {
             mbar_init(hfull + s, 1);
             mbar_init(hxA + s, 1);
@@ -288,13 +311,20 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     // The ring holds exactly one column: chunk c (counted from the top of the degree chain) lives in
     // slot c and its mbarrier phase is the parity of the local column number.  Warp w issues chunk w.
     const double *xbase = P.X + c_first * P.ldx;
+    const double *fbase = MUL ? P.F + c_first * P.ldf : nullptr;
+    const int64_t fstep = ncl * P.ldf;
     if (ncols > 0) {
         if (tid == 0) {
             mbar_expect_tx(hfull, hbytes);
             tma_load_1d(Hb + 2, xbase + hA2, hbytes, hfull);
         }
         for (int c = warp; c < NCH; c += nw) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase, c, c);
+        if (MUL && P.gamma != 0.0 && tid == 0)
+            for (int f = 0; f < P.nf && f < ncols * NCH; ++f) f2_issue_fchunk(P, ffull, fring, fbase + (f / NCH) * fstep, f % NCH, f);
     }
+    // F ring cursor: next chunk of the global F sequence (column-major over columns, chunks ascending)
+    int fslot = 0;
+    uint32_t fph = 0;
 
     // thread <-> element: shifted so that a warp's 32 elements start on a 32 B boundary of the column
     const int par = NPAR == 1 ? 0 : tid / ncE;            // warp-uniform
@@ -384,6 +414,15 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             }
             if (expA) mbar_expect_tx(hxA + hb, (uint32_t)expA);
         }
+        if (MUL && P.gamma != 0.0 && tid == 32 % nthr) {
+            // the part of this column's F that is not in the ring yet: pull it into L2 now
+            const double *fc = fbase + it * fstep;
+            for (int c = P.nf; c < NCH; ++c) {
+                const int64_t gs = ((int64_t)nh + (int64_t)c * G * m) & ~(int64_t)1;
+                const int nr = min(G, q - c * G);
+                if (nr > 0) l2_prefetch_bulk(fc + gs, (uint32_t)(((int64_t)nr * m + 2) & ~(int64_t)1) * 8u);
+            }
+        }
         if (it + 1 < ncols)
             for (int c = warp; c < NCH; c += nw) f2_issue_chunk(P, full, ring, lane, k0, ml, xcol + colstep, c, c);
         if (expA) mbar_wait(hxA + hb, hph);
@@ -461,46 +500,85 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             }
         } else {
             // ---- fused product  r = T x + gamma f,  T = Symmetric(upper data); cs == 1: all hats are mine ----
+            // NPAR == 2: rows j = 2i + par; T never couples j and j+1 there, so a thread needs only its own parity.
             const bool useF = P.gamma != 0.0;
             const double *fcol = P.F + (c_first + it * ncl) * P.ldf;
-            const double *t0 = tT, *t1 = tT + (JMAX + 2), *t2 = tT + 2 * (JMAX + 2);
+            const double *t0 = tT + par, *t1 = tT + (JMAX + 2) + par, *t2 = tT + 2 * (JMAX + 2) + par;
             // the hat rows of the product read x of the coupled bubbles
 #pragma unroll
-            for (int b = 0; b < F2_NBMAX; ++b)
-                if (b < ROWS && b < P.nbT && active) xb[b * ncE + e] = z[b];
-            constexpr int BLK = 8;
-            const double *fo = fcol + nh + k;
-            double *xo = xcol + nh + k;
+            for (int i = 0; i < NBI; ++i) {
+                const int b = NPAR * i + par;
+                if (i < ROWS && b < P.nbT && active) xb[b * ncE + e] = z[i];
+            }
+            constexpr int BLK = G / NPAR;                     // thread rows per F chunk
+            const int64_t xs = (int64_t)NPAR * m;
+            double *xo = xcol + nh + k + (NPAR == 2 ? (int64_t)par * m : 0);
+            const int foff = el + par0 + (NPAR == 2 ? par * m : 0);
+            const int fstride = NPAR * m;
+            const int64_t nfch = ncols * NCH;                 // F chunks of this cluster's sequence
 #pragma unroll
-            for (int i0 = 0; i0 < ROWS; i0 += BLK) {
+            for (int cch = 0; cch < NCH; ++cch) {
+                const int i0 = cch * BLK;
                 double fq[BLK];
+                if (useF) {
+                    // refill the slot of the previous chunk once every warp has read it (deferred by one chunk)
+                    if (cch > 0 && warp == ((cch - 1) % nw)) {
+                        const int ps = fslot == 0 ? P.nf - 1 : fslot - 1;
+                        const uint32_t pph = fslot == 0 ? fph ^ 1 : fph;
+                        mbar_wait(fempty + ps, pph);
+                        const int64_t fnext = it * NCH + (cch - 1) + P.nf;
+                        if (lane == 0 && fnext < nfch) f2_issue_fchunk(P, ffull, fring, fbase + (fnext / NCH) * fstep, (int)(fnext % NCH), ps);
+                    }
+                    mbar_wait(ffull + fslot, fph);
+                    const double *fp = fring + (size_t)fslot * P.slot_stride + foff;
 #pragma unroll
-                for (int u = 0; u < BLK; ++u) {
-                    const int j = i0 + u;
-                    fq[u] = (useF && active && (j <= JSAFE || j < q)) ? __ldg(fo) : 0.0;
-                    fo += m;
+                    for (int u = 0; u < BLK; ++u) {
+                        fq[u] = *fp;
+                        fp += fstride;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(fempty + fslot);
+                    if (++fslot == P.nf) {
+                        fslot = 0;
+                        fph ^= 1;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < BLK; ++u) fq[u] = 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < BLK; ++u) {
-                    const int j = i0 + u;
-                    double acc = t0[j] * z[j];
-                    if (!SKIP1) {
-                        if (j + 1 < ROWS) acc = fma(t1[j], z[j + 1], acc);
-                        if (j >= 1) acc = fma(t1[j - 1], z[j - 1], acc);
+                    const int i = i0 + u;
+                    const int jj = NPAR * i;          // row j = jj + par; table offsets are relative to par
+                    double acc = t0[jj] * z[i];
+                    if (NPAR == 1) {
+                        if (!SKIP1) {
+                            if (i + 1 < ROWS) acc = fma(t1[jj], z[i + 1], acc);
+                            if (i >= 1) acc = fma(t1[jj - 1], z[i - 1], acc);
+                        }
+                        if (i + 2 < ROWS) acc = fma(t2[jj], z[i + 2], acc);
+                        if (i >= 2) acc = fma(t2[jj - 2], z[i - 2], acc);
+                    } else {
+                        if (i + 1 < ROWS) acc = fma(t2[jj], z[i + 1], acc);
+                        if (i >= 1) acc = fma(t2[jj - 2], z[i - 1], acc);
                     }
-                    if (j + 2 < ROWS) acc = fma(t2[j], z[j + 2], acc);
-                    if (j >= 2) acc = fma(t2[j - 2], z[j - 2], acc);
-                    if (j < F2_NBMAX && j < P.nbT) {
-                        const double *sb = P.Trow + (size_t)j * 3 * m + k;
+                    if (i < NBI && jj + par < P.nbT) {
+                        const double *sb = P.Trow + (size_t)(jj + par) * 3 * m + k;
                         acc = fma(__ldg(sb), h0, acc);
                         acc = fma(__ldg(sb + m), h1, acc);
                         acc = fma(__ldg(sb + 2 * m), h2, acc);
                     }
-                    if (active && (j <= JSAFE || j < q)) *xo = fma(P.gamma, fq[u], acc);
-                    xo += m;
+                    if (active && (jj + NPAR - 1 <= JSAFE || jj + par < q)) *xo = fma(P.gamma, fq[u], acc);
+                    xo += xs;
                 }
             }
             __syncthreads();
+            if (useF && tid == 0) {
+                // every warp is past the product loop: the slot of the last chunk can be refilled without waiting
+                const int ps = fslot == 0 ? P.nf - 1 : fslot - 1;
+                const int64_t fnext = it * NCH + (NCH - 1) + P.nf;
+                if (fnext < nfch) f2_issue_fchunk(P, ffull, fring, fbase + (fnext / NCH) * fstep, (int)(fnext % NCH), ps);
+            }
             for (int i = tid; i < nh; i += nthr) {
                 double acc = P.TAd[i] * Hs[i];
                 if (i + 1 < nh) acc = fma(P.TAu[i], Hs[i + 1], acc);
@@ -525,12 +603,8 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
 template <int ROWS>
 static f2_kernel_t f2_pick(int npar, int variant, bool mul) {
     if (npar == 2) {
-        if constexpr (ROWS >= 40) {
-            if (variant == 0) return k_fused2<ROWS, 2, 0, false, false>;
-            return k_fused2<ROWS, 2, 2, true, false>;
-        } else {
-            return nullptr;
-        }
+        if (variant == 0) return mul ? k_fused2<ROWS, 2, 0, false, true> : k_fused2<ROWS, 2, 0, false, false>;
+        return mul ? k_fused2<ROWS, 2, 2, true, true> : k_fused2<ROWS, 2, 2, true, false>;
     }
     if (variant == 0) return mul ? k_fused2<ROWS, 1, 0, false, true> : k_fused2<ROWS, 1, 0, false, false>;
     if (variant == 1) return mul ? k_fused2<ROWS, 1, 2, true, true> : k_fused2<ROWS, 1, 2, true, false>;

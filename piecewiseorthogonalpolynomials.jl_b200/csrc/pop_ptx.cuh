@@ -52,6 +52,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a contiguous global range (size a multiple of 16 B)
+__device__ __forceinline__ void l2_prefetch_bulk(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // shared::cluster address of `p` (an address in this CTA's shared window) in CTA `rank`
 __device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank) {
     uint32_t r;

@@ -322,7 +322,7 @@ extern "C" int pop_solve_mul_axpy(pop_ctx *ctx, const pop_arrowhead *U, const po
         POP_REQUIRE(gamma == 0.0 || (dF != nullptr && ldf >= U->n()), POP_ERR_DIM, "pop_solve_mul_axpy: F panel missing or too small");
     }
     if (nrhs == 0) return POP_OK;
-    if ((!Tm || gamma == 0.0 || !(ldf & 1)) && pop_fused2_supported(ctx, U, Tm, ldr, dR))
+    if ((!Tm || gamma == 0.0 || (!(ldf & 1) && !((uintptr_t)dF & 15))) && pop_fused2_supported(ctx, U, Tm, ldr, dR))
         return pop_launch_solve_fused2(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
     if (pop_fused_supported(ctx, U, Tm)) return pop_launch_solve_fused(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
     // staged fallback: solve, then R <- T*X + gamma*F through a scratch copy
