@@ -184,6 +184,30 @@ int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M
 int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt,
                    int nsteps, int dims, double *dU, int64_t ldu, int64_t nrhs);
 
+/* ---- multi-GPU 2D drivers: one process per GPU, X distributed by column blocks ------------------
+ * The x<->y switch between the row and column sweeps of examples/adi_poisson.jl:53-56 is a distributed
+ * transpose: one kernel transposes tiles through shared memory and stores them into the owning
+ * peer's buffer over NVLink (CUDA IPC mappings of library-owned buffers); device-side flags order
+ * the exchange.  Usage: every rank calls pop_dist_create, exchanges the handles of
+ * pop_dist_get_handle (pop_dist_handle_bytes each, rank order) by any host channel, then
+ * pop_dist_open.  Buffers: 0, 1 work panels, 2 F, 3 F^T (n x w_max, leading dimension pop_dist_ld). */
+typedef struct pop_dist pop_dist;
+int pop_dist_handle_bytes(void);
+int pop_dist_create(pop_ctx *ctx, int rank, int world, int64_t n, pop_dist **out);
+int pop_dist_get_handle(pop_dist *d, void *handle_out);
+int pop_dist_open(pop_dist *d, const void *all_handles);
+int pop_dist_destroy(pop_ctx *ctx, pop_dist *d);
+double *pop_dist_buffer(pop_dist *d, int which);
+int64_t pop_dist_ld(const pop_dist *d);
+int64_t pop_dist_lo(const pop_dist *d, int rank); /* first column of `rank` (rank == world: n) */
+/* dst_all <- src_all^T across the ranks (collective: every rank calls it in the same order) */
+int pop_dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int dst_which);
+/* ADI of examples/adi_poisson.jl:42-59 on the distributed matrix: dF_local = F[:, lo:hi] in,
+ * dX_local = X[:, lo:hi] out (device pointers, column-major). */
+int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhead *K, const pop_arrowhead *M,
+                         const double *dF_local, int64_t ldf, double *dX_local, int64_t ldx, double a,
+                         double b, double c, double dd, double tol, int J);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,16 @@ _PROTOS = {
     "pop_solve_host": (C.c_int, [vp, vp, C.c_int, vp, i64, i64, C.c_int]),
     "pop_solve_shift_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, vp, i64, i64, i64, C.c_int]),
     "pop_solve_mul_axpy": (C.c_int, [vp, vp, vp, C.c_double, vp, i64, vp, i64, i64]),
+    "pop_dist_handle_bytes": (C.c_int, []),
+    "pop_dist_create": (C.c_int, [vp, C.c_int, C.c_int, i64, C.POINTER(vp)]),
+    "pop_dist_get_handle": (C.c_int, [vp, vp]),
+    "pop_dist_open": (C.c_int, [vp, vp]),
+    "pop_dist_destroy": (C.c_int, [vp, vp]),
+    "pop_dist_buffer": (vp, [vp, C.c_int]),
+    "pop_dist_ld": (i64, [vp]),
+    "pop_dist_lo": (i64, [vp, C.c_int]),
+    "pop_dist_transpose": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "pop_adi_poisson_dist": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "pop_transpose": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
     "pop_adi_num_iterations": (C.c_int, [C.c_double] * 5),
     "pop_adi_shifts": (C.c_int, [C.c_int] + [C.c_double] * 4 + [vp, vp]),

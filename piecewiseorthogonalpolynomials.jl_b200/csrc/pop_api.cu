@@ -50,6 +50,14 @@ extern "C" int pop_create(pop_ctx **out, int device, void *stream) {
     }
     POP_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     POP_CUDA(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    {   // keep freed stream-ordered allocations in the pool (handles and driver workspaces are recycled)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     POP_CUDA(cudaMalloc(&ctx->d_info, 4096 * sizeof(int)));
     POP_CUDA(cudaMallocHost(&ctx->h_info, 4096 * sizeof(int)));
     for (int i = 0; i < 2; ++i) POP_CUDA(cudaStreamCreateWithFlags(&ctx->s_copy[i], cudaStreamNonBlocking));
@@ -148,7 +156,8 @@ int pop_alloc_handles(pop_ctx *ctx, const pop_desc &d, int mD, int count, pop_ar
     ArrowSizes s = pop_sizes(d, mD);
     size_t bytes = std::max<size_t>(s.total, 2) * sizeof(double) * (size_t)count;
     pop_slab *slab = new pop_slab();
-    cudaError_t e = cudaMalloc(&slab->dptr, bytes);
+    // stream-ordered pool allocation: the ADI drivers create and drop 4J small handles per solve
+    cudaError_t e = cudaMallocAsync(&slab->dptr, bytes, ctx->stream);
     if (e != cudaSuccess) {
         delete slab;
         pop_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
@@ -156,7 +165,7 @@ int pop_alloc_handles(pop_ctx *ctx, const pop_desc &d, int mD, int count, pop_ar
     }
     e = cudaMemsetAsync(slab->dptr, 0, bytes, ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(slab->dptr);
+        cudaFreeAsync(slab->dptr, ctx->stream);
         delete slab;
         pop_set_error("memset failed: %s", cudaGetErrorString(e));
         return POP_ERR_CUDA;
@@ -316,8 +325,12 @@ extern "C" int pop_arrowhead_download(pop_ctx *ctx, const pop_arrowhead *A, int 
 extern "C" int pop_arrowhead_free(pop_ctx *ctx, pop_arrowhead *A) {
     if (!A) return POP_OK;
     if (A->slab && --A->slab->refs == 0) {
-        if (ctx) cudaStreamSynchronize(ctx->stream);
-        cudaFree(A->slab->dptr);
+        if (ctx) {
+            cudaFreeAsync(A->slab->dptr, ctx->stream);   // ordered after the kernels that still use it
+        } else {
+            cudaDeviceSynchronize();
+            cudaFree(A->slab->dptr);
+        }
         delete A->slab;
     }
     delete A;

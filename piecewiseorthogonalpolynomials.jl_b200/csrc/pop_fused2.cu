@@ -192,6 +192,8 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
     }
     POP_REQUIRE(!(T && gamma != 0.0) || (F && !(ldf & 1) && !((uintptr_t)F & 15)), POP_ERR_DIM,
                 "fused solve+product needs an even leading dimension and a 16-byte aligned F panel");
+    p.stagger_ns = 0;
+    if (const char *e = getenv("POP_F2_STAGGER_NS")) p.stagger_ns = atoi(e);
     p.gamma = gamma;
     p.F = F ? F : X;
     p.ldf = F ? ldf : ldx;
@@ -211,6 +213,28 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (p.cs > 1) {
+        // persistent clusters: never launch more than can be resident at once (GPC boundaries strand a few
+        // SMs for cluster sizes that do not divide the GPC), a second wave would serialise whole columns
+        int maxcl = 0;
+        if (cudaOccupancyMaxActiveClusters(&maxcl, pl.kern, &cfg) == cudaSuccess && maxcl >= 1) {
+            nclusters = std::min<int64_t>(nclusters, maxcl);
+            cfg.gridDim = dim3((unsigned)(nclusters * p.cs));
+        }
+        cudaGetLastError();
+    }
+    if (const char *e = getenv("POP_F2_DEBUG")) {
+        if (atoi(e)) {
+            int occ_blocks = -1, occ_clusters = -1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, pl.kern, pl.threads, pl.smem);
+            cudaOccupancyMaxActiveClusters(&occ_clusters, pl.kern, &cfg);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, pl.kern);
+            fprintf(stderr, "[pop_f2] rows=%d npar=%d variant=%d mul=%d cs=%d threads=%d regs=%d smem=%zu plan-occ=%d  occupancy: %d blocks/SM, %d clusters; grid=%u nf=%d\n",
+                    pl.rows, pl.npar, pl.variant, T != nullptr, p.cs, pl.threads, fa.numRegs, pl.smem, pl.occ, occ_blocks, occ_clusters, cfg.gridDim.x, p.nf);
+            cudaGetLastError();
+        }
+    }
     POP_CUDA(cudaLaunchKernelEx(&cfg, pl.kern, p));
     ctx->launches++;
     return POP_OK;

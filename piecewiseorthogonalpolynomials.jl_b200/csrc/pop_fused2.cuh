@@ -29,6 +29,7 @@ struct F2Params {
     double *X;
     int64_t ldx, nrhs;
     // plan
+    int stagger_ns;        // start-up offset between clusters (de-phases the clusters' memory bursts)
     int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap, nf;   // nf: slots of the F ring (fused product)
     int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_ring, o_fring;   // offsets in doubles
 };
@@ -307,6 +308,14 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         }
         cluster_arrive();
         cluster_wait();
+    }
+    if (P.stagger_ns > 0) {
+        // clusters would otherwise run in phase (same work, same start): all loading, then all in the hat
+        // scans, then all storing.  Offsetting their starts spreads the HBM traffic over the column period.
+        const unsigned ns = (unsigned)((c_first % 16) * (int64_t)P.stagger_ns / 16);
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)ns * 2) {
+        }
     }
     // The ring holds exactly one column: chunk c (counted from the top of the degree chain) lives in
     // slot c and its mbarrier phase is the parity of the local column number.  Warp w issues chunk w.

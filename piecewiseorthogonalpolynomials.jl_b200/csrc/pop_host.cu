@@ -260,7 +260,7 @@ extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_a
     }
     const int64_t ld = (n + 1) & ~(int64_t)1;
     double *buf = nullptr;
-    cudaError_t e = cudaMalloc(&buf, (size_t)ld * n * 3 * sizeof(double));
+    cudaError_t e = cudaMallocAsync(&buf, (size_t)ld * n * 3 * sizeof(double), ctx->stream);
     if (e != cudaSuccess) {
         free_handles(ctx, fac); free_handles(ctx, top);
         pop_set_error("pop_adi_poisson: %zu bytes of workspace: %s", (size_t)ld * n * 3 * 8, cudaGetErrorString(e));
@@ -287,10 +287,10 @@ extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_a
         e = cudaMemcpy2DAsync(dX, ldx * 8, V, ld * 8, n * 8, n, cudaMemcpyDeviceToDevice, ctx->stream);
         if (e != cudaSuccess) { pop_set_error("pop_adi_poisson: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
     } while (0);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(buf);
+    cudaFreeAsync(buf, ctx->stream);
     free_handles(ctx, fac);
     free_handles(ctx, top);
+    cudaStreamSynchronize(ctx->stream);
     return rc;
 }
 

@@ -133,9 +133,10 @@ class DistTranspose:
     def __call__(self, src, dst):
         """src, dst: column-major (n x w) CUDA tensors (views with stride(0) == 1)."""
         import torch
-        ps, pd = _Panel(src, False), _Panel(dst, True)
-        if self.ctx is not None and src.is_cuda:
-            _bind_stream(self.ctx)
+        if src.is_cuda:
+            ps = _Panel(src, False)
+            if self.ctx is not None:
+                _bind_stream(self.ctx)
         off = 0
         for s, (lo, hi) in enumerate(self.bounds):
             rows = hi - lo
@@ -159,6 +160,87 @@ class DistTranspose:
             dst[lo:hi, :].copy_(tile)
             off += rows * self.w
         return dst
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, rows, cols, ld):
+        self.__cuda_array_interface__ = {"shape": (cols, rows), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                         "strides": (ld * 8, 8)}
+
+
+class DistMatrix:
+    """n x n matrix distributed by column blocks over the ranks of a torch.distributed group, with the
+    x<->y switch done by the library's fused transpose+exchange kernel over NVLink peer memory
+    (csrc/pop_dist.cu).  One process per GPU; the CUDA IPC handles of the library-owned buffers are
+    exchanged once through the process group (all_gather_object)."""
+
+    def __init__(self, n, ctx, group=None):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.n = int(n)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lib = L.lib()
+        h = C.c_void_p()
+        L.check(lib.pop_dist_create(ctx.handle, self.rank, self.world, self.n, C.byref(h)), "pop_dist_create")
+        self._h = h
+        if self.world > 1:
+            nb = lib.pop_dist_handle_bytes()
+            mine = C.create_string_buffer(nb)
+            L.check(lib.pop_dist_get_handle(h, mine), "pop_dist_get_handle")
+            allh = [None] * self.world
+            dist.all_gather_object(allh, bytes(mine.raw), group=group)
+            blob = C.create_string_buffer(b"".join(allh), nb * self.world)
+            L.check(lib.pop_dist_open(h, blob), "pop_dist_open")
+            dist.barrier(group=group)
+        self.ld = int(lib.pop_dist_ld(h))
+        self.lo = int(lib.pop_dist_lo(h, self.rank))
+        self.hi = int(lib.pop_dist_lo(h, self.rank + 1))
+        self.w = self.hi - self.lo
+
+    def buffer(self, which):
+        """Column-major (n x w) torch view of local buffer `which` (0, 1 work panels, 2 F, 3 F^T)."""
+        import torch
+        ptr = L.lib().pop_dist_buffer(self._h, int(which))
+        t = torch.as_tensor(_DevView(ptr, self.n, self.w, self.ld), device=f"cuda:{self.ctx.device}")
+        return t.t()
+
+    def transpose(self, src, dst):
+        _bind_stream(self.ctx)
+        L.check(L.lib().pop_dist_transpose(self.ctx.handle, self._h, int(src), int(dst)), "pop_dist_transpose")
+
+    def close(self):
+        if self._h is not None:
+            L.lib().pop_dist_destroy(self.ctx.handle, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def adi_poisson_p2p(M, K, F_local, a, b, c=None, d=None, tol=1e-15, J=0, grid: "DistMatrix" = None, group=None):
+    """Multi-GPU ADI with the fused transpose+exchange kernel.  F_local = F[:, lo:hi] (column-major CUDA
+    tensor, n x w); returns X[:, lo:hi].  Shift computation and the 2J small factorisations are replicated."""
+    Mb, Kb = _base(M), _base(K)
+    ctx = Mb.ctx
+    c = -b if c is None else c
+    d = -a if d is None else d
+    own = grid is None
+    if own:
+        grid = DistMatrix(Mb.n, ctx, group=group)
+    pf = _Panel(F_local, False)
+    X = _new_like(F_local, tuple(F_local.shape))
+    px = _Panel(X, True)
+    _bind_stream(ctx)
+    L.check(L.lib().pop_adi_poisson_dist(ctx.handle, grid._h, Kb._h, Mb._h, pf.ptr, pf.ld, px.ptr, px.ld, a, b, c, d, tol, int(J)), "ADI (distributed)")
+    if own:
+        grid.close()
+    return X
 
 
 def adi_poisson_distributed(M, K, F_local, Ft_local, a, b, c=None, d=None, tol=1e-15, J=0, group=None):
