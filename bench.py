@@ -114,14 +114,25 @@ def cpu_rate(CO, U, ncols, reps=1):
     return n * ncols / best, best
 
 
-def cpu_baseline_sample():
+def cpu_baseline_sample(seconds=12.0):
+    """The C/OpenMP restatement on the box's host cores: the full 4096-column panel, repeated for ~12 s."""
     O, CO, U = oracle_problem()
     cpu_rate(CO, U, 32)                                   # warm up threads / page in
-    r, dt = cpu_rate(CO, U, 128)
-    ncols = int(min(4096, max(128, 12.0 * r / U.n)))     # ~12 s of CPU work
-    r, dt = cpu_rate(CO, U, ncols)
-    return {"value": r, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
-            "sample": f"{ncols} of {CFG['nrhs']} columns of the same workload, C/OpenMP restatement of src/arrowhead.jl:425-486 (oracle/pop_oracle.c), {dt:.2f} s"}
+    n, ncols = U.n, CFG["nrhs"]
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.standard_normal((n, ncols)))
+    Y = X.copy(order="F")
+    CO.solve(U, Y)
+    reps, t = 0, 0.0
+    while t < seconds:
+        np.copyto(Y, X)
+        t0 = time.perf_counter()
+        CO.solve(U, Y)
+        t += time.perf_counter() - t0
+        reps += 1
+    return {"value": n * ncols * reps / t, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
+            "sample": f"all {ncols} columns of the same workload solved {reps} times ({t:.1f} s of CPU work), C/OpenMP restatement of "
+                      f"src/arrowhead.jl:425-486 (oracle/pop_oracle.c), column-parallel over {CO.num_threads()} threads"}
 
 
 def run_reference(args, rank):
@@ -174,11 +185,12 @@ def adi_case(P, torch, dist, rank, world, dev):
     ld = (n + 1) & ~1
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     F = torch.randn((w, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
-    Ft = torch.randn((w, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
-    out = {"workload": "BASELINE config 4: 2D ADI Poisson, DirichletPolynomial m=128, p=64 (n=8191), synthetic F", "n": n, "J": J}
+    out = {"workload": "BASELINE config 4: 2D ADI Poisson, DirichletPolynomial m=128, p=64 (n=8191), synthetic F; X by column blocks over the "
+                       "GPUs, x<->y switch by the fused transpose+exchange kernel over NVLink peer memory", "n": n, "J": J}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     times = []
-    for it in range(2):
+    grid = P.DistMatrix(n, M.data.ctx) if world > 1 else None
+    for it in range(3):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -186,10 +198,12 @@ def adi_case(P, torch, dist, rank, world, dev):
         if world == 1:
             P.adi_poisson(M, K, F, a, b, J=J)
         else:
-            P.adi_poisson_distributed(M, K, F, Ft, a, b, J=J)
+            P.adi_poisson_p2p(M, K, F, a, b, J=J, grid=grid)
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1) * 1e-3)
+    if grid is not None:
+        grid.close()
     t = torch.tensor([times[-1]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -197,7 +211,42 @@ def adi_case(P, torch, dist, rank, world, dev):
     out["s_per_solve"] = s
     out["unknown_rhs_per_s"] = 2.0 * J * n * n / s
     out["hbm_gbs_per_gpu_algorithmic"] = 48.0 * n * n * J / world / s / 1e9
+    out["note"] = "48 B/entry/iteration = two fused half steps (read R, read F, write R'); the transposes between them move another 32 B/entry/iteration"
     return out
+
+
+def heat_case(P, torch, dist, rank, world, dev):
+    """BASELINE config 5: 2D heat, factored backward Euler, m=256, p=64 (n=16383), 100 steps, one factorisation."""
+    m, N, nsteps = 256, 64, 100
+    Q = P.DirichletPolynomial(np.linspace(-1, 1, m + 1))
+    KR = P.Block.oneto(N)
+    M = P.grammatrix(Q)[KR, KR]
+    K = -P.weaklaplacian(Q)[KR, KR]
+    n = M.n
+    lo, hi = P.shard_bounds(n, world)[rank]
+    w = hi - lo
+    ld = (n + 1) & ~1
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    U = torch.randn((w, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
+    grid = P.DistMatrix(n, M.data.ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        P.heat_steps_p2p(M, K, U, 1e-3, nsteps, grid=grid)
+        e1.record()
+        torch.cuda.synchronize()
+    grid.close()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t.item())
+    return {"workload": "BASELINE config 5: 2D heat, factored backward Euler (2D extension of examples/heat.jl:58-63), Dirichlet m=256, p=64 "
+                        "(n=16383), 100 steps, one reused factorisation", "n": n, "steps": nsteps, "s_per_100_steps": s,
+            "unknown_rhs_per_s": 2.0 * nsteps * n * n / s, "hbm_gbs_per_gpu_algorithmic": 32.0 * n * n * nsteps / world / s / 1e9,
+            "note": "32 B/entry/step = two fused solve+product passes; 2 distributed transposes per call"}
 
 
 def main():
@@ -323,12 +372,16 @@ def main():
                "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps, "api": "pop_solve_host (ldiv(F, numpy array)), pinned host panel, chunked H2D/compute/D2H overlap"}
         del hB, hX
 
-    adi = None
+    adi = heat = None
     if not args.no_adi:
         try:
             adi = adi_case(P, torch, dist, rank, world, dev)
         except Exception as ex:  # keep the headline line even if the secondary case fails
             adi = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            heat = heat_case(P, torch, dist, rank, world, dev)
+        except Exception as ex:
+            heat = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -338,8 +391,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "kernel": "k_fused_solve<2,false>", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
-                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi}
+                             "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, cluster of 2 CTAs per column)", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
+                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         else:

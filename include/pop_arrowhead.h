@@ -208,6 +208,11 @@ int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhead *K, cons
                          const double *dF_local, int64_t ldf, double *dX_local, int64_t ldx, double a,
                          double b, double c, double dd, double tol, int J);
 
+/* nsteps of backward Euler U <- S^{-1} M U M S^{-1}, S = M + dt K, on the distributed n x n field
+ * (2D extension of examples/heat.jl:58-63); dU_local = U[:, lo:hi] in place. */
+int pop_heat_steps_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhead *K, const pop_arrowhead *M, double dt,
+                        int nsteps, double *dU_local, int64_t ldu);
+
 #ifdef __cplusplus
 }
 #endif

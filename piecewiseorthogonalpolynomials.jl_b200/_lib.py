@@ -92,6 +92,7 @@ _PROTOS = {
     "pop_dist_lo": (i64, [vp, C.c_int]),
     "pop_dist_transpose": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "pop_adi_poisson_dist": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "pop_heat_steps_dist": (C.c_int, [vp, vp, vp, vp, C.c_double, C.c_int, vp, i64]),
     "pop_transpose": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
     "pop_adi_num_iterations": (C.c_int, [C.c_double] * 5),
     "pop_adi_shifts": (C.c_int, [C.c_int] + [C.c_double] * 4 + [vp, vp]),

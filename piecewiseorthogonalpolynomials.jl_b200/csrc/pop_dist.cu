@@ -302,6 +302,45 @@ extern "C" int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhe
     return rc;
 }
 
+// ------------------------------------------------------------------------------------
+// distributed 2D heat stepping (2D extension of examples/heat.jl:58-63): nsteps of
+// U <- S^{-1} M U M S^{-1}, S = M + dt K, on the column-block distributed field.  Column and row
+// operators commute: all column sweeps are local, then one distributed transpose, the same sweeps
+// again, and one transpose back -- 2 exchanges per call.
+// ------------------------------------------------------------------------------------
+extern "C" int pop_heat_steps_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhead *K, const pop_arrowhead *M, double dt, int nsteps,
+                                   double *dU_local, int64_t ldu) {
+    POP_REQUIRE(ctx && d && K && M && dU_local, POP_ERR_ARG, "pop_heat_steps_dist: null argument");
+    const int64_t n = K->n();
+    POP_REQUIRE(n == d->n && ldu >= n, POP_ERR_DIM, "pop_heat_steps_dist: DimensionMismatch");
+    POP_REQUIRE(nsteps >= 0 && dt > 0, POP_ERR_ARG, "pop_heat_steps_dist: need nsteps >= 0, dt > 0");
+    if (nsteps == 0) return POP_OK;
+    pop_arrowhead *U = nullptr;
+    double one = 1.0;
+    int rc = pop_revchol_shifted_batch(ctx, M, K, &one, &dt, 1, &U, nullptr);   // S = M + dt*K
+    if (rc) return rc;
+    const int64_t ld = d->ld;
+    const int64_t w = d->lo[d->rank + 1] - d->lo[d->rank];
+    MulView mv;
+    pop_make_mulview(M, POP_SYM_UPPER, 0, &mv);
+    cudaError_t e = cudaMemcpy2DAsync(d->buf[0], ld * 8, dU_local, ldu * 8, n * 8, w, cudaMemcpyDeviceToDevice, ctx->stream);
+    int cur = 0;
+    for (int pass = 0; pass < 2 && rc == POP_OK && e == cudaSuccess; ++pass) {
+        double *src = d->buf[cur], *dst = d->buf[cur ^ 1];
+        if ((rc = pop_launch_mul(ctx, mv, 1.0, src, 1, ld, 0.0, dst, 1, ld, w))) break;
+        for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, M, 0.0, dst, ld, dst, ld, w);
+        if (rc) break;
+        if ((rc = pop_solve(ctx, U, POP_LEFT, dst, ld, w, POP_SOLVE_AUTO))) break;
+        if ((rc = pop_dist_transpose(ctx, d, cur ^ 1, cur))) break;     // back into buf[cur], transposed
+    }
+    if (rc == POP_OK && e == cudaSuccess)
+        e = cudaMemcpy2DAsync(dU_local, ldu * 8, d->buf[cur], ld * 8, n * 8, w, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (rc == POP_OK && e != cudaSuccess) { pop_set_error("pop_heat_steps_dist: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
+    cudaStreamSynchronize(ctx->stream);
+    pop_arrowhead_free(ctx, U);
+    return rc;
+}
+
 __global__ void k_scale(double *x, int64_t n, double s) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= s;
 }

@@ -326,11 +326,16 @@ extern "C" int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_ar
             e = cudaMemcpy2DAsync(dU, ldu * 8, buf, ld * 8, n * 8, nrhs, cudaMemcpyDeviceToDevice, ctx->stream);
             if (e != cudaSuccess) { pop_set_error("pop_heat_steps: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
         } else {
-            // U <- S^{-1} M U M S^{-1}: apply G = S^{-1} M along columns, transpose, again, transpose
+            // nsteps of U <- S^{-1} M U M S^{-1} = G^nsteps U (G^T)^nsteps with G = S^{-1} M: the column operator and the
+            // row operator commute, so all nsteps column sweeps run first, then ONE transpose, all row sweeps, and
+            // one transpose back (2 transposes per call instead of 2 per step).  G^k = S^{-1} (M S^{-1})^{k-1} M: one product,
+            // k-1 fused solve+product passes (16 B/entry each), one solve.
             double *cur = dU; int64_t ldc = ldu;
             double *oth = buf; int64_t ldo = ld;
-            for (int s = 0; s < 2 * nsteps && rc == POP_OK; ++s) {
+            for (int pass = 0; pass < 2 && rc == POP_OK; ++pass) {
                 if ((rc = pop_launch_mul(ctx, mv, 1.0, cur, 1, ldc, 0.0, oth, 1, ldo, n))) break;
+                for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, M, 0.0, oth, ldo, oth, ldo, n);
+                if (rc) break;
                 if ((rc = pop_solve(ctx, U, POP_LEFT, oth, ldo, n, POP_SOLVE_AUTO))) break;
                 if ((rc = pop_transpose(ctx, oth, ldo, n, n, cur, ldc))) break;
             }

@@ -243,6 +243,21 @@ def adi_poisson_p2p(M, K, F_local, a, b, c=None, d=None, tol=1e-15, J=0, grid: "
     return X
 
 
+def heat_steps_p2p(M, K, U_local, dt, nsteps, grid: "DistMatrix" = None, group=None):
+    """In place: nsteps of the factored 2D backward Euler on the column-block distributed field U_local = U[:, lo:hi]."""
+    Mb, Kb = _base(M), _base(K)
+    ctx = Mb.ctx
+    own = grid is None
+    if own:
+        grid = DistMatrix(Mb.n, ctx, group=group)
+    p = _Panel(U_local, True)
+    _bind_stream(ctx)
+    L.check(L.lib().pop_heat_steps_dist(ctx.handle, grid._h, Kb._h, Mb._h, float(dt), int(nsteps), p.ptr, p.ld), "heat (distributed)")
+    if own:
+        grid.close()
+    return U_local
+
+
 def adi_poisson_distributed(M, K, F_local, Ft_local, a, b, c=None, d=None, tol=1e-15, J=0, group=None):
     """Multi-GPU ADI.  F_local = F[:, lo:hi], Ft_local = F^T[:, lo:hi] (column blocks of F and of its
     transpose, column-major CUDA tensors).  Returns X[:, lo:hi].  Same operator sequence as
