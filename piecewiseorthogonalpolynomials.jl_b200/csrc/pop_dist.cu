@@ -151,6 +151,40 @@ __global__ void __launch_bounds__(256) k_dist_transpose(const double *__restrict
     }
 }
 
+// PULL variant: dst_me[(lo_s + c) + (rr - lo_me) * ld] = src_s[rr + c * ld] for rr in [lo_me, hi_me), c in [0, w_s):
+// blockIdx.z = source rank; the 256 B runs along rr are read from the peer's buffer over NVLink, the
+// transposed 512 B runs are written locally.
+__global__ void __launch_bounds__(256) k_dist_transpose_pull(double *__restrict__ dst, int64_t ld, int64_t lome, int64_t hime, DistPeers peers) {
+    __shared__ double tile[64][33];
+    const int s = blockIdx.z;
+    const int64_t los = peers.lo[s], ws = peers.lo[s + 1] - los;
+    const int64_t r0 = lome + (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 64;
+    if (r0 >= hime || c0 >= ws) return;
+    const double *__restrict__ src = peers.dst[s];
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t rr = r0 + threadIdx.x, c = c0 + threadIdx.y + 8 * i;
+        v[i] = (rr < hime && c < ws) ? src[c * ld + rr] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[threadIdx.y + 8 * i][threadIdx.x] = v[i];
+    __syncthreads();
+    const bool vec = ((los + c0) & 1) == 0;
+    for (int rrl = threadIdx.y; rrl < 32; rrl += 8) {
+        const int64_t rr = r0 + rrl;
+        if (rr >= hime) continue;
+        double *drow = dst + (rr - lome) * ld + los + c0;
+        const int cl = 2 * threadIdx.x;
+        if (vec && c0 + cl + 1 < ws) {
+            *reinterpret_cast<double2 *>(drow + cl) = make_double2(tile[cl][rrl], tile[cl + 1][rrl]);
+        } else {
+            if (c0 + cl < ws) drow[cl] = tile[cl][rrl];
+            if (c0 + cl + 1 < ws) drow[cl + 1] = tile[cl + 1][rrl];
+        }
+    }
+}
+
 // after the transpose kernel has completed: tell every peer that my tiles of epoch `ep` have landed
 __global__ void k_dist_signal(DistFlags peers, int world, int me, unsigned long long ep) {
     const int r = threadIdx.x;
@@ -185,19 +219,40 @@ extern "C" int pop_dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int 
     POP_REQUIRE(src_which >= 0 && src_which < POP_DIST_NBUF && dst_which >= 0 && dst_which < POP_DIST_NBUF && src_which != dst_which,
                 POP_ERR_ARG, "pop_dist_transpose: bad buffer ids");
     DistPeers peers;
-    for (int r = 0; r < d->world; ++r) peers.dst[r] = d->peer_buf[r][dst_which];
     for (int r = 0; r <= d->world; ++r) peers.lo[r] = d->lo[r];
     const int64_t wme = d->lo[d->rank + 1] - d->lo[d->rank];
-    dim3 block(32, 8), grid((unsigned)((d->wmax + 31) / 32), (unsigned)((wme + 63) / 64), (unsigned)d->world);
-    k_dist_transpose<<<grid, block, 0, ctx->stream>>>(d->buf[src_which], d->ld, wme, d->lo[d->rank], peers);
-    ctx->launches++;
-    if (d->world > 1) {
+    static int pull = -1;
+    if (pull < 0) {
+        const char *e = getenv("POP_DIST_PULL");
+        pull = e ? atoi(e) : 0;
+    }
+    dim3 block(32, 8);
+    if (!pull || d->world == 1) {
+        // PUSH: transpose my tiles and store them into the owners' buffers; then tell everybody and wait for everybody
+        for (int r = 0; r < d->world; ++r) peers.dst[r] = d->peer_buf[r][dst_which];
+        dim3 grid((unsigned)((d->wmax + 31) / 32), (unsigned)((wme + 63) / 64), (unsigned)d->world);
+        k_dist_transpose<<<grid, block, 0, ctx->stream>>>(d->buf[src_which], d->ld, wme, d->lo[d->rank], peers);
+        ctx->launches++;
+        if (d->world > 1) {
+            const unsigned long long ep = ++d->epoch;
+            DistFlags fl = {};
+            for (int r = 0; r < d->world; ++r) fl.f[r] = d->peer_flags[r];
+            k_dist_signal<<<1, 32, 0, ctx->stream>>>(fl, d->world, d->rank, ep);
+            k_dist_wait<<<1, 32, 0, ctx->stream>>>(d->flags, d->world, ep);
+            ctx->launches += 2;
+        }
+    } else {
+        // PULL: tell everybody my source panel is complete, wait for everybody's, then read the peers' tiles.
+        // A peer's "ready" of the next exchange also says it has finished reading my panel of this one.
         const unsigned long long ep = ++d->epoch;
         DistFlags fl = {};
         for (int r = 0; r < d->world; ++r) fl.f[r] = d->peer_flags[r];
         k_dist_signal<<<1, 32, 0, ctx->stream>>>(fl, d->world, d->rank, ep);
         k_dist_wait<<<1, 32, 0, ctx->stream>>>(d->flags, d->world, ep);
-        ctx->launches += 2;
+        for (int r = 0; r < d->world; ++r) peers.dst[r] = d->peer_buf[r][src_which];
+        dim3 grid((unsigned)((wme + 31) / 32), (unsigned)((d->wmax + 63) / 64), (unsigned)d->world);
+        k_dist_transpose_pull<<<grid, block, 0, ctx->stream>>>(d->buf[dst_which], d->ld, d->lo[d->rank], d->lo[d->rank + 1], peers);
+        ctx->launches += 3;
     }
     POP_CUDA(cudaGetLastError());
     return POP_OK;
