@@ -30,6 +30,16 @@ UNIT = "unknown*RHS/s"
 BYTES_PER_UNIT = 16.0   # one read + one write of X per unknown*RHS
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the headline kernel, from the committed
+    ncu --set full capture of this same command (profiles/r1_bench_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_bench_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -390,7 +400,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, cluster of 2 CTAs per column)", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
                 "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat}
         if not args.no_cpu_baseline and world == 1:
