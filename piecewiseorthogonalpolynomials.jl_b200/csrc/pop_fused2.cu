@@ -97,8 +97,10 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         cudaGetLastError();
         return pl;
     }
+    F2Plan first = {};
     for (int cs = 1; cs <= 8; cs *= 2) {
         if (T && cs > 1) break;
+        if (first.ok && cs != 2 * first.p.cs) break;
         if (force_cs && cs != force_cs) continue;
         const int mloc = (d.m + cs - 1) / cs;
         if ((int64_t)(cs - 1) * mloc >= d.m) continue;
@@ -150,9 +152,21 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
             found = true;
         }
         if (!found) continue;
+        if (pl.ok) {
+            // second candidate (twice the cluster size): keep it only if it doubles the CTAs per SM
+            if (pl.occ >= 2) return pl;
+            return first;
+        }
         pl.ok = true;
+        // a full-size block (512 threads x 128 registers, one CTA per SM) leaves an SM with a single phase
+        // at a time; two half-size CTAs of a cluster twice as large interleave theirs (measured: cfg 2, +5 %)
+        if (!force_cs && !T && pl.occ == 1 && threads > 256 && cs < 8 && !(d.m & 1)) {
+            first = pl;
+            continue;
+        }
         break;
     }
+    if (first.ok && !(pl.ok && pl.occ >= 2 && pl.p.cs == 2 * first.p.cs)) return first;
     return pl;
 }
 
