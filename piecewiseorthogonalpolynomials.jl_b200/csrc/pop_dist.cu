@@ -124,9 +124,12 @@ extern "C" int64_t pop_dist_lo(const pop_dist *d, int r) { return (d && r >= 0 &
 // blockIdx.z = destination rank; tiles of 32 source rows x 64 source columns, 32x8 threads.  Reads are
 // 256 B runs along the source rows; writes are 512 B runs along the destination rows (16 B per lane
 // when the destination run is 16 B aligned), which is what the NVLink path to a peer likes.
-__global__ void __launch_bounds__(256) k_dist_transpose(const double *__restrict__ src, int64_t ld, int64_t wme, int64_t lome, DistPeers peers) {
+__global__ void __launch_bounds__(256) k_dist_transpose(const double *__restrict__ src, int64_t ld, int64_t wme, int64_t lome, DistPeers peers,
+                                                        int me, int world) {
     __shared__ double tile[64][33];
-    const int r = blockIdx.z;
+    // blocks are dispatched z-major: rotate the destinations so that at any moment the ranks write to
+    // DIFFERENT peers (no incast on one peer's ingress links while the others idle)
+    const int r = (blockIdx.z + me + 1) % world;
     const int64_t lor = peers.lo[r], hir = peers.lo[r + 1];
     const int64_t r0 = lor + (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 64;
     if (r0 >= hir) return;
@@ -154,9 +157,10 @@ __global__ void __launch_bounds__(256) k_dist_transpose(const double *__restrict
 // PULL variant: dst_me[(lo_s + c) + (rr - lo_me) * ld] = src_s[rr + c * ld] for rr in [lo_me, hi_me), c in [0, w_s):
 // blockIdx.z = source rank; the 256 B runs along rr are read from the peer's buffer over NVLink, the
 // transposed 512 B runs are written locally.
-__global__ void __launch_bounds__(256) k_dist_transpose_pull(double *__restrict__ dst, int64_t ld, int64_t lome, int64_t hime, DistPeers peers) {
+__global__ void __launch_bounds__(256) k_dist_transpose_pull(double *__restrict__ dst, int64_t ld, int64_t lome, int64_t hime, DistPeers peers,
+                                                             int me, int world) {
     __shared__ double tile[64][33];
-    const int s = blockIdx.z;
+    const int s = (blockIdx.z + me + 1) % world;
     const int64_t los = peers.lo[s], ws = peers.lo[s + 1] - los;
     const int64_t r0 = lome + (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 64;
     if (r0 >= hime || c0 >= ws) return;
@@ -231,7 +235,7 @@ extern "C" int pop_dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int 
         // PUSH: transpose my tiles and store them into the owners' buffers; then tell everybody and wait for everybody
         for (int r = 0; r < d->world; ++r) peers.dst[r] = d->peer_buf[r][dst_which];
         dim3 grid((unsigned)((d->wmax + 31) / 32), (unsigned)((wme + 63) / 64), (unsigned)d->world);
-        k_dist_transpose<<<grid, block, 0, ctx->stream>>>(d->buf[src_which], d->ld, wme, d->lo[d->rank], peers);
+        k_dist_transpose<<<grid, block, 0, ctx->stream>>>(d->buf[src_which], d->ld, wme, d->lo[d->rank], peers, d->rank, d->world);
         ctx->launches++;
         if (d->world > 1) {
             const unsigned long long ep = ++d->epoch;
@@ -251,7 +255,7 @@ extern "C" int pop_dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int 
         k_dist_wait<<<1, 32, 0, ctx->stream>>>(d->flags, d->world, ep);
         for (int r = 0; r < d->world; ++r) peers.dst[r] = d->peer_buf[r][src_which];
         dim3 grid((unsigned)((wme + 31) / 32), (unsigned)((d->wmax + 63) / 64), (unsigned)d->world);
-        k_dist_transpose_pull<<<grid, block, 0, ctx->stream>>>(d->buf[dst_which], d->ld, d->lo[d->rank], d->lo[d->rank + 1], peers);
+        k_dist_transpose_pull<<<grid, block, 0, ctx->stream>>>(d->buf[dst_which], d->ld, d->lo[d->rank], d->lo[d->rank + 1], peers, d->rank, d->world);
         ctx->launches += 3;
     }
     POP_CUDA(cudaGetLastError());
