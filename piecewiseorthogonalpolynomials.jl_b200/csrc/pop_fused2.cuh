@@ -233,12 +233,12 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     const int hA = k0, hB = rank == cs - 1 ? nh : min(nh, k0 + ml);   // my hats
     const int nhl = max(hB - hA, 0);
     const int nslots = P.nslots;
-    const int64_t ncl = gridDim.x / cs;
-    const int64_t c_first = blockIdx.x / cs;
-    const int64_t ncols = c_first < P.nrhs ? (P.nrhs - c_first + ncl - 1) / ncl : 0;   // columns of this cluster
+    const int ncl = gridDim.x / cs;
+    const int c_first = blockIdx.x / cs;
+    const int ncols = c_first < P.nrhs ? (int)((P.nrhs - c_first + ncl - 1) / ncl) : 0;   // columns of this cluster
     const int hA2 = hA & ~1;
     const uint32_t hbytes = (uint32_t)(((hB + 1) & ~1) - hA2) * 8u;
-    const int64_t colstep = ncl * P.ldx;
+    const int64_t colstep = (int64_t)ncl * P.ldx;
 
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     }
     // The ring holds exactly one column: chunk c (counted from the top of the degree chain) lives in
     // slot c and its mbarrier phase is the parity of the local column number.  Warp w issues chunk w.
-    const double *xbase = P.X + c_first * P.ldx;
-    const double *fbase = MUL ? P.F + c_first * P.ldf : nullptr;
-    const int64_t fstep = ncl * P.ldf;
+    const double *xbase = P.X + (int64_t)c_first * P.ldx;
+    const double *fbase = MUL ? P.F + (int64_t)c_first * P.ldf : nullptr;
+    const int64_t fstep = (int64_t)ncl * P.ldf;
     if (ncols > 0) {
         if (tid == 0) {
             mbar_expect_tx(hfull, hbytes);
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         }
         for (int c = warp; c < NCH; c += nw) f2_issue_chunk(P, full, ring, lane, k0, ml, xbase, c, c);
         if (MUL && P.gamma != 0.0 && tid == 0)
-            for (int f = 0; f < P.nf && f < ncols * NCH; ++f) f2_issue_fchunk(P, ffull, fring, fbase + (f / NCH) * fstep, f % NCH, f);
+            for (int f = 0; f < P.nf && f < (int64_t)ncols * NCH; ++f) f2_issue_fchunk(P, ffull, fring, fbase + (f / NCH) * fstep, f % NCH, f);
     }
     // F ring cursor: next chunk of the global F sequence (column-major over columns, chunks ascending)
     int fslot = 0;
@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     const double *sbk = P.Sb + k;
     const int expA = cs > 1 ? NPAR * 8 * ((rank > 0) + (rank < cs - 1)) : 0;
 
-    for (int64_t it = 0; it < ncols; ++it) {
-        double *xcol = P.X + (c_first + it * ncl) * P.ldx;
+    for (int it = 0; it < ncols; ++it) {
+        double *xcol = P.X + ((int64_t)c_first + (int64_t)it * ncl) * P.ldx;
         const int hb = (int)(it & 1);
         const uint32_t hph = (uint32_t)(it >> 1) & 1;
         double *Hs = Hb + (size_t)hb * P.hcap + 2 + (hA & 1);   // Hs[u] = hat hA + u; Hs[-1], Hs[nhl] hold the neighbours' hats
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         }
         if (MUL && P.gamma != 0.0 && tid == 32 % nthr) {
             // the part of this column's F that is not in the ring yet: pull it into L2 now
-            const double *fc = fbase + it * fstep;
+            const double *fc = fbase + (int64_t)it * fstep;
             for (int c = P.nf; c < NCH; ++c) {
                 const int64_t gs = ((int64_t)nh + (int64_t)c * G * m) & ~(int64_t)1;
                 const int nr = min(G, q - c * G);
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             // ---- fused product  r = T x + gamma f,  T = Symmetric(upper data); cs == 1: all hats are mine ----
             // NPAR == 2: rows j = 2i + par; T never couples j and j+1 there, so a thread needs only its own parity.
             const bool useF = P.gamma != 0.0;
-            const double *fcol = P.F + (c_first + it * ncl) * P.ldf;
+            const double *fcol = P.F + ((int64_t)c_first + (int64_t)it * ncl) * P.ldf;
             const double *t0 = tT + par, *t1 = tT + (JMAX + 2) + par, *t2 = tT + 2 * (JMAX + 2) + par;
             // the hat rows of the product read x of the coupled bubbles
 #pragma unroll
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             double *xo = xcol + nh + k + (NPAR == 2 ? (int64_t)par * m : 0);
             const int foff = el + par0 + (NPAR == 2 ? par * m : 0);
             const int fstride = NPAR * m;
-            const int64_t nfch = ncols * NCH;                 // F chunks of this cluster's sequence
+            const int64_t nfch = (int64_t)ncols * NCH;                 // F chunks of this cluster's sequence
 #pragma unroll
             for (int cch = 0; cch < NCH; ++cch) {
                 const int i0 = cch * BLK;
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                         const int ps = fslot == 0 ? P.nf - 1 : fslot - 1;
                         const uint32_t pph = fslot == 0 ? fph ^ 1 : fph;
                         mbar_wait(fempty + ps, pph);
-                        const int64_t fnext = it * NCH + (cch - 1) + P.nf;
+                        const int64_t fnext = (int64_t)it * NCH + (cch - 1) + P.nf;
                         if (lane == 0 && fnext < nfch) f2_issue_fchunk(P, ffull, fring, fbase + (fnext / NCH) * fstep, (int)(fnext % NCH), ps);
                     }
                     mbar_wait(ffull + fslot, fph);
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             if (useF && tid == 0) {
                 // every warp is past the product loop: the slot of the last chunk can be refilled without waiting
                 const int ps = fslot == 0 ? P.nf - 1 : fslot - 1;
-                const int64_t fnext = it * NCH + (NCH - 1) + P.nf;
+                const int64_t fnext = (int64_t)it * NCH + (NCH - 1) + P.nf;
                 if (fnext < nfch) f2_issue_fchunk(P, ffull, fring, fbase + (fnext / NCH) * fstep, (int)(fnext % NCH), ps);
             }
             for (int i = tid; i < nh; i += nthr) {
