@@ -248,6 +248,44 @@ def adi_case(P, torch, dist, rank, world, dev):
     return out
 
 
+def shifted_case(P, torch, dist, rank, world, dev):
+    """BASELINE config 3: Dirichlet m=256, p=128 (n=32767), 64 shifts sigma x 1024 RHS: batched shifted factor + solve.
+    The shifts are sharded over the ranks (independent systems, no collective)."""
+    m, N, nshift, nrhs = 256, 128, 64, 1024
+    Q = P.DirichletPolynomial(np.linspace(-1, 1, m + 1))
+    KR = P.Block.oneto(N)
+    M = P.grammatrix(Q)[KR, KR]
+    K = -P.weaklaplacian(Q)[KR, KR]
+    n = M.n
+    sig_all = np.logspace(np.log10(np.pi ** 2 / 4), 9, nshift)
+    mine = [i for i in range(nshift) if i % world == rank]
+    sig = sig_all[mine]
+    ld = (n + 1) & ~1
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    Xb = torch.randn((len(sig) * nrhs, ld), generator=g, dtype=torch.float64, device=dev)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for it in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        facs = P.reversecholesky_shifted(K, M, np.ones_like(sig), sig)
+        e1.record()
+        for i, Fi in enumerate(facs):
+            P.ldiv(Fi, Xb[i * nrhs:(i + 1) * nrhs].t()[:n], overwrite=True)
+        e2.record()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3, e1.elapsed_time(e2) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tf, ts = float(t[0]), float(t[1])
+    peak, _ = measured_peak()
+    gbs = 16.0 * n * nrhs * len(sig) / ts / 1e9
+    return {"workload": "BASELINE config 3: DirichletPolynomial m=256, p=128 (n=32767), 64 shifts sigma x 1024 RHS, batched shifted factor + solve; "
+                        "shifts sharded over the GPUs", "n": n, "nshift": nshift, "nrhs": nrhs, "factor_s": tf, "solve_s": ts,
+            "unknown_rhs_per_s": float(n) * nrhs * nshift / (tf + ts), "solve_gbs_per_gpu": gbs, "solve_frac_of_measured_hbm_peak": gbs / peak}
+
+
 def heat_case(P, torch, dist, rank, world, dev):
     """BASELINE config 5: 2D heat, factored backward Euler, m=256, p=64 (n=16383), 100 steps, one factorisation."""
     m, N, nsteps = 256, 64, 100
@@ -405,7 +443,7 @@ def main():
                "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps, "api": "pop_solve_host (ldiv(F, numpy array)), pinned host panel, chunked H2D/compute/D2H overlap"}
         del hB, hX
 
-    adi = heat = None
+    adi = heat = shifted = None
     if not args.no_adi:
         try:
             adi = adi_case(P, torch, dist, rank, world, dev)
@@ -415,6 +453,10 @@ def main():
             heat = heat_case(P, torch, dist, rank, world, dev)
         except Exception as ex:
             heat = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            shifted = shifted_case(P, torch, dist, rank, world, dev)
+        except Exception as ex:
+            shifted = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -424,8 +466,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                             "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, cluster of 2 CTAs per column)", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
-                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat}
+                             "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, one thread-block cluster per column)", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
+                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat, "shifted_batch": shifted}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         else:
