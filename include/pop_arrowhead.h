@@ -213,6 +213,29 @@ int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhead *K, cons
 int pop_heat_steps_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhead *K, const pop_arrowhead *M, double dt,
                         int nsteps, double *dU_local, int64_t ldu);
 
+/* ---- element-decomposed 2D drivers (csrc/pop_row.cu): X distributed over the GPUs by MESH ELEMENTS of
+ * the column direction.  Rank g holds the n x nloc panel of the columns of its elements (all degrees)
+ * and hats, in arrowhead order (pop_dd_column maps local -> global column).  F \ X and A*X
+ * (examples/adi_poisson.jl:55) are local; X / F and X*A (:54) run along rows with lanes over the rows
+ * and exchange only the hat-segment maps (O(n*world) doubles per half step) through peer memory.
+ * Set-up as pop_dist: create, exchange pop_dd_get_handle blobs (pop_dist_handle_bytes each), open. */
+typedef struct pop_dd pop_dd;
+int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, int q, pop_dd **out);
+int pop_dd_get_handle(pop_dd *d, void *handle_out);
+int pop_dd_open(pop_dd *d, const void *all_handles);
+int pop_dd_destroy(pop_ctx *ctx, pop_dd *d);
+int64_t pop_dd_nloc(const pop_dd *d);
+int64_t pop_dd_ld(const pop_dd *d);
+int64_t pop_dd_column(const pop_dd *d, int64_t local_column);
+/* rows of dR (n x nloc, leading dimension pop_dd_ld):  r <- T (S^{-1} r) + gamma f, S = U U^T, T = Symmetric(Tm)
+ * (Tm may be NULL: plain X / F); collective over the ranks. */
+int pop_dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, const pop_arrowhead *Tm, double gamma,
+                         const double *dF, int64_t ldf, double *dR, int64_t ldr);
+/* ADI of examples/adi_poisson.jl:42-59 without transposes; dF_local / dX_local are n x nloc panels */
+int pop_adi_poisson_dd(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *K, const pop_arrowhead *M, const double *dF_local,
+                       int64_t ldf, double *dX_local, int64_t ldx, double a, double b, double c, double dd,
+                       double tol, int J);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,5 +8,5 @@ from .arrowhead import (BBBArrowheadMatrix, LowerTriangular, ReverseCholesky, Sy
                         UnitUpperTriangular, UpperTriangular, ldiv, mul, rdiv, reversecholesky, reversecholesky_inplace,
                         reversecholesky_shifted)
 from .bases import Block, BlockRange, ContinuousPolynomial, DirichletPolynomial, LazyArrowhead, grammatrix, weaklaplacian
-from .drivers import (DistMatrix, DistTranspose, adi_poisson_p2p, heat_steps_p2p, adi_num_iterations, adi_poisson, adi_poisson_distributed, adi_shifts, heat_steps,
+from .drivers import (DistMatrix, ElementDecomposition, adi_poisson_dd, dd_columns, DistTranspose, adi_poisson_p2p, heat_steps_p2p, adi_num_iterations, adi_poisson, adi_poisson_distributed, adi_shifts, heat_steps,
                       shard_bounds, spectrum_bounds)

@@ -93,6 +93,15 @@ _PROTOS = {
     "pop_dist_transpose": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "pop_adi_poisson_dist": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "pop_heat_steps_dist": (C.c_int, [vp, vp, vp, vp, C.c_double, C.c_int, vp, i64]),
+    "pop_dd_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "pop_dd_get_handle": (C.c_int, [vp, vp]),
+    "pop_dd_open": (C.c_int, [vp, vp]),
+    "pop_dd_destroy": (C.c_int, [vp, vp]),
+    "pop_dd_nloc": (i64, [vp]),
+    "pop_dd_ld": (i64, [vp]),
+    "pop_dd_column": (i64, [vp, i64]),
+    "pop_dd_row_half_step": (C.c_int, [vp, vp, vp, vp, C.c_double, vp, i64, vp, i64]),
+    "pop_adi_poisson_dd": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "pop_transpose": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
     "pop_adi_num_iterations": (C.c_int, [C.c_double] * 5),
     "pop_adi_shifts": (C.c_int, [C.c_int] + [C.c_double] * 4 + [vp, vp]),

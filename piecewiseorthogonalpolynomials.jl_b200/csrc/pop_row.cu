@@ -1,0 +1,605 @@
+// Domain-decomposed 2D drivers: the unknown matrix X (n x n) is distributed over the GPUs by MESH
+// ELEMENTS of the column direction.  Rank g owns the columns that belong to its elements [k0,k1)
+// (all their bubble degrees) and to its hats [hA,hB): a local panel of n rows and
+// nloc = nhl + ml*q columns, laid out like an arrowhead vector (hats, then degrees, element fastest).
+//   * sweeps along the rows' index (F \ X, A*X of examples/adi_poisson.jl:55) act on whole columns:
+//     they are local and use the fused column kernels unchanged;
+//   * sweeps along the columns' index (X / F, X*A of examples/adi_poisson.jl:54) act on rows whose
+//     entries are spread over the GPUs: the bubble chains of an element are local (lanes run over the
+//     rows, so every access is a run of consecutive doubles), only the hat system couples the GPUs.
+//     It is solved exactly like the hats of a column inside a thread-block cluster (pop_fused2.cuh):
+//     edge couplings to the neighbours, then per direction one segment map per GPU, exchanged through
+//     peer memory (CUDA IPC) and ordered by device-side epoch flags.
+// Per row half step the GPUs exchange O(n * world) doubles instead of the O(n^2 / world) of a
+// distributed transpose.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "pop_internal.h"
+
+#define POP_DD_MAXWORLD 16
+#define POP_DD_MAXQ 128
+
+struct pop_dd {
+    int rank, world;
+    int m, nh, q;
+    int k0, ml, hA, nhl;
+    int64_t nrows, ld, nloc;
+    int kb[POP_DD_MAXWORLD + 1];      // element bounds of every rank
+    // peer-visible slab: [inbA 4*nrows][inbB world*nrows][inbC world*nrows][inbD 2*nrows][flags]
+    void *slab;
+    size_t slab_bytes;
+    void *peer_slab[POP_DD_MAXWORLD];
+    unsigned long long epoch;
+    bool opened;
+    // local scratch
+    double *hedge;   // [2][nrows]  hats hA-1 and hB of every row
+    double *xb;      // [4][ml][nrows] x of the coupled bubbles (for the hat rows of the product)
+    double *pconst;  // [2][world]
+    double *work;    // nrows x nloc work panel (leading dimension ld)
+};
+
+struct DDPeers {
+    double *inbA[POP_DD_MAXWORLD], *inbB[POP_DD_MAXWORLD], *inbC[POP_DD_MAXWORLD], *inbD[POP_DD_MAXWORLD];
+    unsigned long long *flags[POP_DD_MAXWORLD];
+};
+
+static void dd_offsets(const pop_dd *d, size_t *oA, size_t *oB, size_t *oC, size_t *oD, size_t *oF) {
+    const size_t nr = (size_t)d->nrows;
+    *oA = 0;
+    *oB = *oA + 4 * nr * 8;
+    *oC = *oB + (size_t)d->world * nr * 8;
+    *oD = *oC + (size_t)d->world * nr * 8;
+    *oF = (*oD + 4 * nr * 8 + 255) & ~(size_t)255;
+}
+
+static void dd_peers(const pop_dd *d, DDPeers *p) {
+    size_t oA, oB, oC, oD, oF;
+    dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
+    for (int r = 0; r < d->world; ++r) {
+        char *base = (char *)(r == d->rank ? d->slab : d->peer_slab[r]);
+        p->inbA[r] = (double *)(base + oA);
+        p->inbB[r] = (double *)(base + oB);
+        p->inbC[r] = (double *)(base + oC);
+        p->inbD[r] = (double *)(base + oD);
+        p->flags[r] = (unsigned long long *)(base + oF);
+    }
+}
+
+extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, int q, pop_dd **out) {
+    POP_REQUIRE(ctx && out, POP_ERR_ARG, "pop_dd_create: null argument");
+    POP_REQUIRE(world >= 1 && world <= POP_DD_MAXWORLD && rank >= 0 && rank < world, POP_ERR_ARG, "pop_dd_create: bad rank/world");
+    POP_REQUIRE(m >= world && q >= 1 && q <= POP_DD_MAXQ && abs(nh - m) <= 1, POP_ERR_DIM, "pop_dd_create: need m >= world, 1 <= q <= %d", POP_DD_MAXQ);
+    pop_dd *d = new pop_dd();
+    memset(d, 0, sizeof(*d));
+    d->rank = rank; d->world = world; d->m = m; d->nh = nh; d->q = q;
+    const int base = m / world, rem = m % world;
+    for (int r = 0; r <= world; ++r) d->kb[r] = r * base + std::min(r, rem);
+    d->k0 = d->kb[rank];
+    d->ml = d->kb[rank + 1] - d->k0;
+    d->hA = d->k0;
+    const int hB = rank == world - 1 ? nh : std::min(nh, d->kb[rank + 1]);
+    d->nhl = std::max(hB - d->hA, 0);
+    d->nrows = (int64_t)nh + (int64_t)m * q;
+    d->ld = (d->nrows + 1) & ~(int64_t)1;
+    d->nloc = (int64_t)d->nhl + (int64_t)d->ml * q;
+    size_t oA, oB, oC, oD, oF;
+    dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
+    d->slab_bytes = oF + 256;
+    cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d->hedge, (size_t)2 * d->nrows * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->xb, (size_t)4 * d->ml * d->nrows * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->pconst, (size_t)2 * POP_DD_MAXWORLD * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->work, (size_t)d->ld * d->nloc * 8);
+    if (e != cudaSuccess) {
+        pop_set_error("pop_dd_create: %s", cudaGetErrorString(e));
+        return POP_ERR_ALLOC;
+    }
+    POP_CUDA(cudaMemsetAsync(d->slab, 0, d->slab_bytes, ctx->stream));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));
+    d->opened = world == 1;
+    *out = d;
+    return POP_OK;
+}
+
+extern "C" int pop_dd_get_handle(pop_dd *d, void *handle_out) {
+    POP_REQUIRE(d && handle_out, POP_ERR_ARG, "pop_dd_get_handle: null argument");
+    cudaIpcMemHandle_t h;
+    POP_CUDA(cudaIpcGetMemHandle(&h, d->slab));
+    memcpy(handle_out, &h, sizeof(h));
+    return POP_OK;
+}
+
+extern "C" int pop_dd_open(pop_dd *d, const void *all_handles) {
+    POP_REQUIRE(d && all_handles, POP_ERR_ARG, "pop_dd_open: null argument");
+    for (int r = 0; r < d->world; ++r) {
+        if (r == d->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)all_handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            pop_set_error("pop_dd_open: cudaIpcOpenMemHandle for rank %d: %s", r, cudaGetErrorString(e));
+            return POP_ERR_CUDA;
+        }
+        d->peer_slab[r] = p;
+    }
+    d->opened = true;
+    return POP_OK;
+}
+
+extern "C" int pop_dd_destroy(pop_ctx *ctx, pop_dd *d) {
+    if (!d) return POP_OK;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < d->world; ++r)
+        if (r != d->rank && d->peer_slab[r]) cudaIpcCloseMemHandle(d->peer_slab[r]);
+    cudaFree(d->slab);
+    cudaFree(d->hedge);
+    cudaFree(d->xb);
+    cudaFree(d->pconst);
+    cudaFree(d->work);
+    delete d;
+    return POP_OK;
+}
+
+extern "C" int64_t pop_dd_nloc(const pop_dd *d) { return d ? d->nloc : 0; }
+extern "C" int64_t pop_dd_ld(const pop_dd *d) { return d ? d->ld : 0; }
+// global column index of local column c (hats first, then degrees, element fastest); -1 if out of range
+extern "C" int64_t pop_dd_column(const pop_dd *d, int64_t c) {
+    if (!d || c < 0 || c >= d->nloc) return -1;
+    if (c < d->nhl) return d->hA + c;
+    const int64_t b = c - d->nhl;
+    const int64_t j = b / d->ml, kl = b % d->ml;
+    return (int64_t)d->nh + j * d->m + d->k0 + kl;
+}
+
+// ------------------------------------------------------------------------------------
+// operator views handed to the row kernels
+// ------------------------------------------------------------------------------------
+struct RowOp {
+    // factor U of the system being solved (upper data, shared D block)
+    const double *rd, *w1, *w2;    // [q]
+    const double *S;               // [nb][3][m]
+    const double *rdA, *offA;      // [nh], [nh-1]
+    int nb;
+    // product operator T = Symmetric(upper data), shared D block (may be absent: nbT = -1)
+    const double *t0, *t1, *t2;    // [q]
+    const double *Ts;              // [nbT][3][m]
+    const double *TAd, *TAu;
+    int nbT;
+    double gamma;
+    int m, nh, q, k0, ml, hA, nhl, hB, rank, world;
+    int64_t nrows, ld, ldf;
+    int kb[POP_DD_MAXWORLD + 1];
+};
+
+// flags: the same epoch protocol as pop_dist.cu
+__global__ void k_dd_signal(DDPeers peers, int world, int me, unsigned long long ep) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        __threadfence_system();
+        volatile unsigned long long *p = peers.flags[r] + me;
+        *p = ep;
+        __threadfence_system();
+    }
+}
+__global__ void k_dd_wait(volatile unsigned long long *flags, int world, unsigned long long ep) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        long long spins = 0;
+        while (flags[r] < ep) {
+            __nanosleep(128);
+            if (++spins > 80000000LL) {   // ~10 s: a peer died
+                flags[POP_DD_MAXWORLD] = ep;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+static int dd_round(pop_ctx *ctx, pop_dd *d, const DDPeers &peers) {
+    if (d->world == 1) return POP_OK;
+    const unsigned long long ep = ++d->epoch;
+    k_dd_signal<<<1, 32, 0, ctx->stream>>>(peers, d->world, d->rank, ep);
+    k_dd_wait<<<1, 32, 0, ctx->stream>>>(peers.flags[d->rank], d->world, ep);
+    ctx->launches += 2;
+    POP_CUDA(cudaGetLastError());
+    return POP_OK;
+}
+
+// multipliers of every rank's hat segment: Pdn[g] = prod(-off[i] rd[i]), Pup[g] = prod(-off[i-1] rd[i]) over its hats
+__global__ void k_dd_pconst(RowOp op, double *pc) {
+    const int g = threadIdx.x;
+    if (g >= op.world) return;
+    const int a = op.kb[g], b = g == op.world - 1 ? op.nh : min(op.nh, op.kb[g + 1]);
+    double pd = 1.0, pu = 1.0;
+    for (int i = a; i < b; ++i) {
+        const double rd = op.rdA[i];
+        pd *= -(i < op.nh - 1 ? op.offA[i] : 0.0) * rd;
+        pu *= -(i > 0 ? op.offA[i - 1] : 0.0) * rd;
+    }
+    pc[g] = pd;
+    pc[POP_DD_MAXWORLD + g] = pu;
+}
+
+// ---- K1: backward bubble sweep along the rows:  z_j = (b_j - w1_j z_{j+1} - w2_j z_{j+2}) rd_j ------------
+// thread <-> (row r, local element kl); the 32 lanes of a warp are 32 consecutive rows.
+__global__ void __launch_bounds__(256) k_row_bwd(RowOp op, double *__restrict__ X) {
+    __shared__ double srd[POP_DD_MAXQ], sw1[POP_DD_MAXQ], sw2[POP_DD_MAXQ];
+    const int q = op.q;
+    for (int j = threadIdx.y * 32 + threadIdx.x; j < q; j += 256) {
+        srd[j] = op.rd[j];
+        sw1[j] = (op.w1 && j + 1 < q) ? op.w1[j] : 0.0;
+        sw2[j] = (op.w2 && j + 2 < q) ? op.w2[j] : 0.0;
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int kl = blockIdx.y * 8 + threadIdx.y;
+    if (r >= op.nrows || kl >= op.ml) return;
+    double *p = X + r + ((int64_t)op.nhl + kl) * op.ld;
+    const int64_t js = (int64_t)op.ml * op.ld;
+    double z1 = 0.0, z2 = 0.0;
+    int j = q - 1;
+    for (; j >= 7; j -= 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j - u) * js];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double t = (v[u] - sw1[j - u] * z1 - sw2[j - u] * z2) * srd[j - u];
+            z2 = z1;
+            z1 = t;
+            v[u] = t;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[(int64_t)(j - u) * js] = v[u];
+    }
+    for (; j >= 0; --j) {
+        const double t = (p[(int64_t)j * js] - sw1[j] * z1 - sw2[j] * z2) * srd[j];
+        p[(int64_t)j * js] = t;
+        z2 = z1;
+        z1 = t;
+    }
+}
+
+// ---- K2a0: couplings of my edge elements to the neighbours' hats (one thread per row) ----------------------
+__global__ void __launch_bounds__(128) k_row_edge(RowOp op, const double *__restrict__ X, DDPeers peers) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= op.nrows) return;
+    const int m = op.m;
+    if (op.rank > 0) {   // element k0, slot t = 0 -> hat k0-1 (last hat of the left neighbour)
+        double acc = 0.0;
+        for (int b = 0; b < op.nb; ++b) acc += op.S[((size_t)b * 3 + 0) * m + op.k0] * X[r + ((int64_t)op.nhl + (int64_t)b * op.ml) * op.ld];
+        peers.inbA[op.rank - 1][op.nrows + r] = acc;
+    }
+    if (op.rank < op.world - 1) {   // element k1-1, slot t = 2 -> hat k1 (first hat of the right neighbour)
+        double acc = 0.0;
+        const int kl = op.ml - 1;
+        for (int b = 0; b < op.nb; ++b) acc += op.S[((size_t)b * 3 + 2) * m + op.k0 + kl] * X[r + ((int64_t)op.nhl + (int64_t)b * op.ml + kl) * op.ld];
+        peers.inbA[op.rank + 1][r] = acc;
+    }
+}
+
+// ---- K2a: hat right-hand sides of my segment + first pass of the downward sweep ------------------------------
+__global__ void __launch_bounds__(128) k_row_hat_a(RowOp op, double *__restrict__ X, DDPeers peers) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= op.nrows) return;
+    const int m = op.m, ml = op.ml, nhl = op.nhl, k0 = op.k0;
+    const double *inA = peers.inbA[op.rank];
+    double t = 0.0;
+    for (int u = nhl - 1; u >= 0; --u) {
+        const int i = op.hA + u;
+        double v = X[r + (int64_t)u * op.ld];
+        for (int b = 0; b < op.nb; ++b)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int kl = i - s + 1 - k0;
+                if (kl >= 0 && kl < ml) v -= op.S[((size_t)b * 3 + s) * m + k0 + kl] * X[r + ((int64_t)nhl + (int64_t)b * ml + kl) * op.ld];
+            }
+        if (u == 0 && op.rank > 0) v -= inA[r];                                  // element k0-1 (slot 2) of the left neighbour
+        if (i == k0 + ml - 1 && op.rank < op.world - 1) v -= inA[op.nrows + r];  // element k1 (slot 0) of the right neighbour
+        X[r + (int64_t)u * op.ld] = v;
+        const double off = i < op.nh - 1 ? op.offA[i] : 0.0;
+        t = (v - off * t) * op.rdA[i];
+    }
+    for (int g = 0; g < op.rank; ++g) peers.inbB[g][(size_t)op.rank * op.nrows + r] = t;   // my map for the ranks below me
+}
+
+// ---- K2b: downward sweep with the exact incoming value, first pass of the upward sweep -----------------------
+__global__ void __launch_bounds__(128) k_row_hat_b(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ gdn) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= op.nrows) return;
+    const double *inB = peers.inbB[op.rank];
+    double G = 0.0;
+    for (int g = op.world - 1; g > op.rank; --g) G = fma(pc[g], G, inB[(size_t)g * op.nrows + r]);
+    gdn[r] = G;
+    double hin = G;
+    for (int u = op.nhl - 1; u >= 0; --u) {
+        const int i = op.hA + u;
+        const double off = i < op.nh - 1 ? op.offA[i] : 0.0;
+        hin = (X[r + (int64_t)u * op.ld] - off * hin) * op.rdA[i];
+        X[r + (int64_t)u * op.ld] = hin;
+    }
+    double t = 0.0;
+    for (int u = 0; u < op.nhl; ++u) {
+        const int i = op.hA + u;
+        const double off = i > 0 ? op.offA[i - 1] : 0.0;
+        t = (X[r + (int64_t)u * op.ld] - off * t) * op.rdA[i];
+    }
+    for (int g = op.rank + 1; g < op.world; ++g) peers.inbC[g][(size_t)op.rank * op.nrows + r] = t;   // my map for the ranks above me
+}
+
+// ---- K2c: upward sweep with the exact incoming value; hats hA-1 and hB of the neighbours -----------------------
+__global__ void __launch_bounds__(128) k_row_hat_c(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, const double *__restrict__ gdn,
+                                                   double *__restrict__ hedge) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= op.nrows) return;
+    const double *inC = peers.inbC[op.rank];
+    const double ydn = gdn[r];   // (gdn aliases hedge[0]: read it before this thread overwrites the slot)
+    double G = 0.0;
+    for (int g = 0; g < op.rank; ++g) G = fma(pc[POP_DD_MAXWORLD + g], G, inC[(size_t)g * op.nrows + r]);
+    double hin = G;
+    for (int u = 0; u < op.nhl; ++u) {
+        const int i = op.hA + u;
+        const double off = i > 0 ? op.offA[i - 1] : 0.0;
+        hin = (X[r + (int64_t)u * op.ld] - off * hin) * op.rdA[i];
+        X[r + (int64_t)u * op.ld] = hin;
+    }
+    hedge[r] = op.rank > 0 ? G : 0.0;                                                        // hat hA-1
+    // hat hB = (y[hB] - off[hB-1] h[hB-1]) rd[hB], y[hB] being the value that entered my downward sweep
+    hedge[op.nrows + r] = (op.hB < op.nh && op.nhl > 0) ? (ydn - op.offA[op.hB - 1] * hin) * op.rdA[op.hB] : 0.0;
+}
+
+// ---- K3: correction of the coupled bubbles, forward sweep, product with T, + gamma F; in place -----------------
+//   x_j = (z_j - w1_{j-1} x_{j-1} - w2_{j-2} x_{j-2}) rd_j ;  r_j = sum_d T(j,j+d) x_{j+d} + coupling to the hats + gamma f_j
+// Row j-2 of the product is emitted once x_j is known (window of five x values).
+__global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hedge,
+                                                     double *__restrict__ xb, DDPeers peers) {
+    __shared__ double srd[POP_DD_MAXQ + 4], sw1[POP_DD_MAXQ + 4], sw2[POP_DD_MAXQ + 4], st0[POP_DD_MAXQ + 4], st1[POP_DD_MAXQ + 4], st2[POP_DD_MAXQ + 4];
+    const int q = op.q;
+    const bool mul = op.nbT >= 0;
+    // tables shifted by 2 so that index j-2 .. j+2 never needs a guard
+    for (int j = threadIdx.y * 32 + threadIdx.x; j < q + 4; j += 256) {
+        const int jj = j - 2;
+        const bool in = jj >= 0 && jj < q;
+        srd[j] = in ? op.rd[jj] : 0.0;
+        sw1[j] = (in && op.w1 && jj + 1 < q) ? op.w1[jj] : 0.0;
+        sw2[j] = (in && op.w2 && jj + 2 < q) ? op.w2[jj] : 0.0;
+        st0[j] = (in && mul) ? op.t0[jj] : 0.0;
+        st1[j] = (in && mul && op.t1 && jj + 1 < q) ? op.t1[jj] : 0.0;
+        st2[j] = (in && mul && op.t2 && jj + 2 < q) ? op.t2[jj] : 0.0;
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int kl = blockIdx.y * 8 + threadIdx.y;
+    if (r >= op.nrows || kl >= op.ml) return;
+    const int m = op.m, ml = op.ml, nhl = op.nhl, k = op.k0 + kl;
+    const int64_t ld = op.ld, js = (int64_t)ml * ld;
+    double *p = X + r + ((int64_t)nhl + kl) * ld;
+    const double *f = F ? F + r + ((int64_t)nhl + kl) * op.ldf : nullptr;
+    const int64_t fs = (int64_t)ml * op.ldf;
+    // hats k-1, k, k+1 of this element (local indices kl-1, kl, kl+1; beyond my segment: the neighbours')
+    const double h0 = kl >= 1 ? X[r + (int64_t)(kl - 1) * ld] : hedge[r];
+    const double h1 = kl < nhl ? X[r + (int64_t)kl * ld] : hedge[op.nrows + r];
+    const double h2 = kl + 1 < nhl ? X[r + (int64_t)(kl + 1) * ld] : (kl + 1 == nhl ? hedge[op.nrows + r] : 0.0);
+    double xw0 = 0.0, xw1 = 0.0, xw2 = 0.0, xw3 = 0.0, xw4 = 0.0;   // x_j, x_{j-1}, ..., x_{j-4}
+    double eL = 0.0, eR = 0.0;                                       // couplings of my edge element to a neighbour's product hat
+    for (int j = 0; j < q + 2; ++j) {
+        double v = 0.0;
+        if (j < q) {
+            v = p[(int64_t)j * js];
+            if (j < op.nb) {
+                const double *sb = op.S + (size_t)j * 3 * m + k;
+                v -= sb[0] * h0 + sb[m] * h1 + sb[2 * m] * h2;
+            }
+            v = (v - sw1[j + 1] * xw0 - sw2[j] * xw1) * srd[j + 2];   // w1_{j-1} x_{j-1}, w2_{j-2} x_{j-2}
+            if (!mul) p[(int64_t)j * js] = v;
+            else if (j < op.nbT) {
+                xb[((size_t)j * ml + kl) * op.nrows + r] = v;
+                const double *tb = op.Ts + (size_t)j * 3 * m + k;
+                eL += tb[0] * v;
+                eR += tb[2 * m] * v;
+            }
+        }
+        xw4 = xw3; xw3 = xw2; xw2 = xw1; xw1 = xw0; xw0 = v;
+        const int jo = j - 2;
+        if (mul && jo >= 0) {
+            // T(jo,jo) x_jo + T(jo,jo+1) x_{jo+1} + T(jo-1,jo) x_{jo-1} + T(jo,jo+2) x_{jo+2} + T(jo-2,jo) x_{jo-2}
+            double acc = st0[jo + 2] * xw2 + st1[jo + 2] * xw1 + st1[jo + 1] * xw3 + st2[jo + 2] * xw0 + st2[jo] * xw4;
+            if (jo < op.nbT) {
+                const double *tb = op.Ts + (size_t)jo * 3 * m + k;
+                acc += tb[0] * h0 + tb[m] * h1 + tb[2 * m] * h2;
+            }
+            p[(int64_t)jo * js] = f ? fma(op.gamma, f[(int64_t)jo * fs], acc) : acc;
+        }
+    }
+    if (mul && op.world > 1) {
+        if (kl == 0 && op.rank > 0) peers.inbD[op.rank - 1][op.nrows + r] = eL;            // element k0 -> hat k0-1
+        if (kl == ml - 1 && op.rank < op.world - 1) peers.inbD[op.rank + 1][r] = eR;      // element k1-1 -> hat k1
+    }
+}
+
+// ---- K4: hat rows of the product (one thread per row) ------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_row_hat_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hedge,
+                                                     const double *__restrict__ xb, DDPeers peers) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= op.nrows) return;
+    const int m = op.m, ml = op.ml, nhl = op.nhl, k0 = op.k0;
+    const double *inD = peers.inbD[op.rank];
+    double hp = hedge[r], hc = nhl > 0 ? X[r] : 0.0;
+    for (int u = 0; u < nhl; ++u) {
+        const int i = op.hA + u;
+        const double hn = u + 1 < nhl ? X[r + (int64_t)(u + 1) * op.ld] : hedge[op.nrows + r];
+        double acc = op.TAd[i] * hc;
+        if (i + 1 < op.nh) acc += op.TAu[i] * hn;
+        if (i > 0) acc += op.TAu[i - 1] * hp;
+        for (int b = 0; b < op.nbT; ++b)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int kl = i - s + 1 - k0;
+                if (kl >= 0 && kl < ml) acc += op.Ts[((size_t)b * 3 + s) * m + k0 + kl] * xb[((size_t)b * ml + kl) * op.nrows + r];
+            }
+        if (u == 0 && op.rank > 0) acc += inD[r];
+        if (i == k0 + ml - 1 && op.rank < op.world - 1) acc += inD[op.nrows + r];
+        X[r + (int64_t)u * op.ld] = F ? fma(op.gamma, F[r + (int64_t)u * op.ldf], acc) : acc;
+        hp = hc;
+        hc = hn;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// one row half step:  R <- (R U^{-T}... ) i.e. rows of R:  r <- T (S^{-1} r) + gamma f   with S = U U^T
+// ------------------------------------------------------------------------------------
+static int dd_make_op(const pop_dd *d, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, int64_t ldf, RowOp *op) {
+    const pop_desc &u = U->d;
+    POP_REQUIRE(U->is_factor && U->mD == 1 && u.uD <= 2 && u.m == d->m && u.nh == d->nh && u.q == d->q, POP_ERR_DIM,
+                "row half step: factor does not match the decomposition (or is not a shared-block factor with <= 2 bands)");
+    memset(op, 0, sizeof(*op));
+    const size_t plane = (size_t)u.q;
+    op->rd = U->p.rdD;
+    op->w1 = u.uD >= 1 ? U->p.D + (size_t)(u.lD + 1) * plane : nullptr;
+    op->w2 = u.uD >= 2 ? U->p.D + (size_t)(u.lD + 2) * plane : nullptr;
+    op->S = U->p.B;
+    op->rdA = U->p.rdA;
+    op->offA = U->p.Au;
+    op->nb = std::min(u.nB, u.q);
+    op->nbT = -1;
+    if (T) {
+        const pop_desc &t = T->d;
+        POP_REQUIRE(T->mD == 1 && t.uD <= 2 && t.m == d->m && t.nh == d->nh && t.q == d->q, POP_ERR_DIM, "row half step: product operator does not match");
+        const size_t tpl = (size_t)t.q;
+        op->t0 = T->p.D + (size_t)t.lD * tpl;
+        op->t1 = t.uD >= 1 ? T->p.D + (size_t)(t.lD + 1) * tpl : nullptr;
+        op->t2 = t.uD >= 2 ? T->p.D + (size_t)(t.lD + 2) * tpl : nullptr;
+        op->Ts = T->p.B;
+        op->TAd = T->p.Ad;
+        op->TAu = T->p.Au;
+        op->nbT = std::min(t.nB, t.q);
+        POP_REQUIRE(op->nbT <= 4, POP_ERR_DIM, "row half step: at most 4 coupling blocks");
+    }
+    op->gamma = gamma;
+    op->m = d->m; op->nh = d->nh; op->q = d->q; op->k0 = d->k0; op->ml = d->ml; op->hA = d->hA; op->nhl = d->nhl;
+    op->hB = d->hA + d->nhl;
+    op->rank = d->rank; op->world = d->world;
+    op->nrows = d->nrows; op->ld = d->ld; op->ldf = ldf;
+    for (int r = 0; r <= d->world; ++r) op->kb[r] = d->kb[r];
+    return POP_OK;
+}
+
+// rows of R (nrows x nloc, leading dimension d->ld):  r <- T (S^{-1} r) + gamma f ; T may be null (plain solve)
+static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *F, int64_t ldf,
+                            double *R) {
+    RowOp op;
+    int rc = dd_make_op(d, U, T, gamma, ldf, &op);
+    if (rc) return rc;
+    DDPeers peers;
+    dd_peers(d, &peers);
+    const dim3 blk2(32, 8), grd2((unsigned)((d->nrows + 31) / 32), (unsigned)((d->ml + 7) / 8));
+    const unsigned grd1 = (unsigned)((d->nrows + 127) / 128);
+    double *gdn = d->hedge;   // reused: hedge[0] holds the incoming downward values between K2b and K2c
+    k_dd_pconst<<<1, 32, 0, ctx->stream>>>(op, d->pconst);
+    k_row_bwd<<<grd2, blk2, 0, ctx->stream>>>(op, R);
+    ctx->launches += 2;
+    if (d->world > 1) {
+        k_row_edge<<<grd1, 128, 0, ctx->stream>>>(op, R, peers);
+        ctx->launches++;
+        if ((rc = dd_round(ctx, d, peers))) return rc;
+    }
+    k_row_hat_a<<<grd1, 128, 0, ctx->stream>>>(op, R, peers);
+    ctx->launches++;
+    if ((rc = dd_round(ctx, d, peers))) return rc;
+    k_row_hat_b<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, gdn);
+    ctx->launches++;
+    if ((rc = dd_round(ctx, d, peers))) return rc;
+    k_row_hat_c<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, gdn, d->hedge);
+    k_row_fwd_mul<<<grd2, blk2, 0, ctx->stream>>>(op, R, (T && gamma != 0.0) ? F : nullptr, d->hedge, d->xb, peers);
+    ctx->launches += 2;
+    if (T) {
+        if ((rc = dd_round(ctx, d, peers))) return rc;
+        k_row_hat_mul<<<grd1, 128, 0, ctx->stream>>>(op, R, gamma != 0.0 ? F : nullptr, d->hedge, d->xb, peers);
+        ctx->launches++;
+    }
+    POP_CUDA(cudaGetLastError());
+    return POP_OK;
+}
+
+// exposed for tests / drivers: one row half step on a caller-owned local panel
+extern "C" int pop_dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *dF,
+                                    int64_t ldf, double *dR, int64_t ldr) {
+    POP_REQUIRE(ctx && d && U && dR, POP_ERR_ARG, "pop_dd_row_half_step: null argument");
+    POP_REQUIRE(d->opened, POP_ERR_ARG, "pop_dd_row_half_step: peers not opened");
+    POP_REQUIRE(ldr == d->ld, POP_ERR_DIM, "pop_dd_row_half_step: the panel must use the leading dimension pop_dd_ld()");
+    POP_REQUIRE(!(T && gamma != 0.0) || (dF && ldf >= d->nrows), POP_ERR_DIM, "pop_dd_row_half_step: F panel missing or too small");
+    return dd_row_half_step(ctx, d, U, T, gamma, dF, ldf, dR);
+}
+
+__global__ void k_dd_scale_copy(const double *__restrict__ src, int64_t lds, double *__restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, double s) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) dst[c * ldd + r] = s * src[c * lds + r];
+}
+
+// ------------------------------------------------------------------------------------
+// ADI of examples/adi_poisson.jl:42-59 on the element-decomposed matrix: no transposes.
+//   R <- -F/p_1 ; for j: rows: R <- (R S1_j^{-1}) T2_j - F/q_j ; columns: R <- T1_{j+1} (S2_j^{-1} R) - F/p_{j+1}
+//   (last iteration: X = S2_J^{-1} R).  dF_local / dX_local: n x nloc panels in the local column order.
+// ------------------------------------------------------------------------------------
+extern "C" int pop_adi_poisson_dd(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *K, const pop_arrowhead *M, const double *dF_local, int64_t ldf,
+                                  double *dX_local, int64_t ldx, double a, double b, double c, double dd, double tol, int J) {
+    POP_REQUIRE(ctx && d && K && M && dF_local && dX_local, POP_ERR_ARG, "pop_adi_poisson_dd: null argument");
+    POP_REQUIRE(d->opened, POP_ERR_ARG, "pop_adi_poisson_dd: peers not opened");
+    const int64_t n = K->n();
+    POP_REQUIRE(n == d->nrows && K->d.m == d->m && K->d.q == d->q, POP_ERR_DIM, "pop_adi_poisson_dd: operator does not match the decomposition");
+    POP_REQUIRE(ldf >= n && ldx >= n && !(ldf & 1) && !((uintptr_t)dF_local & 15), POP_ERR_DIM,
+                "pop_adi_poisson_dd: panels need leading dimensions >= n (F: even, 16-byte aligned)");
+    if (J <= 0) J = pop_adi_num_iterations(a, b, c, dd, tol);
+    POP_REQUIRE(J >= 1 && J <= 2000, POP_ERR_ARG, "pop_adi_poisson_dd: iteration count %d out of range", J);
+    std::vector<double> p(J), q(J);
+    int rc = pop_adi_shifts(J, a, b, c, dd, p.data(), q.data());
+    if (rc) return rc;
+    std::vector<double> al(2 * J), sg(2 * J), ta(2 * J), tb(2 * J);
+    for (int j = 0; j < J; ++j) {
+        al[2 * j] = 1.0; sg[2 * j] = 1.0 / p[j];
+        al[2 * j + 1] = 1.0; sg[2 * j + 1] = -1.0 / q[j];
+        ta[2 * j] = -1.0; tb[2 * j] = 1.0 / p[j];
+        ta[2 * j + 1] = -1.0; tb[2 * j + 1] = -1.0 / q[j];
+    }
+    std::vector<pop_arrowhead *> fac(2 * J, nullptr), top(2 * J, nullptr);
+    auto cleanup = [&]() {
+        for (auto *h : fac) pop_arrowhead_free(ctx, h);
+        for (auto *h : top) pop_arrowhead_free(ctx, h);
+    };
+    rc = pop_revchol_shifted_batch(ctx, K, M, al.data(), sg.data(), 2 * J, fac.data(), nullptr);
+    if (rc) { cleanup(); return rc; }
+    {
+        pop_arrowhead Ku = *K, Mu = *M;   // upper data (Symmetric views)
+        Ku.d.nC = 0; Mu.d.nC = 0;
+        Ku.p.D = K->p.D + (size_t)K->d.lD * K->d.q * K->mD; Ku.d.lD = 0;
+        Mu.p.D = M->p.D + (size_t)M->d.lD * M->d.q * M->mD; Mu.d.lD = 0;
+        rc = pop_launch_axpby_batch(ctx, &Ku, &Mu, ta.data(), tb.data(), 2 * J, top.data());
+        if (rc) { cleanup(); return rc; }
+    }
+    const int64_t ld = d->ld, nloc = d->nloc;
+    double *R = d->work;
+    {
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)std::min<int64_t>(nloc, 32768));
+        k_dd_scale_copy<<<grid, 256, 0, ctx->stream>>>(dF_local, ldf, R, ld, n, nloc, -1.0 / p[0]);
+        ctx->launches++;
+    }
+    for (int j = 0; j < J && rc == POP_OK; ++j) {
+        if ((rc = dd_row_half_step(ctx, d, fac[2 * j], top[2 * j + 1], -1.0 / q[j], dF_local, ldf, R))) break;
+        if (j + 1 < J) rc = pop_solve_mul_axpy(ctx, fac[2 * j + 1], top[2 * j + 2], -1.0 / p[j + 1], dF_local, ldf, R, ld, nloc);
+        else rc = pop_solve(ctx, fac[2 * j + 1], POP_LEFT, R, ld, nloc, POP_SOLVE_AUTO);
+    }
+    if (rc == POP_OK) {
+        cudaError_t e = cudaMemcpy2DAsync(dX_local, ldx * 8, R, ld * 8, n * 8, nloc, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { pop_set_error("pop_adi_poisson_dd: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    return rc;
+}

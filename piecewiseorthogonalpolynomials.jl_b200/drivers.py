@@ -243,6 +243,87 @@ def adi_poisson_p2p(M, K, F_local, a, b, c=None, d=None, tol=1e-15, J=0, grid: "
     return X
 
 
+def dd_columns(m, nh, q, rank, world):
+    """Global column indices of rank's local panel in the element decomposition (csrc/pop_row.cu): its hats
+    [hA,hB), then for every degree j the bubbles of its elements [k0,k1) -- arrowhead order of the local mesh."""
+    base, rem = divmod(m, world)
+    kb = [r * base + min(r, rem) for r in range(world + 1)]
+    k0, k1 = kb[rank], kb[rank + 1]
+    hA, hB = k0, (nh if rank == world - 1 else min(nh, k1))
+    cols = list(range(hA, max(hB, hA)))
+    for j in range(q):
+        cols.extend(nh + j * m + k for k in range(k0, k1))
+    return np.asarray(cols, dtype=np.int64)
+
+
+class ElementDecomposition:
+    """X (n x n) distributed by mesh elements of the column direction (csrc/pop_row.cu)."""
+
+    def __init__(self, M, group=None):
+        import torch.distributed as dist
+        Mb = _base(M)
+        self.ctx = Mb.ctx
+        dsc = Mb.desc
+        self.m, self.nh, self.q = int(dsc.m), int(dsc.nh), int(dsc.q)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lib = L.lib()
+        h = C.c_void_p()
+        L.check(lib.pop_dd_create(self.ctx.handle, self.rank, self.world, self.m, self.nh, self.q, C.byref(h)), "pop_dd_create")
+        self._h = h
+        if self.world > 1:
+            nb = lib.pop_dist_handle_bytes()
+            mine = C.create_string_buffer(nb)
+            L.check(lib.pop_dd_get_handle(h, mine), "pop_dd_get_handle")
+            allh = [None] * self.world
+            dist.all_gather_object(allh, bytes(mine.raw), group=group)
+            blob = C.create_string_buffer(b"".join(allh), nb * self.world)
+            L.check(lib.pop_dd_open(h, blob), "pop_dd_open")
+            dist.barrier(group=group)
+        self.nloc = int(lib.pop_dd_nloc(h))
+        self.ld = int(lib.pop_dd_ld(h))
+        self.n = self.nh + self.m * self.q
+        self.columns = dd_columns(self.m, self.nh, self.q, self.rank, self.world)
+        assert len(self.columns) == self.nloc
+
+    def panel(self, device=None):
+        """Uninitialised local panel (n x nloc, column-major with the library's leading dimension)."""
+        import torch
+        buf = torch.empty((self.nloc, self.ld), dtype=torch.float64, device=device or f"cuda:{self.ctx.device}")
+        return buf.t()[:self.n]
+
+    def close(self):
+        if self._h is not None:
+            L.lib().pop_dd_destroy(self.ctx.handle, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def adi_poisson_dd(M, K, F_local, a, b, c=None, d=None, tol=1e-15, J=0, dd: "ElementDecomposition" = None, group=None):
+    """ADI without transposes on the element-decomposed matrix.  F_local: the columns dd.columns of F as an
+    (n x nloc) panel from dd.panel(); returns the same columns of X."""
+    Mb, Kb = _base(M), _base(K)
+    ctx = Mb.ctx
+    c = -b if c is None else c
+    d = -a if d is None else d
+    own = dd is None
+    if own:
+        dd = ElementDecomposition(M, group=group)
+    pf = _Panel(F_local, False)
+    X = dd.panel()
+    px = _Panel(X, True)
+    _bind_stream(ctx)
+    L.check(L.lib().pop_adi_poisson_dd(ctx.handle, dd._h, Kb._h, Mb._h, pf.ptr, pf.ld, px.ptr, px.ld, a, b, c, d, tol, int(J)), "ADI (element decomposition)")
+    if own:
+        dd.close()
+    return X
+
+
 def heat_steps_p2p(M, K, U_local, dt, nsteps, grid: "DistMatrix" = None, group=None):
     """In place: nsteps of the factored 2D backward Euler on the column-block distributed field U_local = U[:, lo:hi]."""
     Mb, Kb = _base(M), _base(K)
