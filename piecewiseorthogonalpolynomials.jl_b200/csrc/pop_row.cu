@@ -22,6 +22,7 @@
 
 #define POP_DD_MAXWORLD 16
 #define POP_DD_MAXQ 128
+#define POP_DD_MAXHL 1032   // hats of one rank's segment kept in shared memory by the chain kernels
 
 struct pop_dd {
     int rank, world;
@@ -36,7 +37,8 @@ struct pop_dd {
     unsigned long long epoch;
     bool opened;
     // local scratch
-    double *hedge;   // [2][nrows]  hats hA-1 and hB of every row
+    double *hx;      // [nhl+3][nrows]  hats hA-1, my hats, hat hB, one zero row
+    double *gdn;     // [nrows] value that entered the downward sweep
     double *xb;      // [4][ml][nrows] x of the coupled bubbles (for the hat rows of the product)
     double *pconst;  // [2][world]
     double *work;    // nrows x nloc work panel (leading dimension ld)
@@ -73,6 +75,7 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
     POP_REQUIRE(ctx && out, POP_ERR_ARG, "pop_dd_create: null argument");
     POP_REQUIRE(world >= 1 && world <= POP_DD_MAXWORLD && rank >= 0 && rank < world, POP_ERR_ARG, "pop_dd_create: bad rank/world");
     POP_REQUIRE(m >= world && q >= 1 && q <= POP_DD_MAXQ && abs(nh - m) <= 1, POP_ERR_DIM, "pop_dd_create: need m >= world, 1 <= q <= %d", POP_DD_MAXQ);
+    POP_REQUIRE((m + world - 1) / world + 1 <= POP_DD_MAXHL, POP_ERR_DIM, "pop_dd_create: more than %d hats per rank", POP_DD_MAXHL);
     pop_dd *d = new pop_dd();
     memset(d, 0, sizeof(*d));
     d->rank = rank; d->world = world; d->m = m; d->nh = nh; d->q = q;
@@ -90,7 +93,8 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
     dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
     d->slab_bytes = oF + 256;
     cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&d->hedge, (size_t)2 * d->nrows * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->hx, (size_t)(d->nhl + 3) * d->nrows * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->gdn, (size_t)d->nrows * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d->xb, (size_t)4 * d->ml * d->nrows * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d->pconst, (size_t)2 * POP_DD_MAXWORLD * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d->work, (size_t)d->ld * d->nloc * 8);
@@ -137,7 +141,8 @@ extern "C" int pop_dd_destroy(pop_ctx *ctx, pop_dd *d) {
     for (int r = 0; r < d->world; ++r)
         if (r != d->rank && d->peer_slab[r]) cudaIpcCloseMemHandle(d->peer_slab[r]);
     cudaFree(d->slab);
-    cudaFree(d->hedge);
+    cudaFree(d->hx);
+    cudaFree(d->gdn);
     cudaFree(d->xb);
     cudaFree(d->pconst);
     cudaFree(d->work);
@@ -284,86 +289,129 @@ __global__ void __launch_bounds__(128) k_row_edge(RowOp op, const double *__rest
     }
 }
 
-// ---- K2a: hat right-hand sides of my segment + first pass of the downward sweep ------------------------------
-__global__ void __launch_bounds__(128) k_row_hat_a(RowOp op, double *__restrict__ X, DDPeers peers) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= op.nrows) return;
+// ---- K2a: hat right-hand sides of my segment: one thread per (row, hat), fully parallel ------------------------
+__global__ void __launch_bounds__(256) k_row_hat_gather(RowOp op, double *__restrict__ X, DDPeers peers) {
+    const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int u = blockIdx.y * 8 + threadIdx.y;
+    if (r >= op.nrows || u >= op.nhl) return;
     const int m = op.m, ml = op.ml, nhl = op.nhl, k0 = op.k0;
-    const double *inA = peers.inbA[op.rank];
-    double t = 0.0;
-    for (int u = nhl - 1; u >= 0; --u) {
-        const int i = op.hA + u;
-        double v = X[r + (int64_t)u * op.ld];
-        for (int b = 0; b < op.nb; ++b)
+    const int i = op.hA + u;
+    double v = X[r + (int64_t)u * op.ld];
+    for (int b = 0; b < op.nb; ++b)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int kl = i - s + 1 - k0;
-                if (kl >= 0 && kl < ml) v -= op.S[((size_t)b * 3 + s) * m + k0 + kl] * X[r + ((int64_t)nhl + (int64_t)b * ml + kl) * op.ld];
-            }
-        if (u == 0 && op.rank > 0) v -= inA[r];                                  // element k0-1 (slot 2) of the left neighbour
-        if (i == k0 + ml - 1 && op.rank < op.world - 1) v -= inA[op.nrows + r];  // element k1 (slot 0) of the right neighbour
-        X[r + (int64_t)u * op.ld] = v;
-        const double off = i < op.nh - 1 ? op.offA[i] : 0.0;
-        t = (v - off * t) * op.rdA[i];
-    }
-    for (int g = 0; g < op.rank; ++g) peers.inbB[g][(size_t)op.rank * op.nrows + r] = t;   // my map for the ranks below me
+        for (int s = 0; s < 3; ++s) {
+            const int kl = i - s + 1 - k0;
+            if (kl >= 0 && kl < ml) v -= op.S[((size_t)b * 3 + s) * m + k0 + kl] * X[r + ((int64_t)nhl + (int64_t)b * ml + kl) * op.ld];
+        }
+    const double *inA = peers.inbA[op.rank];
+    if (u == 0 && op.rank > 0) v -= inA[r];                                  // element k0-1 (slot 2) of the left neighbour
+    if (i == k0 + ml - 1 && op.rank < op.world - 1) v -= inA[op.nrows + r];  // element k1 (slot 0) of the right neighbour
+    X[r + (int64_t)u * op.ld] = v;
 }
 
-// ---- K2b: downward sweep with the exact incoming value, first pass of the upward sweep -----------------------
+// The hat recurrences: one thread per row, sequential in the hat index, every access a run of consecutive
+// doubles across the lanes.  Loads are issued 8 hats ahead of the dependent chain; the hat factor of the
+// segment sits in shared memory.  c_dn[u] = off(u,u+1) rd[u], c_up[u] = off(u-1,u) rd[u].
+#define DD_HAT_TABLES()                                                                                   \
+    __shared__ double s_rd[POP_DD_MAXHL], s_cdn[POP_DD_MAXHL], s_cup[POP_DD_MAXHL];                       \
+    for (int u = threadIdx.x; u < op.nhl; u += blockDim.x) {                                              \
+        const int i = op.hA + u;                                                                          \
+        const double rdv = op.rdA[i];                                                                     \
+        s_rd[u] = rdv;                                                                                    \
+        s_cdn[u] = (i < op.nh - 1 ? op.offA[i] : 0.0) * rdv;                                              \
+        s_cup[u] = (i > 0 ? op.offA[i - 1] : 0.0) * rdv;                                                  \
+    }                                                                                                     \
+    __syncthreads();
+
+template <bool DOWN, bool STORE>
+__device__ __forceinline__ double dd_chain(double *__restrict__ xr, const int64_t ld, const int nhl, const double *s_rd, const double *s_c, double hin) {
+    for (int b0 = 0; b0 < nhl; b0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int u = DOWN ? nhl - 1 - (b0 + s) : b0 + s;
+            v[s] = (b0 + s < nhl) ? xr[(int64_t)u * ld] : 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int u = DOWN ? nhl - 1 - (b0 + s) : b0 + s;
+            if (b0 + s < nhl) {
+                hin = fma(-s_c[u], hin, v[s] * s_rd[u]);
+                if (STORE) xr[(int64_t)u * ld] = hin;
+            }
+        }
+    }
+    return hin;
+}
+
+// ---- K2b: first pass of the downward sweep (zero incoming): my segment's map for the ranks below me --------------
+__global__ void __launch_bounds__(128) k_row_hat_dn1(RowOp op, double *__restrict__ X, DDPeers peers) {
+    DD_HAT_TABLES()
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= op.nrows) return;
+    const double t = dd_chain<true, false>(X + r, op.ld, op.nhl, s_rd, s_cdn, 0.0);
+    for (int g = 0; g < op.rank; ++g) peers.inbB[g][(size_t)op.rank * op.nrows + r] = t;
+}
+
+// ---- K2c: downward sweep with the exact incoming value, first pass of the upward sweep -----------------------
 __global__ void __launch_bounds__(128) k_row_hat_b(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ gdn) {
+    DD_HAT_TABLES()
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= op.nrows) return;
     const double *inB = peers.inbB[op.rank];
     double G = 0.0;
     for (int g = op.world - 1; g > op.rank; --g) G = fma(pc[g], G, inB[(size_t)g * op.nrows + r]);
     gdn[r] = G;
-    double hin = G;
-    for (int u = op.nhl - 1; u >= 0; --u) {
-        const int i = op.hA + u;
-        const double off = i < op.nh - 1 ? op.offA[i] : 0.0;
-        hin = (X[r + (int64_t)u * op.ld] - off * hin) * op.rdA[i];
-        X[r + (int64_t)u * op.ld] = hin;
+    dd_chain<true, true>(X + r, op.ld, op.nhl, s_rd, s_cdn, G);
+    if (op.world > 1) {
+        const double t = dd_chain<false, false>(X + r, op.ld, op.nhl, s_rd, s_cup, 0.0);
+        for (int g = op.rank + 1; g < op.world; ++g) peers.inbC[g][(size_t)op.rank * op.nrows + r] = t;
     }
-    double t = 0.0;
-    for (int u = 0; u < op.nhl; ++u) {
-        const int i = op.hA + u;
-        const double off = i > 0 ? op.offA[i - 1] : 0.0;
-        t = (X[r + (int64_t)u * op.ld] - off * t) * op.rdA[i];
-    }
-    for (int g = op.rank + 1; g < op.world; ++g) peers.inbC[g][(size_t)op.rank * op.nrows + r] = t;   // my map for the ranks above me
 }
 
-// ---- K2c: upward sweep with the exact incoming value; hats hA-1 and hB of the neighbours -----------------------
+// ---- K2d: upward sweep with the exact incoming value; hx = my hats with the neighbours' hats hA-1 and hB around them ----
+// hx[(u+1)*nrows + r] = hat hA+u, hx[r] = hat hA-1, hx[(nhl+1)*nrows + r] = hat hB, one more zero row behind
 __global__ void __launch_bounds__(128) k_row_hat_c(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, const double *__restrict__ gdn,
-                                                   double *__restrict__ hedge) {
+                                                   double *__restrict__ hx) {
+    DD_HAT_TABLES()
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= op.nrows) return;
     const double *inC = peers.inbC[op.rank];
-    const double ydn = gdn[r];   // (gdn aliases hedge[0]: read it before this thread overwrites the slot)
     double G = 0.0;
     for (int g = 0; g < op.rank; ++g) G = fma(pc[POP_DD_MAXWORLD + g], G, inC[(size_t)g * op.nrows + r]);
     double hin = G;
-    for (int u = 0; u < op.nhl; ++u) {
-        const int i = op.hA + u;
-        const double off = i > 0 ? op.offA[i - 1] : 0.0;
-        hin = (X[r + (int64_t)u * op.ld] - off * hin) * op.rdA[i];
-        X[r + (int64_t)u * op.ld] = hin;
+    const int nhl = op.nhl;
+    for (int b0 = 0; b0 < nhl; b0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v[s] = (b0 + s < nhl) ? X[r + (int64_t)(b0 + s) * op.ld] : 0.0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int u = b0 + s;
+            if (u < nhl) {
+                hin = fma(-s_cup[u], hin, v[s] * s_rd[u]);
+                X[r + (int64_t)u * op.ld] = hin;
+                hx[(size_t)(u + 1) * op.nrows + r] = hin;
+            }
+        }
     }
-    hedge[r] = op.rank > 0 ? G : 0.0;                                                        // hat hA-1
+    hx[r] = op.rank > 0 ? G : 0.0;                                                           // hat hA-1
     // hat hB = (y[hB] - off[hB-1] h[hB-1]) rd[hB], y[hB] being the value that entered my downward sweep
-    hedge[op.nrows + r] = (op.hB < op.nh && op.nhl > 0) ? (ydn - op.offA[op.hB - 1] * hin) * op.rdA[op.hB] : 0.0;
+    hx[(size_t)(nhl + 1) * op.nrows + r] = (op.hB < op.nh && nhl > 0) ? (gdn[r] - op.offA[op.hB - 1] * hin) * op.rdA[op.hB] : 0.0;
+    hx[(size_t)(nhl + 2) * op.nrows + r] = 0.0;
 }
 
 // ---- K3: correction of the coupled bubbles, forward sweep, product with T, + gamma F; in place -----------------
 //   x_j = (z_j - w1_{j-1} x_{j-1} - w2_{j-2} x_{j-2}) rd_j ;  r_j = sum_d T(j,j+d) x_{j+d} + coupling to the hats + gamma f_j
-// Row j-2 of the product is emitted once x_j is known (window of five x values).
-__global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hedge,
+// Row j-2 of the product is emitted once x_j is known (window of five x values).  Blocks of 8 degrees: the 16
+// loads of a block (z and f) are issued before its dependent chain.
+__global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hx,
                                                      double *__restrict__ xb, DDPeers peers) {
-    __shared__ double srd[POP_DD_MAXQ + 4], sw1[POP_DD_MAXQ + 4], sw2[POP_DD_MAXQ + 4], st0[POP_DD_MAXQ + 4], st1[POP_DD_MAXQ + 4], st2[POP_DD_MAXQ + 4];
+    __shared__ double srd[POP_DD_MAXQ + 12], sw1[POP_DD_MAXQ + 12], sw2[POP_DD_MAXQ + 12], st0[POP_DD_MAXQ + 12], st1[POP_DD_MAXQ + 12], st2[POP_DD_MAXQ + 12];
     const int q = op.q;
     const bool mul = op.nbT >= 0;
-    // tables shifted by 2 so that index j-2 .. j+2 never needs a guard
-    for (int j = threadIdx.y * 32 + threadIdx.x; j < q + 4; j += 256) {
+    // tables shifted by 2 so that index j-2 .. j+2 never needs a guard (zero outside [0,q))
+    for (int j = threadIdx.y * 32 + threadIdx.x; j < q + 12; j += 256) {
         const int jj = j - 2;
         const bool in = jj >= 0 && jj < q;
         srd[j] = in ? op.rd[jj] : 0.0;
@@ -382,39 +430,49 @@ __global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restric
     double *p = X + r + ((int64_t)nhl + kl) * ld;
     const double *f = F ? F + r + ((int64_t)nhl + kl) * op.ldf : nullptr;
     const int64_t fs = (int64_t)ml * op.ldf;
-    // hats k-1, k, k+1 of this element (local indices kl-1, kl, kl+1; beyond my segment: the neighbours')
-    const double h0 = kl >= 1 ? X[r + (int64_t)(kl - 1) * ld] : hedge[r];
-    const double h1 = kl < nhl ? X[r + (int64_t)kl * ld] : hedge[op.nrows + r];
-    const double h2 = kl + 1 < nhl ? X[r + (int64_t)(kl + 1) * ld] : (kl + 1 == nhl ? hedge[op.nrows + r] : 0.0);
+    // hats k-1, k, k+1 of this element
+    const double h0 = hx[(size_t)kl * op.nrows + r], h1 = hx[(size_t)(kl + 1) * op.nrows + r], h2 = hx[(size_t)(kl + 2) * op.nrows + r];
     double xw0 = 0.0, xw1 = 0.0, xw2 = 0.0, xw3 = 0.0, xw4 = 0.0;   // x_j, x_{j-1}, ..., x_{j-4}
     double eL = 0.0, eR = 0.0;                                       // couplings of my edge element to a neighbour's product hat
-    for (int j = 0; j < q + 2; ++j) {
-        double v = 0.0;
-        if (j < q) {
-            v = p[(int64_t)j * js];
-            if (j < op.nb) {
-                const double *sb = op.S + (size_t)j * 3 * m + k;
-                v -= sb[0] * h0 + sb[m] * h1 + sb[2 * m] * h2;
-            }
-            v = (v - sw1[j + 1] * xw0 - sw2[j] * xw1) * srd[j + 2];   // w1_{j-1} x_{j-1}, w2_{j-2} x_{j-2}
-            if (!mul) p[(int64_t)j * js] = v;
-            else if (j < op.nbT) {
-                xb[((size_t)j * ml + kl) * op.nrows + r] = v;
-                const double *tb = op.Ts + (size_t)j * 3 * m + k;
-                eL += tb[0] * v;
-                eR += tb[2 * m] * v;
-            }
+    for (int j0 = 0; j0 < q + 2; j0 += 8) {
+        double zv[8], fv[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int j = j0 + s;
+            zv[s] = j < q ? p[(int64_t)j * js] : 0.0;
+            const int jo = j - 2;
+            fv[s] = (f && jo >= 0 && jo < q) ? f[(int64_t)jo * fs] : 0.0;
         }
-        xw4 = xw3; xw3 = xw2; xw2 = xw1; xw1 = xw0; xw0 = v;
-        const int jo = j - 2;
-        if (mul && jo >= 0) {
-            // T(jo,jo) x_jo + T(jo,jo+1) x_{jo+1} + T(jo-1,jo) x_{jo-1} + T(jo,jo+2) x_{jo+2} + T(jo-2,jo) x_{jo-2}
-            double acc = st0[jo + 2] * xw2 + st1[jo + 2] * xw1 + st1[jo + 1] * xw3 + st2[jo + 2] * xw0 + st2[jo] * xw4;
-            if (jo < op.nbT) {
-                const double *tb = op.Ts + (size_t)jo * 3 * m + k;
-                acc += tb[0] * h0 + tb[m] * h1 + tb[2 * m] * h2;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int j = j0 + s;
+            double v = 0.0;
+            if (j < q) {
+                v = zv[s];
+                if (j < op.nb) {
+                    const double *sb = op.S + (size_t)j * 3 * m + k;
+                    v -= sb[0] * h0 + sb[m] * h1 + sb[2 * m] * h2;
+                }
+                v = (v - sw1[j + 1] * xw0 - sw2[j] * xw1) * srd[j + 2];   // w1_{j-1} x_{j-1}, w2_{j-2} x_{j-2}
+                if (!mul) p[(int64_t)j * js] = v;
+                else if (j < op.nbT) {
+                    xb[((size_t)j * ml + kl) * op.nrows + r] = v;
+                    const double *tb = op.Ts + (size_t)j * 3 * m + k;
+                    eL += tb[0] * v;
+                    eR += tb[2 * m] * v;
+                }
             }
-            p[(int64_t)jo * js] = f ? fma(op.gamma, f[(int64_t)jo * fs], acc) : acc;
+            xw4 = xw3; xw3 = xw2; xw2 = xw1; xw1 = xw0; xw0 = v;
+            const int jo = j - 2;
+            if (mul && jo >= 0 && jo < q) {
+                // T(jo,jo) x_jo + T(jo,jo+1) x_{jo+1} + T(jo-1,jo) x_{jo-1} + T(jo,jo+2) x_{jo+2} + T(jo-2,jo) x_{jo-2}
+                double acc = st0[jo + 2] * xw2 + st1[jo + 2] * xw1 + st1[jo + 1] * xw3 + st2[jo + 2] * xw0 + st2[jo] * xw4;
+                if (jo < op.nbT) {
+                    const double *tb = op.Ts + (size_t)jo * 3 * m + k;
+                    acc += tb[0] * h0 + tb[m] * h1 + tb[2 * m] * h2;
+                }
+                p[(int64_t)jo * js] = fma(op.gamma, fv[s], acc);
+            }
         }
     }
     if (mul && op.world > 1) {
@@ -423,32 +481,28 @@ __global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restric
     }
 }
 
-// ---- K4: hat rows of the product (one thread per row) ------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_row_hat_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hedge,
+// ---- K4: hat rows of the product: one thread per (row, hat), reads the hats from hx, writes X -----------------------
+__global__ void __launch_bounds__(256) k_row_hat_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hx,
                                                      const double *__restrict__ xb, DDPeers peers) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= op.nrows) return;
-    const int m = op.m, ml = op.ml, nhl = op.nhl, k0 = op.k0;
-    const double *inD = peers.inbD[op.rank];
-    double hp = hedge[r], hc = nhl > 0 ? X[r] : 0.0;
-    for (int u = 0; u < nhl; ++u) {
-        const int i = op.hA + u;
-        const double hn = u + 1 < nhl ? X[r + (int64_t)(u + 1) * op.ld] : hedge[op.nrows + r];
-        double acc = op.TAd[i] * hc;
-        if (i + 1 < op.nh) acc += op.TAu[i] * hn;
-        if (i > 0) acc += op.TAu[i - 1] * hp;
-        for (int b = 0; b < op.nbT; ++b)
+    const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int u = blockIdx.y * 8 + threadIdx.y;
+    if (r >= op.nrows || u >= op.nhl) return;
+    const int m = op.m, ml = op.ml, k0 = op.k0;
+    const int i = op.hA + u;
+    const double hp = hx[(size_t)u * op.nrows + r], hc = hx[(size_t)(u + 1) * op.nrows + r], hn = hx[(size_t)(u + 2) * op.nrows + r];
+    double acc = op.TAd[i] * hc;
+    if (i + 1 < op.nh) acc += op.TAu[i] * hn;
+    if (i > 0) acc += op.TAu[i - 1] * hp;
+    for (int b = 0; b < op.nbT; ++b)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int kl = i - s + 1 - k0;
-                if (kl >= 0 && kl < ml) acc += op.Ts[((size_t)b * 3 + s) * m + k0 + kl] * xb[((size_t)b * ml + kl) * op.nrows + r];
-            }
-        if (u == 0 && op.rank > 0) acc += inD[r];
-        if (i == k0 + ml - 1 && op.rank < op.world - 1) acc += inD[op.nrows + r];
-        X[r + (int64_t)u * op.ld] = F ? fma(op.gamma, F[r + (int64_t)u * op.ldf], acc) : acc;
-        hp = hc;
-        hc = hn;
-    }
+        for (int s = 0; s < 3; ++s) {
+            const int kl = i - s + 1 - k0;
+            if (kl >= 0 && kl < ml) acc += op.Ts[((size_t)b * 3 + s) * m + k0 + kl] * xb[((size_t)b * ml + kl) * op.nrows + r];
+        }
+    const double *inD = peers.inbD[op.rank];
+    if (u == 0 && op.rank > 0) acc += inD[r];
+    if (i == k0 + ml - 1 && op.rank < op.world - 1) acc += inD[op.nrows + r];
+    X[r + (int64_t)u * op.ld] = F ? fma(op.gamma, F[r + (int64_t)u * op.ldf], acc) : acc;
 }
 
 // ------------------------------------------------------------------------------------
@@ -499,8 +553,8 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
     DDPeers peers;
     dd_peers(d, &peers);
     const dim3 blk2(32, 8), grd2((unsigned)((d->nrows + 31) / 32), (unsigned)((d->ml + 7) / 8));
+    const dim3 grdh((unsigned)((d->nrows + 31) / 32), (unsigned)((d->nhl + 7) / 8));
     const unsigned grd1 = (unsigned)((d->nrows + 127) / 128);
-    double *gdn = d->hedge;   // reused: hedge[0] holds the incoming downward values between K2b and K2c
     k_dd_pconst<<<1, 32, 0, ctx->stream>>>(op, d->pconst);
     k_row_bwd<<<grd2, blk2, 0, ctx->stream>>>(op, R);
     ctx->launches += 2;
@@ -509,19 +563,27 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
         ctx->launches++;
         if ((rc = dd_round(ctx, d, peers))) return rc;
     }
-    k_row_hat_a<<<grd1, 128, 0, ctx->stream>>>(op, R, peers);
-    ctx->launches++;
-    if ((rc = dd_round(ctx, d, peers))) return rc;
-    k_row_hat_b<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, gdn);
-    ctx->launches++;
-    if ((rc = dd_round(ctx, d, peers))) return rc;
-    k_row_hat_c<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, gdn, d->hedge);
-    k_row_fwd_mul<<<grd2, blk2, 0, ctx->stream>>>(op, R, (T && gamma != 0.0) ? F : nullptr, d->hedge, d->xb, peers);
-    ctx->launches += 2;
-    if (T) {
-        if ((rc = dd_round(ctx, d, peers))) return rc;
-        k_row_hat_mul<<<grd1, 128, 0, ctx->stream>>>(op, R, gamma != 0.0 ? F : nullptr, d->hedge, d->xb, peers);
+    if (d->nhl > 0) {
+        k_row_hat_gather<<<grdh, blk2, 0, ctx->stream>>>(op, R, peers);
         ctx->launches++;
+    }
+    if (d->world > 1) {
+        k_row_hat_dn1<<<grd1, 128, 0, ctx->stream>>>(op, R, peers);
+        ctx->launches++;
+        if ((rc = dd_round(ctx, d, peers))) return rc;
+    }
+    k_row_hat_b<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, d->gdn);
+    ctx->launches++;
+    if ((rc = dd_round(ctx, d, peers))) return rc;
+    k_row_hat_c<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, d->gdn, d->hx);
+    k_row_fwd_mul<<<grd2, blk2, 0, ctx->stream>>>(op, R, (T && gamma != 0.0) ? F : nullptr, d->hx, d->xb, peers);
+    ctx->launches += 2;
+    if (T && d->nhl > 0) {
+        if ((rc = dd_round(ctx, d, peers))) return rc;
+        k_row_hat_mul<<<grdh, blk2, 0, ctx->stream>>>(op, R, gamma != 0.0 ? F : nullptr, d->hx, d->xb, peers);
+        ctx->launches++;
+    } else if (T) {
+        if ((rc = dd_round(ctx, d, peers))) return rc;
     }
     POP_CUDA(cudaGetLastError());
     return POP_OK;
