@@ -97,3 +97,13 @@ def test_shard_bounds():
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_dd_columns_partition():
+    """Element decomposition (csrc/pop_row.cu): the ranks' local column sets partition the columns, hats first."""
+    for m, nh, q, world in ((128, 127, 63, 8), (16, 17, 5, 3), (9, 8, 4, 2), (4, 3, 2, 4)):
+        n = nh + m * q
+        allc = np.concatenate([P.dd_columns(m, nh, q, r, world) for r in range(world)])
+        assert sorted(allc.tolist()) == list(range(n))
+        c0 = P.dd_columns(m, nh, q, 0, world)
+        assert c0[0] == 0 and (len(c0) < 2 or c0[1] in (1, nh))

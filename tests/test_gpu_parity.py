@@ -368,6 +368,56 @@ def test_adi_small_vs_oracle():
     assert a2 <= a * (1 + 1e-9) and b2 >= b * (1 - 1e-9) and a2 > 0.5 * a and b2 < 1.5 * b
 
 
+@pytest.mark.parametrize("basis,m,N", [("dirichlet", 6, 10), ("c1", 5, 8), ("dirichlet", 9, 14)])
+def test_element_decomposed_row_half_step_and_adi(basis, m, N):
+    """csrc/pop_row.cu on one GPU (world = 1): the row half step R <- (R S^-1) T + gamma F against the oracle's
+    dense algebra, and the transpose-free ADI against the oracle's ADI (examples/adi_poisson.jl:42-59)."""
+    import ctypes as C
+    from pop_b200 import _lib as L
+    from pop_b200.arrowhead import _bind_stream
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    n = Mo.n
+    rng = np.random.default_rng(5)
+    Rm, Fm = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    if basis == "c1":
+        Kd = Kd + 0.3 * Md            # the pure Neumann Laplacian is singular: test the row kernels with a definite operator
+        K = K + 0.3 * M
+    Sd, Td = Kd + 3.7 * Md, 0.5 * Md - Kd
+    want = np.linalg.solve(Sd, Rm.T).T @ Td - 0.4 * Fm
+    dd = P.ElementDecomposition(M)
+    assert np.array_equal(dd.columns, np.arange(n))           # one rank: the local panel is the matrix itself
+    Fs = P.reversecholesky(K + 3.7 * M)
+    T = 0.5 * M - K
+    R, Fd = dd.panel(), dd.panel()
+    R.copy_(torch.from_numpy(Rm).cuda())
+    Fd.copy_(torch.from_numpy(Fm).cuda())
+    _bind_stream(M.data.ctx)
+    L.check(L.lib().pop_dd_row_half_step(M.data.ctx.handle, dd._h, Fs.factor._h, T.data._h, -0.4, Fd.data_ptr(), Fd.stride(1), R.data_ptr(), R.stride(1)))
+    torch.cuda.synchronize()
+    assert relerr(host(R), want) < TOL
+    # plain X / F on rows (no product)
+    R.copy_(torch.from_numpy(Rm).cuda())
+    L.check(L.lib().pop_dd_row_half_step(M.data.ctx.handle, dd._h, Fs.factor._h, None, 0.0, None, 0, R.data_ptr(), R.stride(1)))
+    torch.cuda.synchronize()
+    assert relerr(host(R), np.linalg.solve(Sd, Rm.T).T) < TOL
+    if basis == "dirichlet":
+        Y = rng.standard_normal((n, n))
+        Fa = Kd @ Y @ Md + Md @ Y @ Kd
+        lam = np.linalg.eigvals(np.linalg.solve(Kd, Md)).real
+        a, b = lam.min(), lam.max()
+        Fd.copy_(torch.from_numpy(Fa).cuda())
+        X = host(P.adi_poisson_dd(M, K, Fd, a, b, dd=dd))
+        Xo = O.adi_packed(Mo, Ko, Fa, a, b, -b, -a)
+        assert np.abs(X - Xo).max() <= 1e-11 * np.abs(Xo).max()
+        Yg = np.linalg.solve(Kd, X.T).T
+        res = Kd @ Yg @ Md + Md @ Yg @ Kd - Fa
+        assert np.linalg.norm(res) / np.linalg.norm(Fa) < 1e-12
+    dd.close()
+
+
 def test_heat_steps_vs_oracle():
     # examples/heat.jl:58-63 (1D) and its factored 2D extension
     m, N = 6, 10
