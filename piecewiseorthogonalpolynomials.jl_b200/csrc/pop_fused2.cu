@@ -25,6 +25,9 @@
 //     lanes run over elements, so every warp store is one run of consecutive doubles.
 #include <cstdlib>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "pop_fused2.cuh"
 
 // ------------------------------------------------------------------------------------
@@ -54,6 +57,22 @@ static f2_kernel_t f2_kernel(int rows, int npar, int variant, bool mul) {
 }
 
 static inline int ev2i(int x) { return (x + 1) & ~1; }
+
+// registers per thread of a kernel, queried once (the planner runs on every launch)
+static int f2_num_regs(const void *kern) {
+    static std::mutex mu;
+    static std::unordered_map<const void *, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(kern);
+    if (it != cache.end()) return it->second;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    cache[kern] = fa.numRegs;
+    return fa.numRegs;
+}
 
 static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, bool gamma_nonzero = false) {
     F2Plan pl = {};
@@ -92,11 +111,9 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
     const size_t limit = (size_t)ctx->max_smem_optin;
     pl.kern = f2_kernel(pl.rows, pl.npar, pl.variant, T != nullptr);
     if (!pl.kern) return pl;
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, pl.kern) != cudaSuccess) {
-        cudaGetLastError();
-        return pl;
-    }
+    struct { int numRegs; } fa;
+    fa.numRegs = f2_num_regs((const void *)pl.kern);
+    if (fa.numRegs <= 0) return pl;
     F2Plan first = {};
     for (int cs = 1; cs <= 8; cs *= 2) {
         if (T && cs > 1) break;

@@ -36,19 +36,25 @@ struct pop_dd {
     void *peer_slab[POP_DD_MAXWORLD];
     unsigned long long epoch;
     bool opened;
+    bool fake_peers;   // profiling aid (POP_DD_FAKE_PEERS=1): every peer aliases this rank's own slab, results are meaningless
     // local scratch
     double *hx;      // [nhl+3][nrows]  hats hA-1, my hats, hat hB, one zero row
     double *gdn;     // [nrows] value that entered the downward sweep
     double *xb;      // [4][ml][nrows] x of the coupled bubbles (for the hat rows of the product)
     double *pconst;  // [2][world]
     double *work;    // nrows x nloc work panel (leading dimension ld)
+    bool hats_merged;   // the hat phase runs as ONE kernel (k_row_hats): tile fits, grid co-resident
+    size_t hats_smem;
+    bool hats_planned;
 };
 
 struct DDPeers {
     double *inbA[POP_DD_MAXWORLD], *inbB[POP_DD_MAXWORLD], *inbC[POP_DD_MAXWORLD], *inbD[POP_DD_MAXWORLD];
-    unsigned long long *flags[POP_DD_MAXWORLD];
+    unsigned long long *flags[POP_DD_MAXWORLD];    // [world] epochs of whole-kernel rounds (+ error slot, + block counters)
+    unsigned long long *bflags[POP_DD_MAXWORLD];   // [row blocks of 32][POP_DD_MAXWORLD] epochs of per-row-block rounds
 };
 
+#define POP_DD_FLAG_BYTES 256
 static void dd_offsets(const pop_dd *d, size_t *oA, size_t *oB, size_t *oC, size_t *oD, size_t *oF) {
     const size_t nr = (size_t)d->nrows;
     *oA = 0;
@@ -68,6 +74,7 @@ static void dd_peers(const pop_dd *d, DDPeers *p) {
         p->inbC[r] = (double *)(base + oC);
         p->inbD[r] = (double *)(base + oD);
         p->flags[r] = (unsigned long long *)(base + oF);
+        p->bflags[r] = (unsigned long long *)(base + oF + POP_DD_FLAG_BYTES);
     }
 }
 
@@ -91,7 +98,7 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
     d->nloc = (int64_t)d->nhl + (int64_t)d->ml * q;
     size_t oA, oB, oC, oD, oF;
     dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
-    d->slab_bytes = oF + 256;
+    d->slab_bytes = oF + POP_DD_FLAG_BYTES + (size_t)((d->nrows + 31) / 32) * POP_DD_MAXWORLD * 8;
     cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&d->hx, (size_t)(d->nhl + 3) * d->nrows * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d->gdn, (size_t)d->nrows * 8);
@@ -103,8 +110,17 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
         return POP_ERR_ALLOC;
     }
     POP_CUDA(cudaMemsetAsync(d->slab, 0, d->slab_bytes, ctx->stream));
+    if (const char *e = getenv("POP_DD_FAKE_PEERS")) {
+        if (atoi(e) && world > 1) {
+            // one GPU stands in for rank `rank` of `world`: all waits pass at once, all peer stores land locally
+            d->fake_peers = true;
+            for (int r = 0; r < world; ++r) d->peer_slab[r] = d->slab;
+            POP_CUDA(cudaMemsetAsync((char *)d->slab + oF, 0x7f, POP_DD_MAXWORLD * 8, ctx->stream));
+            POP_CUDA(cudaMemsetAsync((char *)d->slab + oF + POP_DD_FLAG_BYTES, 0x7f, d->slab_bytes - oF - POP_DD_FLAG_BYTES, ctx->stream));
+        }
+    }
     POP_CUDA(cudaStreamSynchronize(ctx->stream));
-    d->opened = world == 1;
+    d->opened = world == 1 || d->fake_peers;
     *out = d;
     return POP_OK;
 }
@@ -139,7 +155,7 @@ extern "C" int pop_dd_destroy(pop_ctx *ctx, pop_dd *d) {
     if (!d) return POP_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (int r = 0; r < d->world; ++r)
-        if (r != d->rank && d->peer_slab[r]) cudaIpcCloseMemHandle(d->peer_slab[r]);
+        if (!d->fake_peers && r != d->rank && d->peer_slab[r]) cudaIpcCloseMemHandle(d->peer_slab[r]);
     cudaFree(d->slab);
     cudaFree(d->hx);
     cudaFree(d->gdn);
@@ -181,51 +197,73 @@ struct RowOp {
     int kb[POP_DD_MAXWORLD + 1];
 };
 
-// flags: the same epoch protocol as pop_dist.cu
-__global__ void k_dd_signal(DDPeers peers, int world, int me, unsigned long long ep) {
-    const int r = threadIdx.x;
-    if (r < world) {
-        __threadfence_system();
-        volatile unsigned long long *p = peers.flags[r] + me;
-        *p = ep;
-        __threadfence_system();
-    }
-}
-__global__ void k_dd_wait(volatile unsigned long long *flags, int world, unsigned long long ep) {
-    const int r = threadIdx.x;
-    if (r < world) {
+// Flags: the epoch protocol of pop_dist.cu, folded into the kernels (no separate signal / wait launches).
+// A producing kernel ends with dd_signal_last: the last block to finish tells every rank "my data of epoch
+// ep_signal has landed".  A consuming kernel starts with dd_wait_all: every block polls the local flags until
+// all ranks have reached ep_wait.  The waited-for data is produced by kernels that never wait on this one, so
+// the polling cannot deadlock whatever the residency of the grid.
+struct DDSync {
+    unsigned long long *peer_flags[POP_DD_MAXWORLD];   // the flag arrays of all ranks (mine included)
+    unsigned int *cnt;                                 // block counter of the producing kernel (zero on entry)
+    unsigned long long ep_wait, ep_signal;             // 0: no wait / no signal
+    int world, me;
+};
+
+__device__ __forceinline__ void dd_wait_all(const DDSync &sy) {
+    if (sy.ep_wait == 0) return;
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < sy.world) {
+        volatile unsigned long long *fl = sy.peer_flags[sy.me];
         long long spins = 0;
-        while (flags[r] < ep) {
-            __nanosleep(128);
-            if (++spins > 80000000LL) {   // ~10 s: a peer died
-                flags[POP_DD_MAXWORLD] = ep;
+        while (fl[t] < sy.ep_wait) {
+            __nanosleep(64);
+            if (++spins > 100000000LL) {   // a peer died: do not hang the device
+                fl[POP_DD_MAXWORLD] = sy.ep_wait;
                 break;
             }
         }
+        __threadfence_system();
     }
-    __threadfence_system();
+    __syncthreads();
 }
 
-static int dd_round(pop_ctx *ctx, pop_dd *d, const DDPeers &peers) {
-    if (d->world == 1) return POP_OK;
-    const unsigned long long ep = ++d->epoch;
-    k_dd_signal<<<1, 32, 0, ctx->stream>>>(peers, d->world, d->rank, ep);
-    k_dd_wait<<<1, 32, 0, ctx->stream>>>(peers.flags[d->rank], d->world, ep);
-    ctx->launches += 2;
-    POP_CUDA(cudaGetLastError());
-    return POP_OK;
+__device__ __forceinline__ void dd_signal_last(const DDSync &sy) {
+    if (sy.ep_signal == 0) return;
+    __syncthreads();
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        __threadfence_system();
+        const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned prev = atomicAdd(sy.cnt, 1u);
+        if (prev == nblocks - 1) {
+            *sy.cnt = 0;
+            __threadfence_system();
+            for (int r = 0; r < sy.world; ++r) {
+                volatile unsigned long long *p = sy.peer_flags[r] + sy.me;
+                *p = sy.ep_signal;
+            }
+            __threadfence_system();
+        }
+    }
 }
 
 // multipliers of every rank's hat segment: Pdn[g] = prod(-off[i] rd[i]), Pup[g] = prod(-off[i-1] rd[i]) over its hats
-__global__ void k_dd_pconst(RowOp op, double *pc) {
+// One block per factor: ptrs[2f] = rdA, ptrs[2f+1] = offA of factor f; pc + f*2*POP_DD_MAXWORLD receives its multipliers.
+struct DDBounds {
+    int kb[POP_DD_MAXWORLD + 1];
+    int world, nh;
+};
+__global__ void k_dd_pconst(DDBounds bd, const double *const *__restrict__ ptrs, const double *rdA1, const double *offA1, double *pc) {
     const int g = threadIdx.x;
-    if (g >= op.world) return;
-    const int a = op.kb[g], b = g == op.world - 1 ? op.nh : min(op.nh, op.kb[g + 1]);
+    if (g >= bd.world) return;
+    const double *rdA = ptrs ? ptrs[2 * blockIdx.x] : rdA1, *offA = ptrs ? ptrs[2 * blockIdx.x + 1] : offA1;
+    pc += (size_t)blockIdx.x * 2 * POP_DD_MAXWORLD;
+    const int a = bd.kb[g], b = g == bd.world - 1 ? bd.nh : min(bd.nh, bd.kb[g + 1]);
     double pd = 1.0, pu = 1.0;
     for (int i = a; i < b; ++i) {
-        const double rd = op.rdA[i];
-        pd *= -(i < op.nh - 1 ? op.offA[i] : 0.0) * rd;
-        pu *= -(i > 0 ? op.offA[i - 1] : 0.0) * rd;
+        const double rd = rdA[i];
+        pd *= -(i < bd.nh - 1 ? offA[i] : 0.0) * rd;
+        pu *= -(i > 0 ? offA[i - 1] : 0.0) * rd;
     }
     pc[g] = pd;
     pc[POP_DD_MAXWORLD + g] = pu;
@@ -233,7 +271,7 @@ __global__ void k_dd_pconst(RowOp op, double *pc) {
 
 // ---- K1: backward bubble sweep along the rows:  z_j = (b_j - w1_j z_{j+1} - w2_j z_{j+2}) rd_j ------------
 // thread <-> (row r, local element kl); the 32 lanes of a warp are 32 consecutive rows.
-__global__ void __launch_bounds__(256) k_row_bwd(RowOp op, double *__restrict__ X) {
+__global__ void __launch_bounds__(256) k_row_bwd(RowOp op, double *__restrict__ X, DDPeers peers, DDSync sy) {
     __shared__ double srd[POP_DD_MAXQ], sw1[POP_DD_MAXQ], sw2[POP_DD_MAXQ];
     const int q = op.q;
     for (int j = threadIdx.y * 32 + threadIdx.x; j < q; j += 256) {
@@ -244,53 +282,50 @@ __global__ void __launch_bounds__(256) k_row_bwd(RowOp op, double *__restrict__ 
     __syncthreads();
     const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int kl = blockIdx.y * 8 + threadIdx.y;
-    if (r >= op.nrows || kl >= op.ml) return;
-    double *p = X + r + ((int64_t)op.nhl + kl) * op.ld;
-    const int64_t js = (int64_t)op.ml * op.ld;
-    double z1 = 0.0, z2 = 0.0;
-    int j = q - 1;
-    for (; j >= 7; j -= 8) {
-        double v[8];
+    if (r < op.nrows && kl < op.ml) {
+        double *p = X + r + ((int64_t)op.nhl + kl) * op.ld;
+        const int64_t js = (int64_t)op.ml * op.ld;
+        double z1 = 0.0, z2 = 0.0;
+        int j = q - 1;
+        for (; j >= 7; j -= 8) {
+            double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j - u) * js];
+            for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j - u) * js];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const double t = (v[u] - sw1[j - u] * z1 - sw2[j - u] * z2) * srd[j - u];
+            for (int u = 0; u < 8; ++u) {
+                const double t = (v[u] - sw1[j - u] * z1 - sw2[j - u] * z2) * srd[j - u];
+                z2 = z1;
+                z1 = t;
+                v[u] = t;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) p[(int64_t)(j - u) * js] = v[u];
+        }
+        for (; j >= 0; --j) {
+            const double t = (p[(int64_t)j * js] - sw1[j] * z1 - sw2[j] * z2) * srd[j];
+            p[(int64_t)j * js] = t;
             z2 = z1;
             z1 = t;
-            v[u] = t;
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) p[(int64_t)(j - u) * js] = v[u];
+        // couplings of my edge elements to the neighbours' hats (the thread re-reads its own coupled bubbles)
+        const int m = op.m;
+        if (kl == 0 && op.rank > 0) {   // element k0, slot 0 -> hat k0-1 (last hat of the left neighbour)
+            double acc = 0.0;
+            for (int b = 0; b < op.nb; ++b) acc += op.S[((size_t)b * 3 + 0) * m + op.k0] * p[(int64_t)b * js];
+            peers.inbA[op.rank - 1][op.nrows + r] = acc;
+        }
+        if (kl == op.ml - 1 && op.rank < op.world - 1) {   // element k1-1, slot 2 -> hat k1 (first hat of the right neighbour)
+            double acc = 0.0;
+            for (int b = 0; b < op.nb; ++b) acc += op.S[((size_t)b * 3 + 2) * m + op.k0 + kl] * p[(int64_t)b * js];
+            peers.inbA[op.rank + 1][r] = acc;
+        }
     }
-    for (; j >= 0; --j) {
-        const double t = (p[(int64_t)j * js] - sw1[j] * z1 - sw2[j] * z2) * srd[j];
-        p[(int64_t)j * js] = t;
-        z2 = z1;
-        z1 = t;
-    }
-}
-
-// ---- K2a0: couplings of my edge elements to the neighbours' hats (one thread per row) ----------------------
-__global__ void __launch_bounds__(128) k_row_edge(RowOp op, const double *__restrict__ X, DDPeers peers) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= op.nrows) return;
-    const int m = op.m;
-    if (op.rank > 0) {   // element k0, slot t = 0 -> hat k0-1 (last hat of the left neighbour)
-        double acc = 0.0;
-        for (int b = 0; b < op.nb; ++b) acc += op.S[((size_t)b * 3 + 0) * m + op.k0] * X[r + ((int64_t)op.nhl + (int64_t)b * op.ml) * op.ld];
-        peers.inbA[op.rank - 1][op.nrows + r] = acc;
-    }
-    if (op.rank < op.world - 1) {   // element k1-1, slot t = 2 -> hat k1 (first hat of the right neighbour)
-        double acc = 0.0;
-        const int kl = op.ml - 1;
-        for (int b = 0; b < op.nb; ++b) acc += op.S[((size_t)b * 3 + 2) * m + op.k0 + kl] * X[r + ((int64_t)op.nhl + (int64_t)b * op.ml + kl) * op.ld];
-        peers.inbA[op.rank + 1][r] = acc;
-    }
+    dd_signal_last(sy);
 }
 
 // ---- K2a: hat right-hand sides of my segment: one thread per (row, hat), fully parallel ------------------------
-__global__ void __launch_bounds__(256) k_row_hat_gather(RowOp op, double *__restrict__ X, DDPeers peers) {
+__global__ void __launch_bounds__(256) k_row_hat_gather(RowOp op, double *__restrict__ X, DDPeers peers, DDSync sy) {
+    dd_wait_all(sy);
     const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int u = blockIdx.y * 8 + threadIdx.y;
     if (r >= op.nrows || u >= op.nhl) return;
@@ -345,35 +380,42 @@ __device__ __forceinline__ double dd_chain(double *__restrict__ xr, const int64_
 }
 
 // ---- K2b: first pass of the downward sweep (zero incoming): my segment's map for the ranks below me --------------
-__global__ void __launch_bounds__(128) k_row_hat_dn1(RowOp op, double *__restrict__ X, DDPeers peers) {
+__global__ void __launch_bounds__(128) k_row_hat_dn1(RowOp op, double *__restrict__ X, DDPeers peers, DDSync sy) {
     DD_HAT_TABLES()
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= op.nrows) return;
-    const double t = dd_chain<true, false>(X + r, op.ld, op.nhl, s_rd, s_cdn, 0.0);
-    for (int g = 0; g < op.rank; ++g) peers.inbB[g][(size_t)op.rank * op.nrows + r] = t;
+    if (r < op.nrows) {
+        const double t = dd_chain<true, false>(X + r, op.ld, op.nhl, s_rd, s_cdn, 0.0);
+        for (int g = 0; g < op.rank; ++g) peers.inbB[g][(size_t)op.rank * op.nrows + r] = t;
+    }
+    dd_signal_last(sy);
 }
 
 // ---- K2c: downward sweep with the exact incoming value, first pass of the upward sweep -----------------------
-__global__ void __launch_bounds__(128) k_row_hat_b(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ gdn) {
+__global__ void __launch_bounds__(128) k_row_hat_b(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ gdn,
+                                                   DDSync sy) {
     DD_HAT_TABLES()
+    dd_wait_all(sy);
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= op.nrows) return;
-    const double *inB = peers.inbB[op.rank];
-    double G = 0.0;
-    for (int g = op.world - 1; g > op.rank; --g) G = fma(pc[g], G, inB[(size_t)g * op.nrows + r]);
-    gdn[r] = G;
-    dd_chain<true, true>(X + r, op.ld, op.nhl, s_rd, s_cdn, G);
-    if (op.world > 1) {
-        const double t = dd_chain<false, false>(X + r, op.ld, op.nhl, s_rd, s_cup, 0.0);
-        for (int g = op.rank + 1; g < op.world; ++g) peers.inbC[g][(size_t)op.rank * op.nrows + r] = t;
+    if (r < op.nrows) {
+        const double *inB = peers.inbB[op.rank];
+        double G = 0.0;
+        for (int g = op.world - 1; g > op.rank; --g) G = fma(pc[g], G, inB[(size_t)g * op.nrows + r]);
+        gdn[r] = G;
+        dd_chain<true, true>(X + r, op.ld, op.nhl, s_rd, s_cdn, G);
+        if (op.world > 1) {
+            const double t = dd_chain<false, false>(X + r, op.ld, op.nhl, s_rd, s_cup, 0.0);
+            for (int g = op.rank + 1; g < op.world; ++g) peers.inbC[g][(size_t)op.rank * op.nrows + r] = t;
+        }
     }
+    dd_signal_last(sy);
 }
 
 // ---- K2d: upward sweep with the exact incoming value; hx = my hats with the neighbours' hats hA-1 and hB around them ----
 // hx[(u+1)*nrows + r] = hat hA+u, hx[r] = hat hA-1, hx[(nhl+1)*nrows + r] = hat hB, one more zero row behind
 __global__ void __launch_bounds__(128) k_row_hat_c(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, const double *__restrict__ gdn,
-                                                   double *__restrict__ hx) {
+                                                   double *__restrict__ hx, DDSync sy) {
     DD_HAT_TABLES()
+    dd_wait_all(sy);
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= op.nrows) return;
     const double *inC = peers.inbC[op.rank];
@@ -401,12 +443,134 @@ __global__ void __launch_bounds__(128) k_row_hat_c(RowOp op, double *__restrict_
     hx[(size_t)(nhl + 2) * op.nrows + r] = 0.0;
 }
 
+// ---- K2 (merged): the whole hat phase of 32 rows in one block ------------------------------------------------
+// Block = 32 rows x 4 lanes of hats.  The hat right-hand sides of the 32 rows are gathered into a shared-memory
+// tile [nhl][32] by all 128 threads; the recurrences then run on the tile (lane x of warp 0 owns row x: no global
+// latency inside the dependent chains); the two segment-map exchanges use flags PER ROW BLOCK, so a block only
+// waits for the same rows of its peers; the result leaves through all 128 threads again.  With peers the grid
+// must be co-resident (checked by the host; the per-kernel path above is the fallback).
+__device__ __forceinline__ void dd_block_exchange(const DDPeers &peers, int world, int me, unsigned long long ep) {
+    __syncthreads();   // the block's peer stores are issued
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    const size_t slot = (size_t)blockIdx.x * POP_DD_MAXWORLD;
+    if (t == 0) {
+        __threadfence_system();
+        for (int r = 0; r < world; ++r) {
+            volatile unsigned long long *p = peers.bflags[r] + slot + me;
+            *p = ep;
+        }
+    }
+    if (t < world) {
+        volatile unsigned long long *fl = peers.bflags[me] + slot;
+        long long spins = 0;
+        while (fl[t] < ep) {
+            if (++spins > 400000000LL) {   // a peer died: do not hang the device
+                volatile unsigned long long *err = peers.flags[me];
+                err[POP_DD_MAXWORLD] = ep;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_row_hats(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ hx,
+                                                  DDSync sy, unsigned long long epB, unsigned long long epC) {
+    extern __shared__ double sm_h[];
+    const int nhl = op.nhl, nhlp = (nhl + 1) & ~1;
+    double *s_rd = sm_h, *s_cdn = s_rd + nhlp, *s_cup = s_cdn + nhlp, *tile = s_cup + nhlp;
+    const int x = threadIdx.x, y = threadIdx.y, t = y * 32 + x;
+    for (int u = t; u < nhl; u += 128) {
+        const int i = op.hA + u;
+        const double rdv = op.rdA[i];
+        s_rd[u] = rdv;
+        s_cdn[u] = (i < op.nh - 1 ? op.offA[i] : 0.0) * rdv;
+        s_cup[u] = (i > 0 ? op.offA[i - 1] : 0.0) * rdv;
+    }
+    dd_wait_all(sy);   // the neighbours' edge couplings have landed
+    const int64_t r = (int64_t)blockIdx.x * 32 + x;
+    const bool rv = r < op.nrows;
+    const int m = op.m, ml = op.ml, k0 = op.k0, me = op.rank, world = op.world;
+    const bool multi = world > 1;
+    // gather: hat right-hand sides minus the couplings to the (backward-swept) bubbles
+    if (rv) {
+        const double *inA = peers.inbA[me];
+        for (int u = y; u < nhl; u += 4) {
+            const int i = op.hA + u;
+            double v = X[r + (int64_t)u * op.ld];
+            for (int b = 0; b < op.nb; ++b)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int kl = i - s + 1 - k0;
+                    if (kl >= 0 && kl < ml) v -= op.S[((size_t)b * 3 + s) * m + k0 + kl] * X[r + ((int64_t)nhl + (int64_t)b * ml + kl) * op.ld];
+                }
+            if (u == 0 && me > 0) v -= __ldcg(inA + r);
+            if (i == k0 + ml - 1 && me < world - 1) v -= __ldcg(inA + op.nrows + r);
+            tile[u * 32 + x] = v;
+        }
+    }
+    __syncthreads();
+    double *col = tile + x;
+    double Gdn = 0.0, Gup = 0.0;
+    if (multi) {
+        if (y == 0 && rv) {   // my segment's downward map with zero incoming, for the ranks below me
+            double h = 0.0;
+            for (int u = nhl - 1; u >= 0; --u) h = fma(-s_cdn[u], h, col[u * 32] * s_rd[u]);
+            for (int g = 0; g < me; ++g) peers.inbB[g][(size_t)me * op.nrows + r] = h;
+        }
+        dd_block_exchange(peers, world, me, epB);
+        if (y == 0 && rv) {
+            const double *inB = peers.inbB[me];
+            for (int g = world - 1; g > me; --g) Gdn = fma(pc[g], Gdn, __ldcg(inB + (size_t)g * op.nrows + r));
+        }
+    }
+    if (y == 0 && rv) {
+        double h = Gdn;
+        for (int u = nhl - 1; u >= 0; --u) {
+            h = fma(-s_cdn[u], h, col[u * 32] * s_rd[u]);
+            col[u * 32] = h;
+        }
+        if (multi) {
+            h = 0.0;
+            for (int u = 0; u < nhl; ++u) h = fma(-s_cup[u], h, col[u * 32] * s_rd[u]);
+            for (int g = me + 1; g < world; ++g) peers.inbC[g][(size_t)me * op.nrows + r] = h;
+        }
+    }
+    if (multi) {
+        dd_block_exchange(peers, world, me, epC);
+        if (y == 0 && rv) {
+            const double *inC = peers.inbC[me];
+            for (int g = 0; g < me; ++g) Gup = fma(pc[POP_DD_MAXWORLD + g], Gup, __ldcg(inC + (size_t)g * op.nrows + r));
+        }
+    }
+    if (y == 0 && rv) {
+        double h = Gup;
+        for (int u = 0; u < nhl; ++u) {
+            h = fma(-s_cup[u], h, col[u * 32] * s_rd[u]);
+            col[u * 32] = h;
+        }
+        hx[r] = me > 0 ? Gup : 0.0;   // hat hA-1
+        // hat hB = (y[hB] - off[hB-1] h[hB-1]) rd[hB], y[hB] being the value that entered my downward sweep
+        hx[(size_t)(nhl + 1) * op.nrows + r] = (op.hB < op.nh && nhl > 0) ? (Gdn - op.offA[op.hB - 1] * h) * op.rdA[op.hB] : 0.0;
+        hx[(size_t)(nhl + 2) * op.nrows + r] = 0.0;
+    }
+    __syncthreads();
+    if (rv)
+        for (int u = y; u < nhl; u += 4) {
+            const double h = tile[u * 32 + x];
+            X[r + (int64_t)u * op.ld] = h;
+            hx[(size_t)(u + 1) * op.nrows + r] = h;
+        }
+}
+
 // ---- K3: correction of the coupled bubbles, forward sweep, product with T, + gamma F; in place -----------------
 //   x_j = (z_j - w1_{j-1} x_{j-1} - w2_{j-2} x_{j-2}) rd_j ;  r_j = sum_d T(j,j+d) x_{j+d} + coupling to the hats + gamma f_j
 // Row j-2 of the product is emitted once x_j is known (window of five x values).  Blocks of 8 degrees: the 16
 // loads of a block (z and f) are issued before its dependent chain.
-__global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hx,
-                                                     double *__restrict__ xb, DDPeers peers) {
+template <int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_row_fwd_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hx,
+                                                     double *__restrict__ xb, DDPeers peers, DDSync sy) {
     __shared__ double srd[POP_DD_MAXQ + 12], sw1[POP_DD_MAXQ + 12], sw2[POP_DD_MAXQ + 12], st0[POP_DD_MAXQ + 12], st1[POP_DD_MAXQ + 12], st2[POP_DD_MAXQ + 12];
     const int q = op.q;
     const bool mul = op.nbT >= 0;
@@ -424,66 +588,69 @@ __global__ void __launch_bounds__(256) k_row_fwd_mul(RowOp op, double *__restric
     __syncthreads();
     const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int kl = blockIdx.y * 8 + threadIdx.y;
-    if (r >= op.nrows || kl >= op.ml) return;
-    const int m = op.m, ml = op.ml, nhl = op.nhl, k = op.k0 + kl;
-    const int64_t ld = op.ld, js = (int64_t)ml * ld;
-    double *p = X + r + ((int64_t)nhl + kl) * ld;
-    const double *f = F ? F + r + ((int64_t)nhl + kl) * op.ldf : nullptr;
-    const int64_t fs = (int64_t)ml * op.ldf;
-    // hats k-1, k, k+1 of this element
-    const double h0 = hx[(size_t)kl * op.nrows + r], h1 = hx[(size_t)(kl + 1) * op.nrows + r], h2 = hx[(size_t)(kl + 2) * op.nrows + r];
-    double xw0 = 0.0, xw1 = 0.0, xw2 = 0.0, xw3 = 0.0, xw4 = 0.0;   // x_j, x_{j-1}, ..., x_{j-4}
-    double eL = 0.0, eR = 0.0;                                       // couplings of my edge element to a neighbour's product hat
-    for (int j0 = 0; j0 < q + 2; j0 += 8) {
-        double zv[8], fv[8];
+    if (r < op.nrows && kl < op.ml) {
+        const int m = op.m, ml = op.ml, nhl = op.nhl, k = op.k0 + kl;
+        const int64_t ld = op.ld, js = (int64_t)ml * ld;
+        double *p = X + r + ((int64_t)nhl + kl) * ld;
+        const double *f = F ? F + r + ((int64_t)nhl + kl) * op.ldf : nullptr;
+        const int64_t fs = (int64_t)ml * op.ldf;
+        // hats k-1, k, k+1 of this element
+        const double h0 = hx[(size_t)kl * op.nrows + r], h1 = hx[(size_t)(kl + 1) * op.nrows + r], h2 = hx[(size_t)(kl + 2) * op.nrows + r];
+        double xw0 = 0.0, xw1 = 0.0, xw2 = 0.0, xw3 = 0.0, xw4 = 0.0;   // x_j, x_{j-1}, ..., x_{j-4}
+        double eL = 0.0, eR = 0.0;                                       // couplings of my edge element to a neighbour's product hat
+        for (int j0 = 0; j0 < q + 2; j0 += DEPTH) {
+            double zv[DEPTH], fv[DEPTH];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const int j = j0 + s;
-            zv[s] = j < q ? p[(int64_t)j * js] : 0.0;
-            const int jo = j - 2;
-            fv[s] = (f && jo >= 0 && jo < q) ? f[(int64_t)jo * fs] : 0.0;
-        }
+            for (int s = 0; s < DEPTH; ++s) {
+                const int j = j0 + s;
+                zv[s] = j < q ? p[(int64_t)j * js] : 0.0;
+                const int jo = j - 2;
+                fv[s] = (f && jo >= 0 && jo < q) ? f[(int64_t)jo * fs] : 0.0;
+            }
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const int j = j0 + s;
-            double v = 0.0;
-            if (j < q) {
-                v = zv[s];
-                if (j < op.nb) {
-                    const double *sb = op.S + (size_t)j * 3 * m + k;
-                    v -= sb[0] * h0 + sb[m] * h1 + sb[2 * m] * h2;
+            for (int s = 0; s < DEPTH; ++s) {
+                const int j = j0 + s;
+                double v = 0.0;
+                if (j < q) {
+                    v = zv[s];
+                    if (j < op.nb) {
+                        const double *sb = op.S + (size_t)j * 3 * m + k;
+                        v -= sb[0] * h0 + sb[m] * h1 + sb[2 * m] * h2;
+                    }
+                    v = (v - sw1[j + 1] * xw0 - sw2[j] * xw1) * srd[j + 2];   // w1_{j-1} x_{j-1}, w2_{j-2} x_{j-2}
+                    if (!mul) p[(int64_t)j * js] = v;
+                    else if (j < op.nbT) {
+                        xb[((size_t)j * ml + kl) * op.nrows + r] = v;
+                        const double *tb = op.Ts + (size_t)j * 3 * m + k;
+                        eL += tb[0] * v;
+                        eR += tb[2 * m] * v;
+                    }
                 }
-                v = (v - sw1[j + 1] * xw0 - sw2[j] * xw1) * srd[j + 2];   // w1_{j-1} x_{j-1}, w2_{j-2} x_{j-2}
-                if (!mul) p[(int64_t)j * js] = v;
-                else if (j < op.nbT) {
-                    xb[((size_t)j * ml + kl) * op.nrows + r] = v;
-                    const double *tb = op.Ts + (size_t)j * 3 * m + k;
-                    eL += tb[0] * v;
-                    eR += tb[2 * m] * v;
+                xw4 = xw3; xw3 = xw2; xw2 = xw1; xw1 = xw0; xw0 = v;
+                const int jo = j - 2;
+                if (mul && jo >= 0 && jo < q) {
+                    // T(jo,jo) x_jo + T(jo,jo+1) x_{jo+1} + T(jo-1,jo) x_{jo-1} + T(jo,jo+2) x_{jo+2} + T(jo-2,jo) x_{jo-2}
+                    double acc = st0[jo + 2] * xw2 + st1[jo + 2] * xw1 + st1[jo + 1] * xw3 + st2[jo + 2] * xw0 + st2[jo] * xw4;
+                    if (jo < op.nbT) {
+                        const double *tb = op.Ts + (size_t)jo * 3 * m + k;
+                        acc += tb[0] * h0 + tb[m] * h1 + tb[2 * m] * h2;
+                    }
+                    p[(int64_t)jo * js] = fma(op.gamma, fv[s], acc);
                 }
             }
-            xw4 = xw3; xw3 = xw2; xw2 = xw1; xw1 = xw0; xw0 = v;
-            const int jo = j - 2;
-            if (mul && jo >= 0 && jo < q) {
-                // T(jo,jo) x_jo + T(jo,jo+1) x_{jo+1} + T(jo-1,jo) x_{jo-1} + T(jo,jo+2) x_{jo+2} + T(jo-2,jo) x_{jo-2}
-                double acc = st0[jo + 2] * xw2 + st1[jo + 2] * xw1 + st1[jo + 1] * xw3 + st2[jo + 2] * xw0 + st2[jo] * xw4;
-                if (jo < op.nbT) {
-                    const double *tb = op.Ts + (size_t)jo * 3 * m + k;
-                    acc += tb[0] * h0 + tb[m] * h1 + tb[2 * m] * h2;
-                }
-                p[(int64_t)jo * js] = fma(op.gamma, fv[s], acc);
-            }
+        }
+        if (mul && op.world > 1) {
+            if (kl == 0 && op.rank > 0) peers.inbD[op.rank - 1][op.nrows + r] = eL;            // element k0 -> hat k0-1
+            if (kl == ml - 1 && op.rank < op.world - 1) peers.inbD[op.rank + 1][r] = eR;      // element k1-1 -> hat k1
         }
     }
-    if (mul && op.world > 1) {
-        if (kl == 0 && op.rank > 0) peers.inbD[op.rank - 1][op.nrows + r] = eL;            // element k0 -> hat k0-1
-        if (kl == ml - 1 && op.rank < op.world - 1) peers.inbD[op.rank + 1][r] = eR;      // element k1-1 -> hat k1
-    }
+    dd_signal_last(sy);
 }
 
 // ---- K4: hat rows of the product: one thread per (row, hat), reads the hats from hx, writes X -----------------------
 __global__ void __launch_bounds__(256) k_row_hat_mul(RowOp op, double *__restrict__ X, const double *__restrict__ F, const double *__restrict__ hx,
-                                                     const double *__restrict__ xb, DDPeers peers) {
+                                                     const double *__restrict__ xb, DDPeers peers, DDSync sy) {
+    dd_wait_all(sy);
     const int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int u = blockIdx.y * 8 + threadIdx.y;
     if (r >= op.nrows || u >= op.nhl) return;
@@ -544,46 +711,103 @@ static int dd_make_op(const pop_dd *d, const pop_arrowhead *U, const pop_arrowhe
     return POP_OK;
 }
 
+// one kernel for the hat phase if its tile fits in shared memory and (with peers) the whole grid is co-resident
+static void dd_plan_hats(pop_ctx *ctx, pop_dd *d) {
+    d->hats_planned = true;
+    d->hats_merged = false;
+    if (const char *e = getenv("POP_DD_SPLIT_HATS"))
+        if (atoi(e)) return;
+    const int nhlp = (d->nhl + 1) & ~1;
+    const size_t smem = ((size_t)3 * nhlp + (size_t)d->nhl * 32) * 8;
+    if (smem > (size_t)ctx->max_smem_optin || smem > 160 * 1024) return;
+    if (cudaFuncSetAttribute(k_row_hats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (d->world > 1) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row_hats, 128, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        if ((d->nrows + 31) / 32 > (int64_t)occ * ctx->sm_count) return;
+    }
+    d->hats_smem = smem;
+    d->hats_merged = true;
+}
+
 // rows of R (nrows x nloc, leading dimension d->ld):  r <- T (S^{-1} r) + gamma f ; T may be null (plain solve)
 static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *F, int64_t ldf,
-                            double *R) {
+                            double *R, const double *pc) {
     RowOp op;
     int rc = dd_make_op(d, U, T, gamma, ldf, &op);
     if (rc) return rc;
     DDPeers peers;
     dd_peers(d, &peers);
+    const bool multi = d->world > 1;
+    if (!d->hats_planned) dd_plan_hats(ctx, d);
+    // epochs of the four exchange rounds: A edge couplings, B downward maps, C upward maps, D product edges
+    const unsigned long long epA = multi ? ++d->epoch : 0, epB = multi ? ++d->epoch : 0, epC = multi ? ++d->epoch : 0,
+                             epD = (multi && T) ? ++d->epoch : 0;
+    size_t oA, oB, oC, oD, oF;
+    dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
+    unsigned int *cnt = (unsigned int *)((char *)d->slab + oF + 192);
+    auto sync = [&](unsigned long long wait, unsigned long long signal, int slot) {
+        DDSync sy;
+        for (int r = 0; r < POP_DD_MAXWORLD; ++r) sy.peer_flags[r] = r < d->world ? peers.flags[r] : nullptr;
+        sy.cnt = cnt + slot;
+        sy.ep_wait = wait;
+        sy.ep_signal = signal;
+        sy.world = d->world;
+        sy.me = d->rank;
+        return sy;
+    };
     const dim3 blk2(32, 8), grd2((unsigned)((d->nrows + 31) / 32), (unsigned)((d->ml + 7) / 8));
-    const dim3 grdh((unsigned)((d->nrows + 31) / 32), (unsigned)((d->nhl + 7) / 8));
+    const dim3 grdh((unsigned)((d->nrows + 31) / 32), (unsigned)std::max((d->nhl + 7) / 8, 1));
     const unsigned grd1 = (unsigned)((d->nrows + 127) / 128);
-    k_dd_pconst<<<1, 32, 0, ctx->stream>>>(op, d->pconst);
-    k_row_bwd<<<grd2, blk2, 0, ctx->stream>>>(op, R);
-    ctx->launches += 2;
-    if (d->world > 1) {
-        k_row_edge<<<grd1, 128, 0, ctx->stream>>>(op, R, peers);
+    if (!pc) {
+        DDBounds bd;
+        for (int r = 0; r <= d->world; ++r) bd.kb[r] = d->kb[r];
+        bd.world = d->world; bd.nh = d->nh;
+        k_dd_pconst<<<1, 32, 0, ctx->stream>>>(bd, nullptr, op.rdA, op.offA, d->pconst);
         ctx->launches++;
-        if ((rc = dd_round(ctx, d, peers))) return rc;
+        pc = d->pconst;
     }
-    if (d->nhl > 0) {
-        k_row_hat_gather<<<grdh, blk2, 0, ctx->stream>>>(op, R, peers);
-        ctx->launches++;
-    }
-    if (d->world > 1) {
-        k_row_hat_dn1<<<grd1, 128, 0, ctx->stream>>>(op, R, peers);
-        ctx->launches++;
-        if ((rc = dd_round(ctx, d, peers))) return rc;
-    }
-    k_row_hat_b<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, d->gdn);
+    k_row_bwd<<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sync(0, epA, 0));
     ctx->launches++;
-    if ((rc = dd_round(ctx, d, peers))) return rc;
-    k_row_hat_c<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, d->pconst, d->gdn, d->hx);
-    k_row_fwd_mul<<<grd2, blk2, 0, ctx->stream>>>(op, R, (T && gamma != 0.0) ? F : nullptr, d->hx, d->xb, peers);
-    ctx->launches += 2;
-    if (T && d->nhl > 0) {
-        if ((rc = dd_round(ctx, d, peers))) return rc;
-        k_row_hat_mul<<<grdh, blk2, 0, ctx->stream>>>(op, R, gamma != 0.0 ? F : nullptr, d->hx, d->xb, peers);
+    if (d->hats_merged) {
+        k_row_hats<<<(unsigned)((d->nrows + 31) / 32), dim3(32, 4), d->hats_smem, ctx->stream>>>(op, R, peers, pc, d->hx, sync(epA, 0, 0), epB, epC);
         ctx->launches++;
-    } else if (T) {
-        if ((rc = dd_round(ctx, d, peers))) return rc;
+    } else {
+        k_row_hat_gather<<<grdh, blk2, 0, ctx->stream>>>(op, R, peers, sync(epA, 0, 0));
+        ctx->launches++;
+        if (multi) {
+            k_row_hat_dn1<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, sync(0, epB, 1));
+            ctx->launches++;
+        }
+        k_row_hat_b<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, pc, d->gdn, sync(epB, epC, 2));
+        k_row_hat_c<<<grd1, 128, 0, ctx->stream>>>(op, R, peers, pc, d->gdn, d->hx, sync(epC, 0, 0));
+        ctx->launches += 2;
+    }
+    {
+        static int variant = -1;
+        if (variant < 0) {
+            variant = 0;
+            if (const char *e = getenv("POP_DD_FWD_VARIANT")) variant = atoi(e);
+        }
+        const double *Fp = (T && gamma != 0.0) ? F : nullptr;
+        const DDSync sy = sync(0, epD, 3);
+        // measured (profiles/r1_dd_standin.txt): blocks of 4 degrees at 64 registers (4 CTAs/SM) edge out blocks of 8 at 128
+        switch (variant) {
+            case 1: k_row_fwd_mul<8, 2><<<grd2, blk2, 0, ctx->stream>>>(op, R, Fp, d->hx, d->xb, peers, sy); break;
+            case 2: k_row_fwd_mul<8, 4><<<grd2, blk2, 0, ctx->stream>>>(op, R, Fp, d->hx, d->xb, peers, sy); break;
+            default: k_row_fwd_mul<4, 4><<<grd2, blk2, 0, ctx->stream>>>(op, R, Fp, d->hx, d->xb, peers, sy); break;
+        }
+    }
+    ctx->launches++;
+    if (T) {
+        k_row_hat_mul<<<grdh, blk2, 0, ctx->stream>>>(op, R, gamma != 0.0 ? F : nullptr, d->hx, d->xb, peers, sync(epD, 0, 0));
+        ctx->launches++;
     }
     POP_CUDA(cudaGetLastError());
     return POP_OK;
@@ -596,7 +820,7 @@ extern "C" int pop_dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead
     POP_REQUIRE(d->opened, POP_ERR_ARG, "pop_dd_row_half_step: peers not opened");
     POP_REQUIRE(ldr == d->ld, POP_ERR_DIM, "pop_dd_row_half_step: the panel must use the leading dimension pop_dd_ld()");
     POP_REQUIRE(!(T && gamma != 0.0) || (dF && ldf >= d->nrows), POP_ERR_DIM, "pop_dd_row_half_step: F panel missing or too small");
-    return dd_row_half_step(ctx, d, U, T, gamma, dF, ldf, dR);
+    return dd_row_half_step(ctx, d, U, T, gamma, dF, ldf, dR, nullptr);
 }
 
 __global__ void k_dd_scale_copy(const double *__restrict__ src, int64_t lds, double *__restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, double s) {
@@ -652,8 +876,32 @@ extern "C" int pop_adi_poisson_dd(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *
         k_dd_scale_copy<<<grid, 256, 0, ctx->stream>>>(dF_local, ldf, R, ld, n, nloc, -1.0 / p[0]);
         ctx->launches++;
     }
+    // segment multipliers of all row factors in one launch
+    double *pcall = nullptr;
+    const double **dptrs = nullptr;
+    {
+        std::vector<const double *> hp(2 * J);
+        for (int j = 0; j < J; ++j) {
+            hp[2 * j] = fac[2 * j]->p.rdA;
+            hp[2 * j + 1] = fac[2 * j]->p.Au;
+        }
+        cudaError_t e = cudaMallocAsync((void **)&pcall, (size_t)J * 2 * POP_DD_MAXWORLD * 8, ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&dptrs, (size_t)2 * J * sizeof(double *), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dptrs, hp.data(), (size_t)2 * J * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // hp goes out of scope
+        if (e != cudaSuccess) {
+            pop_set_error("pop_adi_poisson_dd: %s", cudaGetErrorString(e));
+            cleanup();
+            return POP_ERR_CUDA;
+        }
+        DDBounds bd;
+        for (int r = 0; r <= d->world; ++r) bd.kb[r] = d->kb[r];
+        bd.world = d->world; bd.nh = d->nh;
+        k_dd_pconst<<<J, 32, 0, ctx->stream>>>(bd, dptrs, nullptr, nullptr, pcall);
+        ctx->launches++;
+    }
     for (int j = 0; j < J && rc == POP_OK; ++j) {
-        if ((rc = dd_row_half_step(ctx, d, fac[2 * j], top[2 * j + 1], -1.0 / q[j], dF_local, ldf, R))) break;
+        if ((rc = dd_row_half_step(ctx, d, fac[2 * j], top[2 * j + 1], -1.0 / q[j], dF_local, ldf, R, pcall + (size_t)j * 2 * POP_DD_MAXWORLD))) break;
         if (j + 1 < J) rc = pop_solve_mul_axpy(ctx, fac[2 * j + 1], top[2 * j + 2], -1.0 / p[j + 1], dF_local, ldf, R, ld, nloc);
         else rc = pop_solve(ctx, fac[2 * j + 1], POP_LEFT, R, ld, nloc, POP_SOLVE_AUTO);
     }
@@ -661,6 +909,8 @@ extern "C" int pop_adi_poisson_dd(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *
         cudaError_t e = cudaMemcpy2DAsync(dX_local, ldx * 8, R, ld * 8, n * 8, nloc, cudaMemcpyDeviceToDevice, ctx->stream);
         if (e != cudaSuccess) { pop_set_error("pop_adi_poisson_dd: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
     }
+    cudaFreeAsync(pcall, ctx->stream);
+    cudaFreeAsync((void *)dptrs, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     cleanup();
     return rc;

@@ -259,7 +259,7 @@ def dd_columns(m, nh, q, rank, world):
 class ElementDecomposition:
     """X (n x n) distributed by mesh elements of the column direction (csrc/pop_row.cu)."""
 
-    def __init__(self, M, group=None):
+    def __init__(self, M, group=None, _standin=None):
         import torch.distributed as dist
         Mb = _base(M)
         self.ctx = Mb.ctx
@@ -267,11 +267,13 @@ class ElementDecomposition:
         self.m, self.nh, self.q = int(dsc.m), int(dsc.nh), int(dsc.q)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if _standin is not None:   # profiling aid: (rank, world) of the shard this single GPU stands in for (POP_DD_FAKE_PEERS=1)
+            self.rank, self.world = _standin
         lib = L.lib()
         h = C.c_void_p()
         L.check(lib.pop_dd_create(self.ctx.handle, self.rank, self.world, self.m, self.nh, self.q, C.byref(h)), "pop_dd_create")
         self._h = h
-        if self.world > 1:
+        if self.world > 1 and _standin is None:
             nb = lib.pop_dist_handle_bytes()
             mine = C.create_string_buffer(nb)
             L.check(lib.pop_dd_get_handle(h, mine), "pop_dd_get_handle")
