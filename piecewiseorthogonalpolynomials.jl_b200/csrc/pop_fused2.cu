@@ -133,7 +133,8 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         p.nch = jmax / F2_G;
         p.hcap = ev2i(mloc + 1) + 8;
         const size_t slot_bytes = (size_t)p.slot_stride * 8;
-        const size_t tail = 512;
+        // cs > 1: the set-up of the segment-map weights uses 5*hcap doubles of scratch at the start of the ring
+        const size_t tail = 512 + (cs > 1 ? (size_t)std::max(0, 5 * p.hcap - p.nch * p.slot_stride) * 8 : 0);
         int o = 0;
         p.o_tab = o; o += 2 * (jmax + 2);
         p.o_tab1 = o; o += ev2i(jmax + 2);
@@ -144,7 +145,8 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         p.o_ct = o; o += 3 * pl.npar * ncE;
         p.o_xb = o; o += T ? F2_NBMAX * ncE : 0;
         p.o_inb = o; o += F2_INB_SIZE;
-        p.o_wagg = o; o += 128;
+        p.o_wagg = o; o += F2_WAGG;
+        p.o_hw = o; o += cs > 1 ? 2 * p.hcap : 0;
         o = (o + 15) & ~15;
         p.o_ring = o;
         const size_t fixed = F2_BAR_BYTES + (size_t)o * 8;
@@ -266,7 +268,29 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
             cudaGetLastError();
         }
     }
+#ifdef F2_PROF
+    static unsigned long long *prof = nullptr;
+    if (!prof) cudaMalloc((void **)&prof, 32 * 8);
+    cudaMemsetAsync(prof, 0, 32 * 8, ctx->stream);
+    p.prof = prof;
+#endif
     POP_CUDA(cudaLaunchKernelEx(&cfg, pl.kern, p));
     ctx->launches++;
+#ifdef F2_PROF
+    if (getenv("POP_F2_PROF_PRINT")) {
+        static const char *names[15] = {"load wait + column->regs", "backward sweep + couplings", "barrier A", "refill issue", "wait edges + hat load",
+                                        "hat rhs", "barrier B", "hat scans: up", "barrier C", "correction + forward", "stores / product",
+                                        "hat scans: dots + send", "hat scans: down pass 1", "hat scans: wait peers", "hat scans: fold + down pass 2"};
+        unsigned long long h[32];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+        unsigned long long tot[2] = {0, 0};
+        for (int o = 0; o < 2; ++o)
+            for (int i = 0; i < 15; ++i) tot[o] += h[o * 16 + i];
+        fprintf(stderr, "[pop_f2 prof] cs=%d threads=%d grid=%u: cycles of block 0 (warp 0 | last warp), share of the column loop\n", p.cs, pl.threads, cfg.gridDim.x);
+        for (int i = 0; i < 15; ++i)
+            fprintf(stderr, "  %-30s %10llu %5.1f%% | %10llu %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (double)tot[0], h[16 + i], 100.0 * h[16 + i] / (double)tot[1]);
+    }
+#endif
     return POP_OK;
 }

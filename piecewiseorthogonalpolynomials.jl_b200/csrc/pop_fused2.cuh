@@ -12,6 +12,9 @@
 #define F2_CLASS 8        // a row class covers q in (ROWS*NPAR - F2_CLASS*NPAR, ROWS*NPAR]
 
 struct F2Params {
+#ifdef F2_PROF
+    unsigned long long *prof;   // [2 observers][16 phases] accumulated SM cycles (debug build only)
+#endif
     // factor U (upper data; D block shared by all elements)
     const double *rdD, *W1, *W2;   // [q] reciprocal pivots, first / second super-diagonal (may be null)
     const double *Sb;              // [nb][3][m] hat <-> bubble coupling
@@ -31,7 +34,7 @@ struct F2Params {
     // plan
     int stagger_ns;        // start-up offset between clusters (de-phases the clusters' memory bursts)
     int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap, nf;   // nf: slots of the F ring (fused product)
-    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_ring, o_fring;   // offsets in doubles
+    int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_hw, o_ring, o_fring;   // offsets in doubles
 };
 
 typedef void (*f2_kernel_t)(const F2Params);
@@ -49,10 +52,11 @@ __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : 
 
 // layout of the small cluster mailboxes (doubles, relative to o_inb)
 #define F2_INB_A 0     // [2 buffers][2 sides][2 parities]  boundary couplings of the neighbours' edge elements
-#define F2_INB_B 8     // [2 buffers][8 ranks]              segment maps of the downward hat sweep
-#define F2_INB_C 24    // [2 buffers][8 ranks]              segment maps of the upward hat sweep
-#define F2_INB_P 40    // [2 directions][8 ranks]           multipliers of the segment maps (constants of the factor)
-#define F2_INB_SIZE 56
+#define F2_INB_B 8     // [2 buffers][8 ranks]              segment maps of the downward hat sweep (zero incoming)
+#define F2_INB_C 24    // [2 buffers][8 ranks]              segment maps of the upward hat sweep (zero incoming, both directions)
+#define F2_INB_P 40    // [3][8 ranks]                      constants of the factor: multipliers down / up, response of the up map to the value entering the down sweep
+#define F2_INB_SIZE 64
+#define F2_WAGG 192    // scratch of the scan warps: [0,64) down, [64,128) up, [128,192) reductions
 
 #ifdef __CUDACC__
 // The hats are DISTRIBUTED over the cluster: CTA r owns hats [hA,hB) (hA = first element of the CTA).
@@ -65,11 +69,13 @@ __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : 
 // hoffl[u] couples local hats u-1 and u (hoffl[0]: the left neighbour's last hat).
 // Returns the value that entered this CTA's segment.
 #define F2_SCAN_WARPS 4   // warps that run the hat scans (the others wait at the block barrier)
+// Pass 1 + composition over the scan warps: thread-local map (t, Pm), then (at, aP) = composite of the scan warps
+// from this lane's warp on (lanes < nsw hold warp `lane`'s suffix / prefix composite).
 template <bool BW>
-__device__ __forceinline__ double f2_scan_dir(double *Hs, const double *hrd, const double *hoffl, const int lo, const int hi, const int tid,
-                                              const int lane, const int warp, const int nsw, double *wagg, const int cs, const int rank,
-                                              uint64_t *xbar, const uint32_t xph, double *inb, const double *Pc, double &hlast) {
-    double t = 0.0, Pm = 1.0;
+__device__ __forceinline__ void f2_scan_local(const double *Hs, const double *hrd, const double *hoffl, const int lo, const int hi, const int lane,
+                                              const int warp, const int nsw, double *wagg, double &t, double &Pm, double &at, double &aP) {
+    t = 0.0;
+    Pm = 1.0;
     for (int ii = lo; ii < hi; ++ii) {
         const int u = BW ? (hi - 1 - (ii - lo)) : ii;
         const double off = BW ? hoffl[u + 1] : hoffl[u];
@@ -88,7 +94,8 @@ __device__ __forceinline__ double f2_scan_dir(double *Hs, const double *hrd, con
         }
     }
     // lane now holds the composite of lanes lane..31 (BW) / 0..lane (forward)
-    double at = t, aP = Pm;
+    at = t;
+    aP = Pm;
     if (nsw > 1) {
         if (lane == (BW ? 0 : 31)) {
             wagg[warp] = t;
@@ -108,28 +115,14 @@ __device__ __forceinline__ double f2_scan_dir(double *Hs, const double *hrd, con
                 aP = aP * P2;
             }
         }
-    } else {
-        // one scan warp: its own composite sits in lane 0 (BW) / lane 31 (forward)
-        at = __shfl_sync(POP_FULL_MASK, t, BW ? 0 : 31);
-        aP = 1.0;
     }
-    // cluster level: my segment's map goes to the ranks below (BW) / above (forward) me
-    double Gc = 0.0;
-    if (cs > 1) {
-        const int nfrom = BW ? cs - 1 - rank : rank;      // peers whose maps I need
-        if (tid == (BW ? 0 : (nsw > 1 ? nsw - 1 : 0))) {  // this lane holds the composite of all scan warps
-            for (int r = BW ? 0 : rank + 1; r < (BW ? rank : cs); ++r) st_async_f64(mapa_u32(inb + rank, r), at, mapa_u32(xbar, r));
-        }
-        if (nfrom > 0) {
-            if (tid == 0) mbar_expect_tx(xbar, (uint32_t)nfrom * 8u);
-            mbar_wait(xbar, xph);
-            if (BW) {
-                for (int r = cs - 1; r > rank; --r) Gc = fma(Pc[r], Gc, inb[r]);
-            } else {
-                for (int r = 0; r < rank; ++r) Gc = fma(Pc[r], Gc, inb[r]);
-            }
-        }
-    }
+}
+
+// Pass 2: the reference recurrence itself, started from the exact value Gc that enters this CTA's segment.
+template <bool BW>
+__device__ __forceinline__ void f2_scan_finish(double *Hs, const double *hrd, const double *hoffl, const int lo, const int hi, const int lane, const int warp,
+                                               const int nsw, const double t, const double Pm, const double at, const double aP, const double Gc,
+                                               double &hlast) {
     // value entering this warp: composite of the scan warps after (BW) / before (forward) it applied to Gc
     double Gin = Gc;
     if (nsw > 1) {
@@ -147,7 +140,35 @@ __device__ __forceinline__ double f2_scan_dir(double *Hs, const double *hrd, con
         Hs[u] = hin;
     }
     hlast = hin;   // the last hat this thread wrote
-    return Gc;
+}
+
+// Set-up helper: in-place inclusive scan of the affine maps x -> A[u] x + B[u] in shared memory (Hillis-Steele,
+// all threads of the block): afterwards (A[u], B[u]) = map_u o ... o map_0, or map_u o ... o map_{n-1} if REV.
+template <bool REV>
+__device__ __forceinline__ void f2_setup_scan(double *A, double *B, double *tA, double *tB, const int n, const int tid, const int nthr) {
+    double *sa = A, *sb = B, *da = tA, *db = tB;
+    for (int d = 1; d < n; d <<= 1) {
+        for (int u = tid; u < n; u += nthr) {
+            const int v = REV ? u + d : u - d;
+            double a = sa[u], b = sb[u];
+            if (v >= 0 && v < n) {
+                b = fma(a, sb[v], b);
+                a = a * sa[v];
+            }
+            da[u] = a;
+            db[u] = b;
+        }
+        __syncthreads();
+        double *x = sa; sa = da; da = x;
+        x = sb; sb = db; db = x;
+    }
+    if (sa != A) {
+        for (int u = tid; u < n; u += nthr) {
+            A[u] = sa[u];
+            B[u] = sb[u];
+        }
+    }
+    __syncthreads();
 }
 
 // TMA loads of one chunk (rows j0 .. j0+nr-1 of column xcol) into its ring slot; one warp.
@@ -219,6 +240,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     double *xb = sm + P.o_xb;                                   // x of the coupled bubbles (fused product)
     double *inb = sm + P.o_inb;
     double *wagg = sm + P.o_wagg;
+    double *hwd = sm + P.o_hw, *hwu = hwd + P.hcap;   // cs > 1: weights of the segment maps (see the set-up below)
     double *ring = sm + P.o_ring;
     double *fring = sm + P.o_fring;
 
@@ -294,6 +316,53 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             wagg[32 + warp] = pu;
         }
         __syncthreads();
+        // With zero incoming values both segment maps are LINEAR FUNCTIONALS of the hat right-hand sides H of
+        // my segment (a_u = -off(u,u+1) rd_u, b_u = -off(u-1,u) rd_u):
+        //   down:  y_0     = sum_k hwd[k] H[k] + pd * Gdn,   hwd[k] = rd_k prod_{u<k} a_u
+        //   up:    h_{n-1} = sum_k wup[k] y_k  + pu * Gup,   wup[k] = rd_k prod_{u>k} b_u
+        //          with y_k = y0_k + (prod_{u>=k} a_u) Gdn:   = sum_j hwu[j] H[j] + kappa * Gdn + pu * Gup,
+        //          hwu[j] = rd_j c_j,  c_j = wup[j] + a_{j-1} c_{j-1},  kappa = sum_k wup[k] prod_{u>=k} a_u.
+        // So ONE exchange of two dot products per column replaces the two dependent map exchanges.
+        {
+            const int n = nhl, hc = P.hcap;
+            double *s0 = ring, *s1 = s0 + hc, *s2 = s1 + hc, *s3 = s2 + hc, *s4 = s3 + hc;
+            for (int u = tid; u < n; u += nthr) {
+                s0[u] = -hoffl[u + 1] * hrd[u];
+                s1[u] = 0.0;
+            }
+            __syncthreads();
+            f2_setup_scan<false>(s0, s1, s2, s3, n, tid, nthr);   // s0[k] = prod_{u<=k} a_u
+            for (int u = tid; u < n; u += nthr) hwd[u] = hrd[u] * (u > 0 ? s0[u - 1] : 1.0);
+            __syncthreads();
+            for (int u = tid; u < n; u += nthr) {
+                s0[u] = -hoffl[u] * hrd[u];
+                s1[u] = 0.0;
+            }
+            __syncthreads();
+            f2_setup_scan<true>(s0, s1, s2, s3, n, tid, nthr);    // s0[k] = prod_{u>=k} b_u
+            for (int u = tid; u < n; u += nthr) s4[u] = hrd[u] * (u + 1 < n ? s0[u + 1] : 1.0);   // wup
+            __syncthreads();
+            for (int u = tid; u < n; u += nthr) {
+                s0[u] = -hoffl[u + 1] * hrd[u];
+                s1[u] = 0.0;
+            }
+            __syncthreads();
+            f2_setup_scan<true>(s0, s1, s2, s3, n, tid, nthr);    // s0[k] = prod_{u>=k} a_u
+            double kp = 0.0;
+            for (int u = tid; u < n; u += nthr) kp = fma(s4[u], s0[u], kp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) kp += __shfl_xor_sync(POP_FULL_MASK, kp, o);
+            if (lane == 0) wagg[128 + warp] = kp;
+            __syncthreads();
+            for (int u = tid; u < n; u += nthr) {
+                s0[u] = u > 0 ? -hoffl[u] * hrd[u - 1] : 0.0;
+                s1[u] = s4[u];
+            }
+            __syncthreads();
+            f2_setup_scan<false>(s0, s1, s2, s3, n, tid, nthr);   // s1[j] = c_j
+            for (int u = tid; u < n; u += nthr) hwu[u] = hrd[u] * s1[u];
+            fence_proxy_async();   // the scratch lives in the ring: order these writes before the first TMA refill
+        }
         if (tid == 0) {
             pd = 1.0;
             pu = 1.0;
@@ -301,9 +370,12 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 pd *= wagg[w];
                 pu *= wagg[32 + w];
             }
+            double kp = 0.0;
+            for (int w = 0; w < nw; ++w) kp += wagg[128 + w];
             for (int r = 0; r < cs; ++r) {
                 st_cluster_f64(mapa_u32(inb + F2_INB_P + rank, r), pd);
                 st_cluster_f64(mapa_u32(inb + F2_INB_P + 8 + rank, r), pu);
+                st_cluster_f64(mapa_u32(inb + F2_INB_P + 16 + rank, r), kp);
             }
         }
         cluster_arrive();
@@ -352,6 +424,18 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     const double *sbk = P.Sb + k;
     const int expA = cs > 1 ? NPAR * 8 * ((rank > 0) + (rank < cs - 1)) : 0;
 
+#ifdef F2_PROF
+    const int pobs = (blockIdx.x == 0 && lane == 0) ? (warp == 0 ? 0 : (warp == nw - 1 ? 1 : -1)) : -1;
+    long long pt = clock64();
+#define F2_TICK(ph)                                                         \
+    if (pobs >= 0) {                                                        \
+        const long long now = clock64();                                    \
+        atomicAdd(P.prof + pobs * 16 + (ph), (unsigned long long)(now - pt)); \
+        pt = now;                                                           \
+    }
+#else
+#define F2_TICK(ph)
+#endif
     for (int it = 0; it < ncols; ++it) {
         double *xcol = P.X + ((int64_t)c_first + (int64_t)it * ncl) * P.ldx;
         const int hb = (int)(it & 1);
@@ -376,6 +460,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 pr += rp;
             }
         }
+        F2_TICK(0)   // column -> registers (waits for the loads)
         // ---- backward sweep  z_j = (b_j - W1(j) z_{j+1} - W2(j) z_{j+2}) rd_j  (:439-441) --------
 #pragma unroll
         for (int i = ROWS - 1; i >= 0; --i) {
@@ -413,29 +498,14 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 }
             }
         }
+        F2_TICK(1)   // backward sweep + couplings
         fence_proxy_async();   // this thread's earlier writes to the hat buffer vs. the TMA refill below
         __syncthreads();
-        // every row of this column is in registers: refill the ring (and the other hat buffer)
-        if (tid == 0) {
-            if (it + 1 < ncols) {
-                mbar_expect_tx(hfull + (hb ^ 1), hbytes);
-                tma_load_1d(Hb + (size_t)(hb ^ 1) * P.hcap + 2, xcol + colstep + hA2, hbytes, hfull + (hb ^ 1));
-            }
-            if (expA) mbar_expect_tx(hxA + hb, (uint32_t)expA);
-        }
-        if (MUL && P.gamma != 0.0 && tid == 32 % nthr) {
-            // the part of this column's F that is not in the ring yet: pull it into L2 now
-            const double *fc = fbase + (int64_t)it * fstep;
-            for (int c = P.nf; c < NCH; ++c) {
-                const int64_t gs = ((int64_t)nh + (int64_t)c * G * m) & ~(int64_t)1;
-                const int nr = min(G, q - c * G);
-                if (nr > 0) l2_prefetch_bulk(fc + gs, (uint32_t)(((int64_t)nr * m + 2) & ~(int64_t)1) * 8u);
-            }
-        }
-        if (it + 1 < ncols)
-            for (int c = warp; c < NCH; c += nw) f2_issue_chunk(P, full, ring, lane, k0, ml, xcol + colstep, c, c);
+        F2_TICK(2)   // barrier A
+        if (expA && tid == 0) mbar_expect_tx(hxA + hb, (uint32_t)expA);
         if (expA) mbar_wait(hxA + hb, hph);
         mbar_wait(hfull + hb, hph);
+        F2_TICK(4)   // wait for the neighbours' edge couplings and the hat load
         // ---- right-hand sides of my hats: hat hA+u collects elements u-1 (t=2), u (t=1), u+1 (t=0) ----
         for (int u = tid; u < nhl; u += nthr) {
             double v = 0.0;
@@ -452,13 +522,89 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             }
             Hs[u] -= v;
         }
+        F2_TICK(5)   // hat right-hand sides
         __syncthreads();
+        F2_TICK(6)   // barrier B
+        // every row of this column is in registers: refill the ring (and the other hat buffer).  The LAST warps
+        // issue (warp nw-1 first): issuing a chunk of a cluster column (8 bulk copies from divergent lanes) stalls
+        // the warp for thousands of cycles, so the scan warps stay out of it when other warps exist.
+        {
+            const int iw = nw - 1 - warp;
+            const int nissue = nw > nsw ? nw - nsw : nw;
+            if (iw == 0 && lane == 0 && it + 1 < ncols) {
+                mbar_expect_tx(hfull + (hb ^ 1), hbytes);
+                tma_load_1d(Hb + (size_t)(hb ^ 1) * P.hcap + 2, xcol + colstep + hA2, hbytes, hfull + (hb ^ 1));
+            }
+            if (MUL && P.gamma != 0.0 && tid == 32 % nthr) {
+                // the part of this column's F that is not in the ring yet: pull it into L2 now
+                const double *fc = fbase + (int64_t)it * fstep;
+                for (int c = P.nf; c < NCH; ++c) {
+                    const int64_t gs = ((int64_t)nh + (int64_t)c * G * m) & ~(int64_t)1;
+                    const int nr = min(G, q - c * G);
+                    if (nr > 0) l2_prefetch_bulk(fc + gs, (uint32_t)(((int64_t)nr * m + 2) & ~(int64_t)1) * 8u);
+                }
+            }
+            if (it + 1 < ncols && iw < nissue)
+                for (int c = iw; c < NCH; c += nissue) f2_issue_chunk(P, full, ring, lane, k0, ml, xcol + colstep, c, c);
+        }
+        F2_TICK(3)   // refill issue
         if (warp < nsw) {
-            double hl;
-            const double Gdn = f2_scan_dir<true>(Hs, hrd, hoffl, lo, hi, tid, lane, warp, nsw, wagg, cs, rank, hxB + hb, hph,
-                                                 inb + F2_INB_B + hb * 8, inb + F2_INB_P, hl);
-            const double Gup = f2_scan_dir<false>(Hs, hrd, hoffl, lo, hi, tid, lane, warp, nsw, wagg + 64, cs, rank, hxC + hb, hph,
-                                                  inb + F2_INB_C + hb * 8, inb + F2_INB_P + 8, hl);
+            double hl, t, Pm, at, aP, Gdn = 0.0, Gup = 0.0, Td = 0.0;
+            double *ib = inb + F2_INB_B + hb * 8, *ic = inb + F2_INB_C + hb * 8;
+            if (cs > 1) {
+                // my segment's two zero-incoming maps as dot products with the hat right-hand sides -> every peer
+                double sd = 0.0, su = 0.0;
+                for (int u = lo; u < hi; ++u) {
+                    const double h = Hs[u];
+                    sd = fma(hwd[u], h, sd);
+                    su = fma(hwu[u], h, su);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sd += __shfl_xor_sync(POP_FULL_MASK, sd, o);
+                    su += __shfl_xor_sync(POP_FULL_MASK, su, o);
+                }
+                if (lane == 0) {
+                    wagg[128 + warp] = sd;
+                    wagg[160 + warp] = su;
+                }
+                named_bar_sync(2, nsw * 32);
+                double Tu = 0.0;
+                for (int w = 0; w < nsw; ++w) {
+                    Td += wagg[128 + w];
+                    Tu += wagg[160 + w];
+                }
+                if (tid == 0) {
+                    for (int r = 0; r < cs; ++r)
+                        if (r != rank) {
+                            st_async_f64(mapa_u32(ib + rank, r), Td, mapa_u32(hxB + hb, r));
+                            st_async_f64(mapa_u32(ic + rank, r), Tu, mapa_u32(hxB + hb, r));
+                        }
+                    mbar_expect_tx(hxB + hb, (uint32_t)(cs - 1) * 16u);
+                }
+            }
+            F2_TICK(11)   // dot products + send
+            f2_scan_local<true>(Hs, hrd, hoffl, lo, hi, lane, warp, nsw, wagg, t, Pm, at, aP);
+            F2_TICK(12)   // down: pass 1 + composition
+            if (cs > 1) {
+                mbar_wait(hxB + hb, hph);
+                F2_TICK(13)   // wait for the peers' maps
+                // value entering every rank's downward sweep (top down), and with it the exact upward maps below me
+                const double *Pdn = inb + F2_INB_P, *Pup = Pdn + 8, *kap = Pdn + 16;
+                double g = 0.0, mult = 1.0;
+                for (int r = cs - 1; r >= 0; --r) {
+                    if (r == rank) Gdn = g;
+                    if (r < rank) {
+                        Gup = fma(mult, fma(kap[r], g, ic[r]), Gup);
+                        mult *= Pup[r];
+                    }
+                    g = fma(Pdn[r], g, r == rank ? Td : ib[r]);
+                }
+            }
+            f2_scan_finish<true>(Hs, hrd, hoffl, lo, hi, lane, warp, nsw, t, Pm, at, aP, Gdn, hl);
+            F2_TICK(14)   // fold + down pass 2
+            f2_scan_local<false>(Hs, hrd, hoffl, lo, hi, lane, warp, nsw, wagg + 64, t, Pm, at, aP);
+            f2_scan_finish<false>(Hs, hrd, hoffl, lo, hi, lane, warp, nsw, t, Pm, at, aP, Gup, hl);
             // the neighbours' hats next to my segment: hat hA-1 entered the upward sweep; hat hB follows
             // from the value that entered the downward sweep and my last hat (both recurrences, one step)
             if (tid == 0) Hs[-1] = rank > 0 ? Gup : 0.0;
@@ -467,7 +613,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 Hs[nhl + 1] = 0.0;
             }
         }
+        F2_TICK(7)   // hat scans (scan warps only)
         __syncthreads();
+        F2_TICK(8)   // barrier C
         // ---- correct the coupled bubbles (:475-477): hats k-1, k, k+1 of element k ----------------
         const double h0 = Hs[el - 1], h1 = Hs[el], h2 = Hs[el + 1];
 #pragma unroll
@@ -495,6 +643,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             }
             z[i] = v * cf.x;
         }
+        F2_TICK(9)   // correction + forward sweep
         if (!MUL) {
             for (int u = tid; u < nhl; u += nthr) xcol[hA + u] = Hs[u];
             if (active) {
@@ -601,6 +750,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 xcol[i] = useF ? fma(P.gamma, fcol[i], acc) : acc;
             }
         }
+        F2_TICK(10)   // stores (or product + stores)
     }
     if (cs > 1) {
         cluster_arrive();
