@@ -143,8 +143,23 @@ for (UPLO, UNIT, Tri, uplo, unit) in (('U', 'N', UpperTriangular, POP_UPPER, 0),
     end
 end
 
-# unpack_upper! writes the downloaded upper data back into the banded fields (omitted: 10 lines of
-# index loops inverse to `pack`).
-function unpack_upper! end
+# unpack_upper!: inverse of `pack` for the upper data of a factor (diagonal and super-diagonal of A, the
+# hat-bubble couplings B, the upper bands of every D_k); the lower parts are not touched (UpperTriangular view).
+function unpack_upper!(A::BBBArrowheadMatrix{Float64}, Ad, Au, Bp, Dp)
+    nh, m = size(A.A, 1), length(A.D)
+    q = size(A.D[1], 1); lD, uD = bandwidths(A.D[1])
+    for i in 1:nh
+        A.A[i, i] = Ad[i]
+        i < nh && (A.A[i, i+1] = Au[i])
+    end
+    for (b, Bb) in enumerate(A.B), k in 1:m, t in 0:2              # Bp[k, t+1, b] = entry (hat of slot t, bubble (b,k))
+        i = k + t - 1 - (nh == m + 1 ? 0 : 1) + 1
+        1 <= i <= nh && (Bb[i, k] = Bp[k, t+1, b])
+    end
+    for k in 1:m, j in 1:q, d in 0:uD
+        j + d <= q && (A.D[k][j, j+d] = Dp[k, j, lD+d+1])
+    end
+    A
+end
 
 end # module
