@@ -52,8 +52,7 @@ __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : 
 
 // layout of the small cluster mailboxes (doubles, relative to o_inb)
 #define F2_INB_A 0     // [2 buffers][2 sides][2 parities]  boundary couplings of the neighbours' edge elements
-#define F2_INB_B 8     // [2 buffers][8 ranks]              segment maps of the downward hat sweep (zero incoming)
-#define F2_INB_C 24    // [2 buffers][8 ranks]              segment maps of the upward hat sweep (zero incoming, both directions)
+#define F2_INB_B 8     // [2 buffers][8 ranks][2]           zero-incoming segment maps of the downward / upward hat sweep (16 B pairs)
 #define F2_INB_P 40    // [3][8 ranks]                      constants of the factor: multipliers down / up, response of the up map to the value entering the down sweep
 #define F2_INB_SIZE 64
 #define F2_WAGG 192    // scratch of the scan warps: [0,64) down, [64,128) up, [128,192) reductions
@@ -550,7 +549,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         F2_TICK(3)   // refill issue
         if (warp < nsw) {
             double hl, t, Pm, at, aP, Gdn = 0.0, Gup = 0.0, Td = 0.0;
-            double *ib = inb + F2_INB_B + hb * 8, *ic = inb + F2_INB_C + hb * 8;
+            double *ibc = inb + F2_INB_B + hb * 16;   // [rank][down, up]
             if (cs > 1) {
                 // my segment's two zero-incoming maps as dot products with the hat right-hand sides -> every peer
                 double sd = 0.0, su = 0.0;
@@ -574,14 +573,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                     Td += wagg[128 + w];
                     Tu += wagg[160 + w];
                 }
-                if (tid == 0) {
-                    for (int r = 0; r < cs; ++r)
-                        if (r != rank) {
-                            st_async_f64(mapa_u32(ib + rank, r), Td, mapa_u32(hxB + hb, r));
-                            st_async_f64(mapa_u32(ic + rank, r), Tu, mapa_u32(hxB + hb, r));
-                        }
-                    mbar_expect_tx(hxB + hb, (uint32_t)(cs - 1) * 16u);
-                }
+                // lane r of warp 0 sends the pair to rank r: one instruction for all peers
+                if (warp == 0 && lane < cs && lane != rank) st_async_v2f64(mapa_u32(ibc + 2 * rank, lane), Td, Tu, mapa_u32(hxB + hb, lane));
+                if (tid == 0) mbar_expect_tx(hxB + hb, (uint32_t)(cs - 1) * 16u);
             }
             F2_TICK(11)   // dot products + send
             f2_scan_local<true>(Hs, hrd, hoffl, lo, hi, lane, warp, nsw, wagg, t, Pm, at, aP);
@@ -595,10 +589,10 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 for (int r = cs - 1; r >= 0; --r) {
                     if (r == rank) Gdn = g;
                     if (r < rank) {
-                        Gup = fma(mult, fma(kap[r], g, ic[r]), Gup);
+                        Gup = fma(mult, fma(kap[r], g, ibc[2 * r + 1]), Gup);
                         mult *= Pup[r];
                     }
-                    g = fma(Pdn[r], g, r == rank ? Td : ib[r]);
+                    g = fma(Pdn[r], g, r == rank ? Td : ibc[2 * r]);
                 }
             }
             f2_scan_finish<true>(Hs, hrd, hoffl, lo, hi, lane, warp, nsw, t, Pm, at, aP, Gdn, hl);

@@ -74,6 +74,12 @@ __device__ __forceinline__ void st_async_f64(uint32_t dst_cluster_addr, double v
                  "l"(__double_as_longlong(v)), "r"(bar_cluster_addr)
                  : "memory");
 }
+// 16-byte variant (dst 16 B aligned): two doubles in one instruction, completing 16 bytes on the PEER's mbarrier
+__device__ __forceinline__ void st_async_v2f64(uint32_t dst_cluster_addr, double a, double b, uint32_t bar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(dst_cluster_addr),
+                 "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(bar_cluster_addr)
+                 : "memory");
+}
 // plain store into a peer CTA's shared memory (made visible by the cluster barrier)
 __device__ __forceinline__ void st_cluster_f64(uint32_t dst_cluster_addr, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst_cluster_addr), "d"(v) : "memory");
