@@ -84,6 +84,11 @@ __device__ __forceinline__ void st_async_v2f64(uint32_t dst_cluster_addr, double
 __device__ __forceinline__ void st_cluster_f64(uint32_t dst_cluster_addr, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst_cluster_addr), "d"(v) : "memory");
 }
+// streaming store that does not allocate a line in L1 (keeps the small L1 for the read-only coupling tables)
+__device__ __forceinline__ void stg_na_f64(double *p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
