@@ -67,6 +67,9 @@ __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : 
 // st.async + mbarrier; pass 2 is the reference recurrence itself with the exact incoming value.
 // hoffl[u] couples local hats u-1 and u (hoffl[0]: the left neighbour's last hat).
 // Returns the value that entered this CTA's segment.
+#ifndef F2_EARLY_COEF
+#define F2_EARLY_COEF 0   // 1: load the correction coefficients before the hat solve (measured: the 24 extra live registers spill, -10 %)
+#endif
 #ifndef F2_STORE_NA
 #define F2_STORE_NA 0   // 1: result stores bypass L1 allocation (measured: no gain for cluster columns, -4 % for single-CTA columns)
 #endif
@@ -450,7 +453,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         double *Hs = Hb + (size_t)hb * P.hcap + 2 + (hA & 1);   // Hs[u] = hat hA + u; Hs[-1], Hs[nhl] hold the neighbours' hats
         double *inbA = inb + F2_INB_A + hb * 4;
 
-        // ---- column -> registers (ring order = backward-sweep order) --------------------------
+        // ---- column -> registers, chunk by chunk in backward-sweep order, each chunk swept as soon as it is in:
+        //      z_j = (b_j - W1(j) z_{j+1} - W2(j) z_{j+2}) rd_j  (:439-441); the dependent chain runs under the wait
+        //      for the next chunk --------------------------------------------------------------------------
         double z[ROWS];
 #pragma unroll
         for (int cc = NCH - 1; cc >= 0; --cc) {
@@ -466,21 +471,21 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 }
                 pr += rp;
             }
-        }
-        F2_TICK(0)   // column -> registers (waits for the loads)
-        // ---- backward sweep  z_j = (b_j - W1(j) z_{j+1} - W2(j) z_{j+2}) rd_j  (:439-441) --------
+            constexpr int BL = G / NPAR;   // chain entries of this thread per chunk
 #pragma unroll
-        for (int i = ROWS - 1; i >= 0; --i) {
-            const double2 cf = tabp[NPAR * i];
-            double v = z[i];
-            if (NPAR == 1) {
-                if (ND >= 1 && !SKIP1 && i + 1 < ROWS) v = fma(-tab1p[i], z[i + 1], v);
-                if (ND >= 2 && i + 2 < ROWS) v = fma(-cf.y, z[i + 2], v);
-            } else {
-                if (ND >= 2 && i + 1 < ROWS) v = fma(-cf.y, z[i + 1], v);
+            for (int i = (cc + 1) * BL - 1; i >= cc * BL; --i) {
+                const double2 cf = tabp[NPAR * i];
+                double v = z[i];
+                if (NPAR == 1) {
+                    if (ND >= 1 && !SKIP1 && i + 1 < ROWS) v = fma(-tab1p[i], z[i + 1], v);
+                    if (ND >= 2 && i + 2 < ROWS) v = fma(-cf.y, z[i + 2], v);
+                } else {
+                    if (ND >= 2 && i + 1 < ROWS) v = fma(-cf.y, z[i + 1], v);
+                }
+                z[i] = v * cf.x;
             }
-            z[i] = v * cf.x;
         }
+        F2_TICK(0)   // column -> registers + backward sweep
         // ---- coupling to the hats: per-element contributions (:449-451) -----------------------
         {
             double c0 = 0.0, c1 = 0.0, c2 = 0.0;
@@ -532,6 +537,18 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         F2_TICK(5)   // hat right-hand sides
         __syncthreads();
         F2_TICK(6)   // barrier B
+#if F2_EARLY_COEF
+        // coupling entries for the correction after the hat solve: issued now, their L2 latency passes under the scans
+        double sc[NBI][3];
+#pragma unroll
+        for (int i = 0; i < NBI; ++i) {
+            const int b = NPAR * i + par;
+            const double *sb = sbk + (size_t)(b < nb ? b : 0) * 3 * m;
+            sc[i][0] = __ldg(sb);
+            sc[i][1] = __ldg(sb + m);
+            sc[i][2] = __ldg(sb + 2 * m);
+        }
+#endif
         // every row of this column is in registers: refill the ring (and the other hat buffer).  The LAST warps
         // issue (warp nw-1 first): issuing a chunk of a cluster column (8 bulk copies from divergent lanes) stalls
         // the warp for thousands of cycles, so the scan warps stay out of it when other warps exist.
@@ -624,15 +641,25 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         for (int i = 0; i < NBI; ++i) {
             const int b = NPAR * i + par;
             if (i < ROWS && b < nb) {
-                const double *sb = sbk + (size_t)b * 3 * m;
                 double v = z[i];
+#if F2_EARLY_COEF
+                v = fma(-sc[i][0], h0, v);
+                v = fma(-sc[i][1], h1, v);
+                v = fma(-sc[i][2], h2, v);
+#else
+                const double *sb = sbk + (size_t)b * 3 * m;
                 v = fma(-__ldg(sb), h0, v);
                 v = fma(-__ldg(sb + m), h1, v);
                 v = fma(-__ldg(sb + 2 * m), h2, v);
+#endif
                 z[i] = v;
             }
         }
         // ---- forward sweep  x_j = (z_j - W1(j-1) x_{j-1} - W2(j-2) x_{j-2}) rd_j  (:480-482) --------
+        // plain solve: every x_j leaves for global memory as soon as it is final, so the stores drain under the
+        // latency of the dependent chain instead of in one burst behind it
+        double *xo = xcol + nh + k + (NPAR == 2 ? (int64_t)par * m : 0);
+        const int64_t xs = (int64_t)NPAR * m;
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
             const double2 cf = tabp[NPAR * i];
@@ -644,20 +671,15 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 if (ND >= 2 && i >= 1) v = fma(-tabp[NPAR * (i - 1)].y, z[i - 1], v);
             }
             z[i] = v * cf.x;
+            if (!MUL) {
+                const int jj = NPAR * i;                       // row j = jj + par
+                if (active && (jj + NPAR - 1 <= JSAFE || jj + par < q)) F2_STORE(xo, z[i]);
+                xo += xs;
+            }
         }
-        F2_TICK(9)   // correction + forward sweep
+        F2_TICK(9)   // correction + forward sweep (+ the bubble stores of the plain solve)
         if (!MUL) {
             for (int u = tid; u < nhl; u += nthr) xcol[hA + u] = Hs[u];
-            if (active) {
-                double *xo = xcol + nh + k + (NPAR == 2 ? (int64_t)par * m : 0);
-                const int64_t xs = (int64_t)NPAR * m;
-#pragma unroll
-                for (int i = 0; i < ROWS; ++i) {
-                    const int jj = NPAR * i;                       // row j = jj + par
-                    if (jj + NPAR - 1 <= JSAFE || jj + par < q) F2_STORE(xo, z[i]);
-                    xo += xs;
-                }
-            }
         } else {
             // ---- fused product  r = T x + gamma f,  T = Symmetric(upper data); cs == 1: all hats are mine ----
             // NPAR == 2: rows j = 2i + par; T never couples j and j+1 there, so a thread needs only its own parity.
