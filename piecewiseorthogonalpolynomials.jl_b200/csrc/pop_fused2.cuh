@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         mbar_wait(hfull + hb, hph);
         F2_TICK(4)   // wait for the neighbours' edge couplings and the hat load
         // ---- right-hand sides of my hats: hat hA+u collects elements u-1 (t=2), u (t=1), u+1 (t=0) ----
+        // cs > 1: the two zero-incoming segment maps are dot products of these right-hand sides with constant weights
+        // (see the set-up); every thread adds its hats, the warp sums meet the scan warps behind barrier B
+        double sd = 0.0, su = 0.0;
         for (int u = tid; u < nhl; u += nthr) {
             double v = 0.0;
 #pragma unroll
@@ -532,7 +535,23 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                     v += inbA[pp];
                 }
             }
-            Hs[u] -= v;
+            const double h = Hs[u] - v;
+            Hs[u] = h;
+            if (cs > 1) {
+                sd = fma(hwd[u], h, sd);
+                su = fma(hwu[u], h, su);
+            }
+        }
+        if (cs > 1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sd += __shfl_xor_sync(POP_FULL_MASK, sd, o);
+                su += __shfl_xor_sync(POP_FULL_MASK, su, o);
+            }
+            if (lane == 0) {
+                wagg[128 + warp] = sd;
+                wagg[160 + warp] = su;
+            }
         }
         F2_TICK(5)   // hat right-hand sides
         __syncthreads();
@@ -576,25 +595,9 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
             double hl, t, Pm, at, aP, Gdn = 0.0, Gup = 0.0, Td = 0.0;
             double *ibc = inb + F2_INB_B + hb * 16;   // [rank][down, up]
             if (cs > 1) {
-                // my segment's two zero-incoming maps as dot products with the hat right-hand sides -> every peer
-                double sd = 0.0, su = 0.0;
-                for (int u = lo; u < hi; ++u) {
-                    const double h = Hs[u];
-                    sd = fma(hwd[u], h, sd);
-                    su = fma(hwu[u], h, su);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sd += __shfl_xor_sync(POP_FULL_MASK, sd, o);
-                    su += __shfl_xor_sync(POP_FULL_MASK, su, o);
-                }
-                if (lane == 0) {
-                    wagg[128 + warp] = sd;
-                    wagg[160 + warp] = su;
-                }
-                named_bar_sync(2, nsw * 32);
+                // my segment's two zero-incoming maps -> every peer
                 double Tu = 0.0;
-                for (int w = 0; w < nsw; ++w) {
+                for (int w = 0; w < nw; ++w) {
                     Td += wagg[128 + w];
                     Tu += wagg[160 + w];
                 }
