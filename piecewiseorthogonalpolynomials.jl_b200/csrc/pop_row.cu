@@ -19,8 +19,8 @@
 #include <vector>
 
 #include "pop_internal.h"
+#include "pop_row.h"
 
-#define POP_DD_MAXWORLD 16
 #define POP_DD_MAXQ 128
 #define POP_DD_MAXHL 1032   // hats of one rank's segment kept in shared memory by the chain kernels
 
@@ -176,26 +176,6 @@ extern "C" int64_t pop_dd_column(const pop_dd *d, int64_t c) {
     const int64_t j = b / d->ml, kl = b % d->ml;
     return (int64_t)d->nh + j * d->m + d->k0 + kl;
 }
-
-// ------------------------------------------------------------------------------------
-// operator views handed to the row kernels
-// ------------------------------------------------------------------------------------
-struct RowOp {
-    // factor U of the system being solved (upper data, shared D block)
-    const double *rd, *w1, *w2;    // [q]
-    const double *S;               // [nb][3][m]
-    const double *rdA, *offA;      // [nh], [nh-1]
-    int nb;
-    // product operator T = Symmetric(upper data), shared D block (may be absent: nbT = -1)
-    const double *t0, *t1, *t2;    // [q]
-    const double *Ts;              // [nbT][3][m]
-    const double *TAd, *TAu;
-    int nbT;
-    double gamma;
-    int m, nh, q, k0, ml, hA, nhl, hB, rank, world;
-    int64_t nrows, ld, ldf;
-    int kb[POP_DD_MAXWORLD + 1];
-};
 
 // Flags: the epoch protocol of pop_dist.cu, folded into the kernels (no separate signal / wait launches).
 // A producing kernel ends with dd_signal_last: the last block to finish tells every rank "my data of epoch
@@ -702,6 +682,7 @@ static int dd_make_op(const pop_dd *d, const pop_arrowhead *U, const pop_arrowhe
         op->nbT = std::min(t.nB, t.q);
         POP_REQUIRE(op->nbT <= 4, POP_ERR_DIM, "row half step: at most 4 coupling blocks");
     }
+    op->has1 = ((u.uD >= 1 && !U->band1_zero) || (T && T->d.uD >= 1 && !T->band1_zero)) ? 1 : 0;
     op->gamma = gamma;
     op->m = d->m; op->nh = d->nh; op->q = d->q; op->k0 = d->k0; op->ml = d->ml; op->hA = d->hA; op->nhl = d->nhl;
     op->hB = d->hA + d->nhl;
@@ -742,6 +723,11 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
     RowOp op;
     int rc = dd_make_op(d, U, T, gamma, ldf, &op);
     if (rc) return rc;
+    if (d->world == 1) {
+        // one GPU: the row block stays on chip for the whole half step (pop_row1.cuh), one pass over HBM
+        rc = pop_row1_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R);
+        if (rc != POP_ROW1_UNSUPPORTED) return rc;
+    }
     DDPeers peers;
     dd_peers(d, &peers);
     const bool multi = d->world > 1;

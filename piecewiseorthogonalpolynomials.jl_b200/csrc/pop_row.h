@@ -1,0 +1,34 @@
+// Shared by pop_row.cu (element-decomposed row kernels) and pop_row1.cuh (one-pass row kernel).
+#pragma once
+#include "pop_internal.h"
+
+#define POP_DD_MAXWORLD 16
+
+// ------------------------------------------------------------------------------------
+// operator views handed to the row kernels
+// ------------------------------------------------------------------------------------
+struct RowOp {
+    // factor U of the system being solved (upper data, shared D block)
+    const double *rd, *w1, *w2;    // [q]
+    const double *S;               // [nb][3][m]
+    const double *rdA, *offA;      // [nh], [nh-1]
+    int nb;
+    // product operator T = Symmetric(upper data), shared D block (may be absent: nbT = -1)
+    const double *t0, *t1, *t2;    // [q]
+    const double *Ts;              // [nbT][3][m]
+    const double *TAd, *TAu;
+    int nbT;
+    int has1;                      // the first super-diagonal of a D block (factor or product) may be non-zero
+    double gamma;
+    int m, nh, q, k0, ml, hA, nhl, hB, rank, world;
+    int64_t nrows, ld, ldf;
+    int kb[POP_DD_MAXWORLD + 1];
+};
+
+
+// One-pass row half step on ONE GPU (pop_row1.cuh): rows of R <- T (S^{-1} r) + gamma f with the row block resident in the
+// registers of a thread-block cluster.  Returns POP_OK, an error, or POP_ROW1_UNSUPPORTED (caller falls back).
+#define POP_ROW1_UNSUPPORTED 1
+int pop_row1_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R);
+// X / F on a row panel (nrhs x n): POP_OK, an error, or POP_ROW1_UNSUPPORTED
+int pop_row1_solve_right(pop_ctx *ctx, const pop_arrowhead *U, double *dX, int64_t ldx, int64_t nrhs);

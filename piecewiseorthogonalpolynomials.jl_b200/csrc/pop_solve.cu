@@ -9,6 +9,7 @@
 //   RIGHT (rows of an nrhs x n matrix)   : sv = ld, sc = 1   -> lanes run over the batch
 // so every warp access is a run of consecutive doubles in both cases.
 #include "pop_internal.h"
+#include "pop_row.h"
 
 #define FULL 0xffffffffu
 
@@ -292,7 +293,13 @@ extern "C" int pop_solve(pop_ctx *ctx, const pop_arrowhead *U, int side, double 
         if (pop_fused_supported(ctx, U, nullptr)) return pop_launch_solve_fused(ctx, U, nullptr, 0.0, nullptr, 0, dX, ldx, nrhs);
         POP_REQUIRE(algo != POP_SOLVE_FUSED && algo != POP_SOLVE_FUSED_SMEM, POP_ERR_DIM, "pop_solve: fused kernel does not support this shape (n=%lld)", (long long)U->n());
     }
-    POP_REQUIRE(!(side == POP_RIGHT && (algo == POP_SOLVE_FUSED || algo == POP_SOLVE_FUSED_SMEM)), POP_ERR_ARG, "pop_solve: the fused kernel acts on columns only");
+    if (side == POP_RIGHT && (algo == POP_SOLVE_AUTO || algo == POP_SOLVE_FUSED)) {
+        // X / F: the one-pass row kernel keeps a block of rows on chip for both sweeps (pop_row1.cuh)
+        rc = pop_row1_solve_right(ctx, U, dX, ldx, nrhs);
+        if (rc != POP_ROW1_UNSUPPORTED) return rc;
+    }
+    POP_REQUIRE(!(side == POP_RIGHT && (algo == POP_SOLVE_FUSED || algo == POP_SOLVE_FUSED_SMEM)), POP_ERR_ARG,
+                "pop_solve: no single-pass kernel for this row panel (shared D block with <= 2 bands, q <= 64 needed)");
     TriView up, lo;
     pop_make_triview(U, POP_UPPER, 0, 0, &up);
     pop_make_triview(U, POP_UPPER, 1, 0, &lo);

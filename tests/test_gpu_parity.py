@@ -418,6 +418,81 @@ def test_element_decomposed_row_half_step_and_adi(basis, m, N):
     dd.close()
 
 
+@pytest.mark.parametrize("basis,m,N,nrows", [("c1", 3, 10, 1), ("dirichlet", 8, 12, 9), ("c1", 16, 40, 37), ("dirichlet", 32, 64, 50), ("dirichlet", 6, 80, 5)])
+def test_rdiv_one_pass_rows(basis, m, N, nrows):
+    """X / F (examples/adi_poisson.jl:54) on a row panel: pop_solve(side=RIGHT) runs the one-pass row kernel
+    (csrc/pop_row1.cuh) when the chain fits (q <= 64), the staged row kernels otherwise; both against the oracle."""
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    S = -Lp + 2.5 * M
+    So = O.packed_axpby(-1.0, Lo, 2.5, Mo)
+    Uo = O.packed_revchol(So)
+    F = P.reversecholesky(S)
+    n = Mo.n
+    rng = np.random.default_rng(21)
+    R = rng.standard_normal((nrows, n))
+    want = O.packed_solve(Uo, R.T.copy()).T
+    auto = host(P.rdiv(dev(R), F))
+    staged = host(P.rdiv(dev(R), F, algo=P.SOLVE_STAGED))
+    assert relerr(auto, want) < TOL
+    assert relerr(staged, want) < TOL
+    assert relerr(auto, staged) < 1e-13
+    if N - 1 <= 64:
+        assert relerr(host(P.rdiv(dev(R), F, algo=P.SOLVE_FUSED)), want) < TOL    # must not fall back
+    else:
+        with pytest.raises(Exception):
+            P.rdiv(dev(R), F, algo=P.SOLVE_FUSED)
+
+
+@pytest.mark.parametrize("basis,m,N,cs,rb", [
+    ("dirichlet", 8, 12, 2, 16), ("dirichlet", 8, 12, 4, 16), ("dirichlet", 8, 12, 8, 16), ("c1", 8, 9, 4, 16), ("c1", 8, 9, 8, 8),
+    ("dirichlet", 16, 9, 8, 8), ("dirichlet", 12, 20, 4, 16), ("c1", 6, 21, 2, 8), ("dirichlet", 8, 40, 4, 16), ("c1", 4, 64, 2, 16),
+    ("dirichlet", 8, 65, 8, 16), ("dirichlet", 5, 33, 1, 16)])
+def test_one_pass_row_half_step(basis, m, N, cs, rb, monkeypatch):
+    """csrc/pop_row1.cuh: the register-resident one-pass row half step (one GPU) for every chain class, cluster size
+    and row-block height, against the oracle's dense algebra AND against the two-pass row kernels of pop_row.cu."""
+    from pop_b200 import _lib as L
+    from pop_b200.arrowhead import _bind_stream
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    n = Mo.n
+    rng = np.random.default_rng(11)
+    Rm, Fm = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    if basis == "c1":
+        Kd = Kd + 0.3 * Md
+        K = K + 0.3 * M
+    Sd, Td = Kd + 3.7 * Md, 0.5 * Md - Kd
+    want = np.linalg.solve(Sd, Rm.T).T @ Td - 0.4 * Fm
+    dd = P.ElementDecomposition(M)
+    Fs = P.reversecholesky(K + 3.7 * M)
+    T = 0.5 * M - K
+    R, Fd = dd.panel(), dd.panel()
+    Fd.copy_(torch.from_numpy(Fm).cuda())
+    _bind_stream(M.data.ctx)
+    got = {}
+    for mode in ("one-pass", "one-pass-direct-f", "one-pass-unsplit", "two-pass"):
+        monkeypatch.setenv("POP_ROW1", "0" if mode == "two-pass" else "2")    # 2: also for the half step with the product
+        monkeypatch.setenv("POP_ROW1_NPAR", "1" if mode == "one-pass-unsplit" else "2")   # 2: even/odd degree chains on two threads
+        monkeypatch.setenv("POP_ROW1_CS", str(cs))
+        monkeypatch.setenv("POP_ROW1_RB", str(rb))
+        monkeypatch.setenv("POP_ROW1_STAGE_F", "0" if mode == "one-pass-direct-f" else "1")
+        monkeypatch.setenv("POP_ROW1_STRICT", "1")    # the forced plan must apply: no silent fallback to the two-pass kernels
+        R.copy_(torch.from_numpy(Rm).cuda())
+        L.check(L.lib().pop_dd_row_half_step(M.data.ctx.handle, dd._h, Fs.factor._h, T.data._h, -0.4, Fd.data_ptr(), Fd.stride(1), R.data_ptr(), R.stride(1)))
+        torch.cuda.synchronize()
+        got[mode] = host(R)
+        assert relerr(got[mode], want) < TOL, mode
+        R.copy_(torch.from_numpy(Rm).cuda())
+        L.check(L.lib().pop_dd_row_half_step(M.data.ctx.handle, dd._h, Fs.factor._h, None, 0.0, None, 0, R.data_ptr(), R.stride(1)))
+        torch.cuda.synchronize()
+        assert relerr(host(R), np.linalg.solve(Sd, Rm.T).T) < TOL, mode
+    assert relerr(got["one-pass"], got["two-pass"]) < 1e-13
+    assert relerr(got["one-pass-unsplit"], got["two-pass"]) < 1e-13
+    assert np.array_equal(got["one-pass"], got["one-pass-direct-f"])
+    dd.close()
+
+
 def test_heat_steps_vs_oracle():
     # examples/heat.jl:58-63 (1D) and its factored 2D extension
     m, N = 6, 10
