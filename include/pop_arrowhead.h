@@ -112,6 +112,13 @@ int pop_arrowhead_copy(pop_ctx *ctx, const pop_arrowhead *A, pop_arrowhead **out
 int pop_assemble(pop_ctx *ctx, int basis, int m, int N, double h, pop_arrowhead **mass,
                  pop_arrowhead **lap);
 
+/* Non-uniform mesh: h_elems[k] = points[k+1]-points[k] (host array of m element lengths).  One D block per element
+ * (desc.uniform = 0).  mass: the reference's generic grammatrix L'*G*L (src/continuouspolynomial.jl:259-265,293-297);
+ * lap: -(diff C)' G (diff C) with the per-element scalings of src/continuouspolynomial.jl:318-325 (the reference
+ * defines weaklaplacian itself for ranges only).  Synchronises the context's stream. */
+int pop_assemble_mesh(pop_ctx *ctx, int basis, int m, int N, const double *h_elems, pop_arrowhead **mass,
+                      pop_arrowhead **lap);
+
 /* ---- algebra: alpha*X + beta*Y with ragged B/C and D bands (src/arrowhead.jl:392-417) */
 int pop_axpby(pop_ctx *ctx, double alpha, const pop_arrowhead *X, double beta,
               const pop_arrowhead *Y, pop_arrowhead **out);

@@ -682,9 +682,8 @@ def packed_axpby(alpha, X: Packed, beta, Y: Packed) -> Packed:
 C1, DIRICHLET = 0, 1
 
 
-def assemble_mass(basis: int, m: int, N: int, h: float) -> Packed:
-    """grammatrix(C)[KR,KR] upper data, KR = Block.(oneto(N)).
-    C1: src/continuouspolynomial.jl:274-290 ; Dirichlet: src/dirichlet.jl:180-196."""
+def _assemble_mass_uniform(basis: int, m: int, N: int, h: float) -> Packed:
+    """The reference's own expressions on a range (src/continuouspolynomial.jl:274-290, src/dirichlet.jl:180-196)."""
     q = N - 1
     nh = m + 1 if basis == C1 else m - 1
     if basis == C1:
@@ -708,13 +707,11 @@ def assemble_mass(basis: int, m: int, N: int, h: float) -> Packed:
     if q > 2:
         i2 = i1[:q - 2]
         D[2, :q - 2] = ((h / 2) * (-2.0) / ((2 * i2 + 1) * (2 * i2 + 3) * (2 * i2 + 5)))[:, None]
-    B = B[:, :, :]
     return Packed(m, nh, q, 0, 2, Ad, Au, np.zeros_like(Au), B, np.zeros((0, 3, m)), D)
 
 
-def assemble_weaklaplacian(basis: int, m: int, N: int, h: float) -> Packed:
-    """weaklaplacian(C)[KR,KR] upper data (negative semi-definite).
-    C1: src/continuouspolynomial.jl:348-357 ; Dirichlet: src/dirichlet.jl:169-178."""
+def _assemble_weaklaplacian_uniform(basis: int, m: int, N: int, h: float) -> Packed:
+    """src/continuouspolynomial.jl:348-357 (C1), src/dirichlet.jl:169-178 (Dirichlet)."""
     q = N - 1
     nh = m + 1 if basis == C1 else m - 1
     si = 1.0 / h
@@ -725,6 +722,81 @@ def assemble_weaklaplacian(basis: int, m: int, N: int, h: float) -> Packed:
     D = np.zeros((1, q, m))
     i1 = np.arange(1, q + 1, dtype=float)
     D[0] = (-4.0 / (h * (2 * i1 + 1)))[:, None]
+    return Packed(m, nh, q, 0, 0, Ad, Au, np.zeros_like(Au), np.zeros((0, 3, m)), np.zeros((0, 3, m)), D)
+
+
+def _element_steps(h, m: int) -> np.ndarray:
+    """Element lengths: a scalar step (uniform mesh, `step(r)`) or the m values `diff(points)`."""
+    hk = np.asarray(h, dtype=np.float64)
+    if hk.ndim == 0:
+        hk = np.full(m, float(hk))
+    if hk.shape != (m,) or np.any(hk <= 0):
+        raise ValueError("need m positive element lengths")
+    return hk
+
+
+def assemble_mass(basis: int, m: int, N: int, h) -> Packed:
+    """grammatrix(C)[KR,KR] upper data, KR = Block.(oneto(N)).
+    C1: src/continuouspolynomial.jl:274-290 ; Dirichlet: src/dirichlet.jl:180-196.
+    `h` scalar: the closed forms of a uniform mesh, as in the reference.  `h` array (element lengths of a
+    non-uniform mesh): the same element integrals with h_k per element, i.e. what the reference's generic
+    `L' * grammatrix(P) * L` (src/continuouspolynomial.jl:259-265,293-297) evaluates to."""
+    q = N - 1
+    nh = m + 1 if basis == C1 else m - 1
+    if np.ndim(h) == 0:
+        return _assemble_mass_uniform(basis, m, N, float(h))
+    hk = _element_steps(h, m)
+    # hat i of the C1 basis sits on node i (elements i-1 and i); the Dirichlet basis drops nodes 0 and m
+    node = np.zeros(m + 1)
+    node[:-1] += hk / 3
+    node[1:] += hk / 3
+    if basis == C1:
+        Ad = node.copy()
+        Au = hk / 6                       # hats k, k+1 share element k
+    else:
+        Ad = node[1:-1].copy()
+        Au = hk[1:-1] / 6                 # hats i, i+1 (nodes i+1, i+2) share element i+1
+    B = np.zeros((2, 3, m))
+    ks = np.arange(m)
+    # left hat of element k: C1 -> hat k (slot 1), Dirichlet -> hat k-1 (slot 0)
+    tl, tr = (1, 2) if basis == C1 else (0, 1)
+    for t, v1, v2 in ((tl, hk / 6, -hk / 30), (tr, hk / 6, hk / 30)):
+        i = ks + t - 1
+        ok = (i >= 0) & (i < nh)
+        B[0, t, ok] = v1[ok]
+        B[1, t, ok] = v2[ok]
+    D = np.zeros((3, q, m))
+    i1 = np.arange(1, q + 1, dtype=float)
+    D[0] = (hk / 2)[None, :] * 4.0 / ((2 * i1 - 1) * (2 * i1 + 1) * (2 * i1 + 3))[:, None]
+    if q > 2:
+        i2 = i1[:q - 2]
+        D[2, :q - 2] = (hk / 2)[None, :] * (-2.0) / ((2 * i2 + 1) * (2 * i2 + 3) * (2 * i2 + 5))[:, None]
+    return Packed(m, nh, q, 0, 2, Ad, Au, np.zeros_like(Au), B, np.zeros((0, 3, m)), D)
+
+
+def assemble_weaklaplacian(basis: int, m: int, N: int, h) -> Packed:
+    """weaklaplacian(C)[KR,KR] upper data (negative semi-definite).
+    C1: src/continuouspolynomial.jl:348-357 ; Dirichlet: src/dirichlet.jl:169-178 (uniform meshes; the reference
+    defines it for ranges only).  With an array of element lengths: -(diff C)' G (diff C) with the per-element
+    scalings of `diff` on a non-uniform mesh (src/continuouspolynomial.jl:318-325)."""
+    q = N - 1
+    nh = m + 1 if basis == C1 else m - 1
+    if np.ndim(h) == 0:
+        return _assemble_weaklaplacian_uniform(basis, m, N, float(h))
+    hk = _element_steps(h, m)
+    si = 1.0 / hk
+    node = np.zeros(m + 1)
+    node[:-1] -= si
+    node[1:] -= si
+    if basis == C1:
+        Ad = node.copy()
+        Au = si.copy()
+    else:
+        Ad = node[1:-1].copy()
+        Au = si[1:-1].copy()
+    D = np.zeros((1, q, m))
+    i1 = np.arange(1, q + 1, dtype=float)
+    D[0] = -4.0 / (hk[None, :] * (2 * i1 + 1)[:, None])
     return Packed(m, nh, q, 0, 0, Ad, Au, np.zeros_like(Au), np.zeros((0, 3, m)), np.zeros((0, 3, m)), D)
 
 
@@ -753,10 +825,11 @@ def bubble_values(xi, nmax):
     return W, dW
 
 
-def quadrature_matrices(basis: int, m: int, N: int, h: float):
-    """Dense mass and weak-Laplacian (= -stiffness) of the C1 / Dirichlet basis on a uniform
-    mesh of m elements with blocks 1..N, computed by Gauss-Legendre quadrature."""
+def quadrature_matrices(basis: int, m: int, N: int, h):
+    """Dense mass and weak-Laplacian (= -stiffness) of the C1 / Dirichlet basis on a mesh of m elements
+    (scalar h: uniform; array: element lengths) with blocks 1..N, computed by Gauss-Legendre quadrature."""
     q = N - 1
+    hk = _element_steps(h, m)
     ng = N + 4
     xg, wg = np.polynomial.legendre.leggauss(ng)
     W, dW = bubble_values(xg, N)
@@ -770,8 +843,8 @@ def quadrature_matrices(basis: int, m: int, N: int, h: float):
         idx = [k, k + 1] + [nhC + j * m + k for j in range(q)]
         F = np.vstack([hat, W[2:N + 1]])
         dF = np.vstack([dhat, dW[2:N + 1]])
-        Ml = (F * wg) @ F.T * (h / 2)
-        Kl = (dF * wg) @ dF.T * (2 / h)
+        Ml = (F * wg) @ F.T * (hk[k] / 2)
+        Kl = (dF * wg) @ dF.T * (2 / hk[k])
         Mm[np.ix_(idx, idx)] += Ml
         Km[np.ix_(idx, idx)] += Kl
     if basis == DIRICHLET:

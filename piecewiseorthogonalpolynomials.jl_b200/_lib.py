@@ -70,6 +70,7 @@ _PROTOS = {
     "pop_arrowhead_free": (C.c_int, [vp, vp]),
     "pop_arrowhead_copy": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "pop_assemble": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(vp), C.POINTER(vp)]),
+    "pop_assemble_mesh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp)]),
     "pop_axpby": (C.c_int, [vp, C.c_double, vp, C.c_double, vp, C.POINTER(vp)]),
     "pop_revchol": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "pop_revchol_inplace": (C.c_int, [vp, vp]),

@@ -3,8 +3,9 @@
 Mirrors, for the hot path only, /root/reference/src/continuouspolynomial.jl:274-290,348-357 and
 src/dirichlet.jl:169-196 (closed forms on a uniform mesh) plus the truncation `M[KR,KR]` with
 `KR = Block.(oneto(N))` (src/arrowhead.jl:141-149).  The entries are generated on the device by
-pop_assemble; nothing is computed on the host.  Non-uniform meshes (generic `L'*G*L`,
-src/continuouspolynomial.jl:293-297) are a "next" row and raise.
+pop_assemble; nothing is computed on the host.  Non-uniform meshes (the reference's generic
+`L'*G*L`, src/continuouspolynomial.jl:259-265,293-297, and `diff`, :318-325) go through pop_assemble_mesh: one
+D block per element, factor / solve / product on the per-element kernels.
 """
 from __future__ import annotations
 
@@ -36,16 +37,17 @@ class Block:
         return BlockRange(int(N))
 
 
-def _uniform_step(points) -> float:
+def _mesh_steps(points):
+    """(uniform?, step, element lengths): a range (`AbstractRange` in the reference) takes the closed forms of
+    src/continuouspolynomial.jl:274-290; any other increasing grid is a non-uniform mesh."""
     p = np.asarray(points, dtype=np.float64)
     if p.ndim != 1 or p.size < 2:
         raise ValueError("points must be a 1-D grid with at least two nodes")
     h = np.diff(p)
     if np.any(h <= 0):
         raise ValueError("points must be increasing")
-    if np.max(np.abs(h - h[0])) > 8 * np.finfo(float).eps * max(1.0, np.abs(p).max()):
-        raise NotImplementedError("non-uniform meshes are not on the accelerated path yet (SURVEY.md 8f-3)")
-    return float((p[-1] - p[0]) / (p.size - 1))
+    uniform = bool(np.max(np.abs(h - h[0])) <= 8 * np.finfo(float).eps * max(1.0, np.abs(p).max()))
+    return uniform, float((p[-1] - p[0]) / (p.size - 1)), np.ascontiguousarray(h)
 
 
 class _Basis:
@@ -53,7 +55,7 @@ class _Basis:
 
     def __init__(self, points):
         self.points = np.asarray(points, dtype=np.float64)
-        self.h = _uniform_step(self.points)
+        self.uniform, self.h, self.hk = _mesh_steps(self.points)
         self.m = self.points.size - 1
 
     def __eq__(self, o):
@@ -123,8 +125,12 @@ class LazyArrowhead:
             raise TypeError("arrowhead truncation needs [Block.oneto(N), Block.oneto(N)]")
         ctx = self.ctx or L.default_context()
         hm, hl = C.c_void_p(), C.c_void_p()
-        L.check(L.lib().pop_assemble(ctx.handle, self.basis.basis_id, self.basis.m, KR.N, self.basis.h,
-                                     C.byref(hm) if self.cm != 0 else None, C.byref(hl) if self.cl != 0 else None), "assemble")
+        pm, pl = (C.byref(hm) if self.cm != 0 else None), (C.byref(hl) if self.cl != 0 else None)
+        if self.basis.uniform:
+            L.check(L.lib().pop_assemble(ctx.handle, self.basis.basis_id, self.basis.m, KR.N, self.basis.h, pm, pl), "assemble")
+        else:
+            hk = self.basis.hk
+            L.check(L.lib().pop_assemble_mesh(ctx.handle, self.basis.basis_id, self.basis.m, KR.N, hk.ctypes.data_as(C.c_void_p), pm, pl), "assemble")
         Mh = BBBArrowheadMatrix(ctx=ctx, _handle=hm) if self.cm != 0 else None
         Lh = BBBArrowheadMatrix(ctx=ctx, _handle=hl) if self.cl != 0 else None
         if Mh is not None and Lh is not None:

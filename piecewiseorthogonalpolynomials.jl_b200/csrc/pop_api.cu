@@ -506,6 +506,87 @@ extern "C" int pop_assemble(pop_ctx *ctx, int basis, int m, int N, double h, pop
     return POP_OK;
 }
 
+// Non-uniform mesh: element k has length hk[k]; one D block per element (mD = m), element index fastest.
+// The element integrals are those of the uniform closed forms with h -> h_k, i.e. what the reference's generic
+// L' * grammatrix(P) * L (src/continuouspolynomial.jl:259-265,293-297) and -(diff C)' G (diff C)
+// (src/continuouspolynomial.jl:318-325) evaluate to.
+__global__ void k_assemble_mesh(ArrowPtrs M, ArrowPtrs L, int basis, int m, int nh, int q, const double *__restrict__ hk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nh) {
+        // hat i sits on node i (C1) or node i+1 (Dirichlet): elements node-1 and node
+        const int node = basis == POP_BASIS_C1 ? i : i + 1;
+        const double hl = node >= 1 ? hk[node - 1] : 0.0, hr = node < m ? hk[node] : 0.0;
+        if (M.Ad) M.Ad[i] = (hl + hr) / 3;
+        if (L.Ad) L.Ad[i] = -((node >= 1 ? 1.0 / hl : 0.0) + (node < m ? 1.0 / hr : 0.0));
+        if (i < nh - 1) {   // hats i and i+1 share element `node`
+            if (M.Au) M.Au[i] = hr / 6;
+            if (L.Au) L.Au[i] = 1.0 / hr;
+        }
+    }
+    if (i < m && M.B) {
+        const double h = hk[i];
+        const int tl = basis == POP_BASIS_C1 ? 1 : 0;
+        const int il = i + tl - 1, ir = il + 1;
+        if (il >= 0 && il < nh) {
+            M.B[(0 * 3 + tl) * (size_t)m + i] = h / 6;
+            M.B[(1 * 3 + tl) * (size_t)m + i] = -h / 30;
+        }
+        if (ir >= 0 && ir < nh) {
+            M.B[(0 * 3 + tl + 1) * (size_t)m + i] = h / 6;
+            M.B[(1 * 3 + tl + 1) * (size_t)m + i] = h / 30;
+        }
+    }
+    // D[band][j][k]: one thread per (j, k)
+    const size_t plane = (size_t)q * m;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e / m), k = (int)(e % m);
+        const double h = hk[k], j1 = j + 1.0;
+        if (M.D) {
+            M.D[e] = (h / 2) * 4.0 / ((2 * j1 - 1) * (2 * j1 + 1) * (2 * j1 + 3));
+            M.D[plane + e] = 0.0;
+            M.D[2 * plane + e] = (j + 2 < q) ? (h / 2) * (-2.0) / ((2 * j1 + 1) * (2 * j1 + 3) * (2 * j1 + 5)) : 0.0;
+        }
+        if (L.D) L.D[e] = -4.0 / (h * (2 * j1 + 1));
+    }
+}
+
+extern "C" int pop_assemble_mesh(pop_ctx *ctx, int basis, int m, int N, const double *h_elems, pop_arrowhead **mass, pop_arrowhead **lap) {
+    POP_REQUIRE(ctx && h_elems, POP_ERR_ARG, "pop_assemble_mesh: null argument");
+    POP_REQUIRE(basis == POP_BASIS_C1 || basis == POP_BASIS_DIRICHLET, POP_ERR_ARG, "pop_assemble_mesh: unknown basis %d", basis);
+    POP_REQUIRE(N >= 1, POP_ERR_ARG, "pop_assemble_mesh: need N>=1");
+    const int nh = basis == POP_BASIS_C1 ? m + 1 : m - 1;
+    POP_REQUIRE(m >= 1 && nh >= 1, POP_ERR_DIM, "pop_assemble_mesh: mesh of %d elements has no hat functions for this basis", m);
+    for (int k = 0; k < m; ++k) POP_REQUIRE(h_elems[k] > 0, POP_ERR_ARG, "pop_assemble_mesh: element %d has non-positive length (points must be increasing)", k);
+    const int q = N - 1;
+    double *dh = nullptr;
+    int rc = pop_ctx_scratch(ctx, (size_t)m * sizeof(double), (void **)&dh);
+    if (rc) return rc;
+    POP_CUDA(cudaMemcpyAsync(dh, h_elems, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    pop_arrowhead *hm = nullptr, *hl = nullptr;
+    ArrowPtrs pm = {}, pl = {};
+    if (mass) {
+        pop_desc d = {m, nh, q, 2, 0, 0, 2, 0};
+        rc = pop_alloc_handles(ctx, d, m, 1, &hm);
+        if (rc) return rc;
+        pm = hm->p;
+    }
+    if (lap) {
+        pop_desc d = {m, nh, q, 0, 0, 0, 0, 0};
+        rc = pop_alloc_handles(ctx, d, m, 1, &hl);
+        if (rc) { pop_arrowhead_free(ctx, hm); return rc; }
+        pl = hl->p;
+    }
+    const size_t work = std::max<size_t>((size_t)q * m, (size_t)std::max(nh, m));
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, 4096);
+    k_assemble_mesh<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(pm, pl, basis, m, nh, q, dh);
+    LAUNCH_COUNT(ctx);
+    POP_CUDA(cudaGetLastError());
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's h_elems and the scratch copy may be reused at once
+    if (mass) { hm->bmask = basis == POP_BASIS_C1 ? 6 : 3; hm->band1_zero = true; *mass = hm; }
+    if (lap) { hl->band1_zero = true; *lap = hl; }
+    return POP_OK;
+}
+
 struct BatchPtrs {  // device-side array element for batched outputs
     ArrowPtrs p;
 };

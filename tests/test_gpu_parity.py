@@ -418,6 +418,40 @@ def test_element_decomposed_row_half_step_and_adi(basis, m, N):
     dd.close()
 
 
+@pytest.mark.parametrize("basis", ["c1", "dirichlet"])
+def test_nonuniform_mesh_assembly_factor_solve(basis):
+    """grammatrix / weaklaplacian on a non-uniform mesh (pop_assemble_mesh, one D block per element),
+    reverse Cholesky, F \\ X, X / F and the product against the oracle (closed forms verified by quadrature)."""
+    pts = np.concatenate([[-1.0], -1.0 + 2.0 * np.sort(np.random.default_rng(3).random(10)), [1.0]])
+    hk = np.diff(pts)
+    m, N = hk.size, 12
+    bo = O.C1 if basis == "c1" else O.DIRICHLET
+    Q = P.ContinuousPolynomial(1, pts) if basis == "c1" else P.DirichletPolynomial(pts)
+    assert not Q.uniform
+    KR = P.Block.oneto(N)
+    M, Lp = P.grammatrix(Q)[KR, KR], P.weaklaplacian(Q)[KR, KR]
+    Mo, Lo = O.assemble_mass(bo, m, N, hk), O.assemble_weaklaplacian(bo, m, N, hk)
+    Md, Ld = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Lo)).to_dense()
+    assert relerr(M.to_dense(), Md) < 1e-15
+    assert relerr(Lp.to_dense(), Ld) < 1e-15
+    S = -Lp + 1.5 * M
+    Sd = -Ld + 1.5 * Md
+    F = P.reversecholesky(S)
+    Uo = O.packed_revchol(O.packed_axpby(-1.0, Lo, 1.5, Mo))
+    assert relerr(F.U.to_dense(), O.unpack(Uo).to_dense()) < TOL
+    n = Mo.n
+    rng = np.random.default_rng(9)
+    Bm = rng.standard_normal((n, 33))
+    want = O.packed_solve(Uo, Bm.copy())
+    for algo in (P.SOLVE_AUTO, P.SOLVE_STAGED, P.SOLVE_FUSED_SMEM):
+        X = host(P.ldiv(F, dev(Bm), algo=algo))
+        assert relerr(X, want) < TOL, algo
+        assert np.linalg.norm(Sd @ X - Bm) / (np.linalg.norm(Sd, 2) * np.linalg.norm(X)) < TOL
+    R = rng.standard_normal((7, n))
+    assert relerr(host(P.rdiv(dev(R), F)), np.linalg.solve(Sd, R.T).T) < TOL
+    assert relerr(host(S @ dev(Bm)), Sd @ Bm) < TOL
+
+
 @pytest.mark.parametrize("basis,m,N,nrows", [("c1", 3, 10, 1), ("dirichlet", 8, 12, 9), ("c1", 16, 40, 37), ("dirichlet", 32, 64, 50), ("dirichlet", 6, 80, 5)])
 def test_rdiv_one_pass_rows(basis, m, N, nrows):
     """X / F (examples/adi_poisson.jl:54) on a row panel: pop_solve(side=RIGHT) runs the one-pass row kernel

@@ -253,3 +253,30 @@ def test_heat_1d():
     for _ in range(10):
         w = np.linalg.solve(Md + 1e-3 * Kd, Md @ w)
     np.testing.assert_allclose(u, w, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("basis", [O.C1, O.DIRICHLET])
+def test_nonuniform_mesh_closed_forms_match_quadrature(basis):
+    """the per-element closed forms on a non-uniform mesh (what the reference's generic L'*G*L,
+    src/continuouspolynomial.jl:259-265,293-297, evaluates to) against Gauss quadrature of the basis; a uniform
+    array of element lengths reproduces the range closed forms exactly (test_continuouspolynomial.jl:69-80)."""
+    pts = np.array([-1.0, -0.7, -0.55, 0.1, 0.2, 1.0])
+    hk = np.diff(pts)
+    m, N = hk.size, 9
+    Mq, Lq = O.quadrature_matrices(basis, m, N, hk)
+    Mc = O.unpack(O.packed_symmetrize(O.assemble_mass(basis, m, N, hk))).to_dense()
+    Lc = O.unpack(O.packed_symmetrize(O.assemble_weaklaplacian(basis, m, N, hk))).to_dense()
+    assert np.abs(Mc - Mq).max() < 1e-14
+    assert np.abs(Lc - Lq).max() < 1e-12
+    hu = np.full(m, 0.4)
+    for f in (O.assemble_mass, O.assemble_weaklaplacian):
+        a, b = f(basis, m, N, hu), f(basis, m, N, 0.4)
+        for x, y in ((a.Ad, b.Ad), (a.Au, b.Au), (a.B, b.B), (a.D, b.D)):
+            assert np.allclose(x, y, rtol=4e-16, atol=0)
+    # the graded-mesh Helmholtz operator factors and solves like the uniform one
+    So = O.packed_axpby(-1.0, O.assemble_weaklaplacian(basis, m, N, hk), 1.0, O.assemble_mass(basis, m, N, hk))
+    Uo = O.packed_revchol(So)
+    b = np.random.default_rng(4).standard_normal(So.n)
+    x = O.packed_solve(Uo, b.copy())
+    Sd = Mc - Lc
+    assert np.linalg.norm(Sd @ x - b) / np.linalg.norm(b) < 1e-12
