@@ -171,6 +171,23 @@ int pop_solve_shift_batch(pop_ctx *ctx, pop_arrowhead *const *U, int nshift, dou
 int pop_solve_mul_axpy(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *Tm, double gamma,
                        const double *dF, int64_t ldf, double *dR, int64_t ldr, int64_t nrhs);
 
+/* ---- right-hand-side pipeline of examples/adi_poisson.jl ------------------------------
+ * analysis_2D (examples/adi_poisson.jl:60-76): dV is the (n p) x (n p) matrix of function values, entry
+ * (i p + s, j p + t) = f at node s of cell i in x and node t of cell j in y; T_host (p x p, column-major, host)
+ * is the analysis matrix of the cell grid (`plan_grid_transform(legendre(0..dx), (p,p))`: coefficients = T * values).
+ * dF receives the tensor Legendre coefficients interlaced like a block vector: F[i + n a, j + n b]
+ * (`F[i+1:n:n*p, j+1:n:n*p] = T * f_.(z, z')`).  p <= 64.  Synchronises the stream. */
+int pop_legendre_analysis_2d(pop_ctx *ctx, int n, int p, const double *T_host, const double *dV, int64_t ldv,
+                             double *dF, int64_t ldf);
+/* (Q'P)[KR,KR] = (P\Q)' (P'P), Q = ContinuousPolynomial{1} or DirichletPolynomial, P = ContinuousPolynomial{0}
+ * (examples/adi_poisson.jl:105; P\C: src/continuouspolynomial.jl:226-235, C\Q: src/dirichlet.jl:35-42, P'P:
+ * src/continuouspolynomial.jl:259-272), KR = Block.(oneto(N)):
+ *   side LEFT :  Y (n x cnt)  <- (Q'P) X ,   X is (m N) x cnt in P ordering (degree a of element k at a m + k)
+ *   side RIGHT:  Y (cnt x n)  <- X (Q'P)',   X is cnt x (m N)
+ * so F = (Q'P) fp (Q'P)' is one LEFT and one RIGHT call.  h: uniform step; h_elems (host, [m]) overrides it. */
+int pop_weakform_apply(pop_ctx *ctx, int basis, int m, int N, double h, const double *h_elems, int side,
+                       const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t cnt);
+
 /* out-of-place transpose dst (cols x rows, ldd) <- src^T, src rows x cols (lds) */
 int pop_transpose(pop_ctx *ctx, const double *dsrc, int64_t lds, int64_t rows, int64_t cols,
                   double *ddst, int64_t ldd);

@@ -896,6 +896,122 @@ def c1_evaluate(c: np.ndarray, points: np.ndarray, N: int, x: float) -> float:
 
 
 # ---------------------------------------------------------------------------
+# Right-hand-side pipeline of examples/adi_poisson.jl:60-76,105: per-cell Legendre
+# analysis, the conversion P \ C (src/continuouspolynomial.jl:226-235) and the weak form (Q'P) fp (Q'P)'
+# ---------------------------------------------------------------------------
+
+
+def legendre_grid_transform(p: int, kind: str = "gauss"):
+    """Nodes z (reference cell [-1,1]) and the p x p analysis matrix T with  Legendre coefficients = T @ values:
+    what `plan_grid_transform(legendre(..), (p, p))` (examples/adi_poisson.jl:64) provides.  T = V^-1 with the
+    Legendre Vandermonde V[s,a] = P_a(z_s); the node family is the caller's (`gauss`: Gauss-Legendre,
+    `chebyshev1`: first-kind Chebyshev points), the coefficients of a resolved function do not depend on it."""
+    if kind == "gauss":
+        z, w = np.polynomial.legendre.leggauss(p)
+        V = np.polynomial.legendre.legvander(z, p - 1)
+        T = ((2 * np.arange(p) + 1) / 2)[:, None] * V.T * w[None, :]
+    elif kind == "chebyshev1":
+        z = np.cos(np.pi * (2 * np.arange(p)[::-1] + 1) / (2 * p))
+        V = np.polynomial.legendre.legvander(z, p - 1)
+        T = np.linalg.inv(V)
+    else:
+        raise ValueError(kind)
+    return z, T
+
+
+def analysis_2d(vals: np.ndarray, n: int, p: int, T: np.ndarray) -> np.ndarray:
+    """examples/adi_poisson.jl:60-76: vals[i*p+s, j*p+t] = f at node s of cell i (x) and node t of cell j (y);
+    returns F with F[i + n*a, j + n*b] = sum_st T[a,s] vals[...] T[b,t]  (`F[i+1:n:n*p, j+1:n:n*p] = T * f_.(z, z')`):
+    coefficients in P (x) P, P = ContinuousPolynomial{0}, interlaced like every block vector here."""
+    V4 = np.asarray(vals, dtype=np.float64).reshape(n, p, n, p)
+    C = np.einsum("as,isjt,bt->aibj", T, V4, T, optimize=True)
+    return C.reshape(n * p, n * p)
+
+
+def lowering_dense(basis: int, m: int, N: int) -> np.ndarray:
+    """(P \\ C)[KR,KR] (src/continuouspolynomial.jl:226-235) resp. (P \\ Q)[KR,KR] = (P\\C)(C\\Q) (src/dirichlet.jl:35-53),
+    KR = Block.(1:N), dense: rows = piecewise Legendre degree a (0..N-1) of element k at a*m+k, columns = the
+    C1 / Dirichlet ordering.  A = [1/2 1/2] bidiagonal, B_1 = I/3, C_1 = [-1/2 +1/2], D = tridiag(v_j above, -v_j
+    below), v_j = 1/(2j+1): hat_k = (P_0 - P_1)/2, hat_{k+1} = (P_0 + P_1)/2, W_{j+1} = (P_{j-1} - P_{j+1})/(2j+1)."""
+    q = N - 1
+    nhC = m + 1
+    R = np.zeros((m * N, nhC + m * q))
+    for k in range(m):
+        R[k, k] = R[k, k + 1] = 0.5                       # degree 0
+        if N >= 2:
+            R[m + k, k], R[m + k, k + 1] = -0.5, 0.5      # degree 1
+        for j in range(1, q + 1):                         # bubble j <-> W_{j+1}
+            v = 1.0 / (2 * j + 1)
+            col = nhC + (j - 1) * m + k
+            R[(j - 1) * m + k, col] += v
+            if j + 1 <= N - 1:
+                R[(j + 1) * m + k, col] -= v
+    if basis == DIRICHLET:
+        keep = [c for c in range(R.shape[1]) if c not in (0, m)]
+        R = R[:, keep]
+    return R
+
+
+def lowering_by_quadrature(basis: int, m: int, N: int) -> np.ndarray:
+    """The same matrix from Gauss quadrature of the basis functions against P_a (independent of the closed form)."""
+    q = N - 1
+    xg, wg = np.polynomial.legendre.leggauss(N + 4)
+    Pt = _legendre_table(xg, N)
+    W, _ = bubble_values(xg, N)
+    funcs = np.vstack([(1 - xg) / 2, (1 + xg) / 2, W[2:N + 1]])          # hat_k, hat_{k+1}, W_2..W_N on one element
+    coef = ((2 * np.arange(N) + 1) / 2)[:, None] * ((Pt[:N] * wg) @ funcs.T)   # [a, func]
+    nhC = m + 1
+    R = np.zeros((m * N, nhC + m * q))
+    for k in range(m):
+        rows = np.arange(N) * m + k
+        R[rows, k] += coef[:, 0]
+        R[rows, k + 1] += coef[:, 1]
+        for j in range(1, q + 1):
+            R[rows, nhC + (j - 1) * m + k] += coef[:, 1 + j]
+    if basis == DIRICHLET:
+        keep = [c for c in range(R.shape[1]) if c not in (0, m)]
+        R = R[:, keep]
+    return R
+
+
+def legendre_mass_diag(m: int, N: int, h) -> np.ndarray:
+    """grammatrix(ContinuousPolynomial{0})[KR,KR] (src/continuouspolynomial.jl:259-272): diagonal h_k/(2a+1) at a*m+k."""
+    hk = _element_steps(h, m)
+    return (hk[None, :] / (2 * np.arange(N)[:, None] + 1)).reshape(-1)
+
+
+def weakform_dense(basis: int, m: int, N: int, h) -> np.ndarray:
+    """(Q'P)[KR,KR] = (P\\Q)' (P'P)  (examples/adi_poisson.jl:105, src/continuouspolynomial.jl:299-304)."""
+    return lowering_dense(basis, m, N).T * legendre_mass_diag(m, N, h)[None, :]
+
+
+def weakform_rhs(basis: int, m: int, N: int, h, fp: np.ndarray) -> np.ndarray:
+    """F = (Q'P) fp (Q'P)'  (examples/adi_poisson.jl:105)."""
+    A = weakform_dense(basis, m, N, h)
+    return A @ fp @ A.T
+
+
+def basis_eval_matrix(basis: int, points: np.ndarray, N: int, x: np.ndarray) -> np.ndarray:
+    """Q[x, KR] / C[x, KR]: values of the basis functions (columns, arrowhead order) at the points x."""
+    m = len(points) - 1
+    q = N - 1
+    nhC = m + 1
+    E = np.zeros((len(x), nhC + m * q))
+    for r, xv in enumerate(x):
+        k = min(max(int(np.searchsorted(points, xv, side="right")) - 1, 0), m - 1)
+        a, b = points[k], points[k + 1]
+        xi = (2 * xv - a - b) / (b - a)
+        E[r, k], E[r, k + 1] = (1 - xi) / 2, (1 + xi) / 2
+        Wv, _ = bubble_values(np.array([xi]), N)
+        for n_ in range(2, N + 1):
+            E[r, nhC + (n_ - 2) * m + k] = Wv[n_, 0]
+    if basis == DIRICHLET:
+        keep = [c for c in range(E.shape[1]) if c not in (0, m)]
+        E = E[:, keep]
+    return E
+
+
+# ---------------------------------------------------------------------------
 # ADI driver (examples/adi_poisson.jl:11-59) and heat stepping (examples/heat.jl:58-63)
 # ---------------------------------------------------------------------------
 

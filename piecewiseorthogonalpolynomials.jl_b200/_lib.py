@@ -103,6 +103,8 @@ _PROTOS = {
     "pop_dd_column": (i64, [vp, i64]),
     "pop_dd_row_half_step": (C.c_int, [vp, vp, vp, vp, C.c_double, vp, i64, vp, i64]),
     "pop_adi_poisson_dd": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "pop_legendre_analysis_2d": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, i64]),
+    "pop_weakform_apply": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, C.c_int, vp, i64, vp, i64, i64]),
     "pop_transpose": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
     "pop_adi_num_iterations": (C.c_int, [C.c_double] * 5),
     "pop_adi_shifts": (C.c_int, [C.c_int] + [C.c_double] * 4 + [vp, vp]),

@@ -1,0 +1,84 @@
+"""Right-hand-side pipeline of examples/adi_poisson.jl on the device.
+
+  legendre_grid_transform : nodes + analysis matrix of one cell, what `plan_grid_transform(legendre(0..dx), (p,p))`
+                            (examples/adi_poisson.jl:64) provides (host arithmetic, O(p^3) once)
+  analysis_2d             : `analysis_2D` (examples/adi_poisson.jl:60-76): values on the cell grids -> tensor Legendre
+                            coefficients in P (x) P, P = ContinuousPolynomial{0}  (pop_legendre_analysis_2d)
+  weakform_apply / weakform_rhs : (Q'P)[KR,KR] X, X (Q'P)[KR,KR]' and F = (Q'P) fp (Q'P)'  (examples/adi_poisson.jl:105)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .arrowhead import _Panel, _bind_stream, _new_like
+from .bases import BlockRange, _Basis
+
+
+def legendre_grid_transform(p: int, kind: str = "gauss"):
+    """(z, T): p nodes on the reference cell [-1,1] and the analysis matrix (Legendre coefficients = T @ values),
+    T = V^-1 with V[s,a] = P_a(z_s).  `gauss`: Gauss-Legendre nodes (T = diag((2a+1)/2) V' diag(w), no inversion);
+    `chebyshev1`: first-kind Chebyshev points."""
+    if kind == "gauss":
+        z, w = np.polynomial.legendre.leggauss(p)
+        V = np.polynomial.legendre.legvander(z, p - 1)
+        T = ((2 * np.arange(p) + 1) / 2)[:, None] * V.T * w[None, :]
+    elif kind == "chebyshev1":
+        z = np.cos(np.pi * (2 * np.arange(p)[::-1] + 1) / (2 * p))
+        T = np.linalg.inv(np.polynomial.legendre.legvander(z, p - 1))
+    else:
+        raise ValueError(f"unknown node family {kind!r}")
+    return z, np.asfortranarray(T)
+
+
+def cell_grid(points, z):
+    """All nodes of a uniform mesh, cell by cell: x[i*p + s] = node s of cell i (what `f_.(z, z')` is evaluated on)."""
+    pts = np.asarray(points, dtype=np.float64)
+    a, b = pts[:-1], pts[1:]
+    return ((a + b)[:, None] / 2 + (b - a)[:, None] / 2 * np.asarray(z)[None, :]).reshape(-1)
+
+
+def analysis_2d(vals, n: int, p: int, T, ctx=None):
+    """vals: CUDA torch tensor, (n p) x (n p) column-major, vals[i p + s, j p + t] = f(x_{i,s}, y_{j,t}).
+    Returns F with F[i + n a, j + n b] = tensor Legendre coefficient (a, b) of cell (i, j)."""
+    pv = _Panel(vals, False)
+    if not pv.torch:
+        raise TypeError("analysis_2d works on device-resident (CUDA torch) values")
+    if pv.rows != n * p or pv.cols != n * p:
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: values are {pv.rows}x{pv.cols}, expected {n * p}x{n * p}")
+    T = np.asfortranarray(np.asarray(T, dtype=np.float64))
+    if T.shape != (p, p):
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: analysis matrix is {T.shape}, expected {(p, p)}")
+    ctx = ctx or L.default_context()
+    F = _new_like(vals, (n * p, n * p))
+    pf = _Panel(F, True)
+    _bind_stream(ctx)
+    L.check(L.lib().pop_legendre_analysis_2d(ctx.handle, int(n), int(p), T.ctypes.data_as(C.c_void_p), pv.ptr, pv.ld, pf.ptr, pf.ld), "analysis_2D")
+    return F
+
+
+def weakform_apply(Q: _Basis, KR: BlockRange, X, side=L.LEFT, ctx=None):
+    """(Q'P)[KR,KR] @ X (side LEFT, X has m N rows) or X @ (Q'P)[KR,KR]' (side RIGHT, X has m N columns)."""
+    N = KR.N
+    px = _Panel(X, False)
+    if not px.torch:
+        raise TypeError("weakform_apply works on device-resident (CUDA torch) panels")
+    n = Q.nh + Q.m * (N - 1)
+    nP = Q.m * N
+    if (px.rows if side == L.LEFT else px.cols) != nP:
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: (Q'P) is {n}x{nP}, panel is {px.rows}x{px.cols}")
+    cnt = px.cols if side == L.LEFT else px.rows
+    Y = _new_like(X, (n, cnt) if side == L.LEFT else (cnt, n))
+    py = _Panel(Y, True)
+    ctx = ctx or L.default_context()
+    _bind_stream(ctx)
+    hk = None if Q.uniform else Q.hk.ctypes.data_as(C.c_void_p)
+    L.check(L.lib().pop_weakform_apply(ctx.handle, Q.basis_id, Q.m, int(N), float(Q.h), hk, side, px.ptr, px.ld, py.ptr, py.ld, cnt), "weak form")
+    return Y
+
+
+def weakform_rhs(Q: _Basis, KR: BlockRange, fp, ctx=None):
+    """F = (Q'P)[KR,KR] * fp * (Q'P)[KR,KR]'  (examples/adi_poisson.jl:105)."""
+    return weakform_apply(Q, KR, weakform_apply(Q, KR, fp, L.LEFT, ctx), L.RIGHT, ctx)

@@ -1,0 +1,163 @@
+"""Right-hand-side pipeline of examples/adi_poisson.jl:60-76,105: per-cell Legendre analysis, the
+conversion P\\C and the weak form (Q'P) fp (Q'P)'.  CPU tests pin the oracle (closed forms against quadrature and the
+reference's own identities); GPU tests compare the CUDA kernels with the oracle and run the example end to end
+against its own `@test u_exact.(z) ≈ Ua`."""
+import numpy as np
+import pytest
+
+from oracle import arrowhead_oracle as O
+
+TOL = 1e-12
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+# ------------------------------------------------------------------------------------------------ oracle (CPU)
+@pytest.mark.parametrize("basis", [O.C1, O.DIRICHLET])
+@pytest.mark.parametrize("m,N", [(3, 6), (5, 9), (2, 4)])
+def test_lowering_closed_form_matches_quadrature(basis, m, N):
+    # P \ C (src/continuouspolynomial.jl:226-235) and (P\C)(C\Q) (src/dirichlet.jl:35-53)
+    assert np.abs(O.lowering_dense(basis, m, N) - O.lowering_by_quadrature(basis, m, N)).max() < 1e-14
+
+
+@pytest.mark.parametrize("basis", [O.C1, O.DIRICHLET])
+def test_lowering_reproduces_the_mass_matrix(basis):
+    # test_continuouspolynomial.jl:64: R[KR,JR]'*((P'P)[KR,KR]*R[KR,JR]) ≈ (C'C)[JR,JR], KR one block longer than JR
+    m, N = 4, 8
+    for h in (0.5, np.array([0.2, 0.7, 0.4, 0.7])):
+        R = O.lowering_dense(basis, m, N + 1)
+        G = O.legendre_mass_diag(m, N + 1, h)
+        Md = O.unpack(O.packed_symmetrize(O.assemble_mass(basis, m, N, h))).to_dense()
+        n = Md.shape[0]
+        assert np.abs(((R.T * G) @ R)[:n, :n] - Md).max() < 1e-15
+
+
+@pytest.mark.parametrize("kind", ["gauss", "chebyshev1"])
+def test_cell_analysis_is_exact_on_polynomials(kind):
+    n, p = 3, 9
+    z, T = O.legendre_grid_transform(p, kind)
+    assert np.abs(T @ np.polynomial.legendre.legvander(z, p - 1) - np.eye(p)).max() < 1e-13
+    rng = np.random.default_rng(0)
+    coef = rng.standard_normal((p, n, p, n))                       # [a, i, b, j]
+    Pz = np.polynomial.legendre.legvander(z, p - 1)                 # [s, a]
+    vals = np.einsum("sa,aibj,tb->isjt", Pz, coef, Pz).reshape(n * p, n * p)
+    F = O.analysis_2d(vals, n, p, T)
+    assert relerr(F, coef.reshape(n * p, n * p)) < 1e-13           # row a*n + i, column b*n + j
+
+
+def _poisson_example(K, p):
+    """examples/adi_poisson.jl:78-117 at a small size: returns everything the GPU test needs too."""
+    r = np.linspace(-1, 1, K + 1)
+    h = 2.0 / K
+    f = lambda x, y: -2 * np.sin(np.pi * x) * (2 * np.pi * y * np.cos(np.pi * y) + (1 - np.pi ** 2 * y ** 2) * np.sin(np.pi * y))
+    u = lambda x, y: np.sin(np.pi * x) * np.sin(np.pi * y) * y ** 2
+    z, T = O.legendre_grid_transform(p)
+    xs = ((r[:-1] + r[1:])[:, None] / 2 + h / 2 * z[None, :]).reshape(-1)
+    vals = f(xs[:, None], xs[None, :])
+    return r, h, f, u, z, T, xs, vals
+
+
+def test_adi_poisson_example_end_to_end_oracle():
+    # the reference's own check: @test u_exact.(z) ≈ Ua  (examples/adi_poisson.jl:117)
+    K, p = 4, 22
+    r, h, f, u, z, T, xs, vals = _poisson_example(K, p)
+    fp = O.analysis_2d(vals, K, p, T)
+    F = O.weakform_rhs(O.DIRICHLET, K, p, h, fp)
+    Mo = O.assemble_mass(O.DIRICHLET, K, p, h)
+    Ko = O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.DIRICHLET, K, p, h), 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    lam = np.linalg.eigvals(np.linalg.solve(Kd, Md)).real
+    X = O.adi_packed(Mo, Ko, F, lam.min(), lam.max(), -lam.max(), -lam.min())
+    Y = np.linalg.solve(Kd, X.T).T                                  # Y = (U' \ (U \ X'))'
+    pts = np.linspace(-1, 1, 41)
+    E = O.basis_eval_matrix(O.DIRICHLET, r, p, pts)
+    Ua = E @ Y @ E.T
+    assert np.abs(Ua - u(pts[:, None], pts[None, :])).max() < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------ CUDA kernels
+def _gpu():
+    import torch
+    import pop_b200 as P
+    return torch, P
+
+
+def _dev(torch, A):
+    A = np.asarray(A, dtype=np.float64)
+    ld = (A.shape[0] + 1) & ~1
+    buf = torch.zeros((A.shape[1], ld), dtype=torch.float64, device="cuda")
+    buf[:, :A.shape[0]] = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()
+    return buf.t()[:A.shape[0]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 5), (3, 16), (7, 33), (2, 64), (5, 62)])
+def test_analysis_2d_kernel_vs_oracle(n, p):
+    torch, P = _gpu()
+    z, T = P.legendre_grid_transform(p, "gauss" if p % 2 else "chebyshev1")
+    assert np.abs(T - O.legendre_grid_transform(p, "gauss" if p % 2 else "chebyshev1")[1]).max() == 0
+    vals = np.random.default_rng(n * 100 + p).standard_normal((n * p, n * p))
+    F = P.analysis_2d(_dev(torch, vals), n, p, T)
+    want = O.analysis_2d(vals, n, p, T)
+    assert relerr(F.cpu().numpy(), want) < TOL
+
+
+@pytest.mark.gpu
+def test_analysis_2d_rejects_what_it_cannot_hold():
+    torch, P = _gpu()
+    z, T = P.legendre_grid_transform(65)
+    with pytest.raises(P.DimensionMismatch):
+        P.analysis_2d(_dev(torch, np.zeros((65, 65))), 1, 65, T)
+    z, T = P.legendre_grid_transform(4)
+    with pytest.raises(P.DimensionMismatch):
+        P.analysis_2d(_dev(torch, np.zeros((9, 8))), 2, 4, T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis", ["c1", "dirichlet"])
+@pytest.mark.parametrize("m,N,uniform", [(2, 1, True), (3, 2, True), (5, 9, True), (8, 20, False), (33, 7, False)])
+def test_weakform_kernel_vs_oracle(basis, m, N, uniform):
+    torch, P = _gpu()
+    if basis == "dirichlet" and m < 2:
+        pytest.skip("no interior node")
+    rng = np.random.default_rng(m * 10 + N)
+    pts = np.linspace(-1, 1, m + 1) if uniform else np.concatenate([[-1.0], np.sort(rng.uniform(-0.9, 0.9, m - 1)), [1.0]])
+    Q = P.ContinuousPolynomial(1, pts) if basis == "c1" else P.DirichletPolynomial(pts)
+    bo = O.C1 if basis == "c1" else O.DIRICHLET
+    A = O.weakform_dense(bo, m, N, np.diff(pts))
+    KR = P.Block.oneto(N)
+    X = rng.standard_normal((m * N, 13))
+    assert relerr(P.weakform_apply(Q, KR, _dev(torch, X), P.LEFT).cpu().numpy(), A @ X) < TOL
+    Xr = rng.standard_normal((37, m * N))
+    assert relerr(P.weakform_apply(Q, KR, _dev(torch, Xr), P.RIGHT).cpu().numpy(), Xr @ A.T) < TOL
+    fp = rng.standard_normal((m * N, m * N))
+    assert relerr(P.weakform_rhs(Q, KR, _dev(torch, fp)).cpu().numpy(), A @ fp @ A.T) < TOL
+    with pytest.raises(P.DimensionMismatch):
+        P.weakform_apply(Q, KR, _dev(torch, np.zeros((m * N + 1, 2))), P.LEFT)
+
+
+@pytest.mark.gpu
+def test_adi_poisson_example_end_to_end_gpu():
+    """examples/adi_poisson.jl:78-117 through the CUDA path: analysis_2D -> (Q'P) fp (Q'P)' -> ADI -> X / Delta ->
+    evaluation, against the exact solution (the reference's `@test u_exact.(z) ≈ Ua`) and against the oracle pipeline."""
+    torch, P = _gpu()
+    K, p = 4, 22
+    r, h, f, u, z, T, xs, vals = _poisson_example(K, p)
+    Q = P.DirichletPolynomial(r)
+    KR = P.Block.oneto(p)
+    assert np.allclose(P.cell_grid(r, z), xs)
+    fp = P.analysis_2d(_dev(torch, vals), K, p, T)
+    F = P.weakform_rhs(Q, KR, fp)
+    Fo = O.weakform_rhs(O.DIRICHLET, K, p, h, O.analysis_2d(vals, K, p, T))
+    assert relerr(F.cpu().numpy(), Fo) < TOL
+    M = P.grammatrix(Q)[KR, KR]
+    Kh = -P.weaklaplacian(Q)[KR, KR]
+    a, b = P.spectrum_bounds(M, Kh, iters=400)
+    X = P.adi_poisson(M, Kh, F, a, b)
+    Y = P.rdiv(X, P.reversecholesky(Kh))                            # Y = (U' \ (U \ X'))'
+    pts = np.linspace(-1, 1, 41)
+    E = O.basis_eval_matrix(O.DIRICHLET, r, p, pts)
+    Ua = E @ Y.cpu().numpy() @ E.T
+    assert np.abs(Ua - u(pts[:, None], pts[None, :])).max() < 1e-10
