@@ -26,44 +26,70 @@ struct WeakOp {
 
 __device__ __forceinline__ double wf_h(const WeakOp &w, int k) { return w.hk ? w.hk[k] : w.h; }
 
-// sv: stride between consecutive entries of a vector, sc: stride between vectors (LEFT: 1, ld; RIGHT: ld, 1)
-// lanes run over `fast` (LEFT: the output row; RIGHT: the batch index), so every access is a run of consecutive doubles
+// One thread per (element k, vector c) walks the degrees of its element with a window of three inputs, so every input is
+// read once and every output written once (16 B per entry).  LEFT: lanes over k (entries of a column are contiguous in
+// k), RIGHT: lanes over c (the vectors are rows of the panels, contiguous in c).  The hat on the left node of element k
+// (and, for the last element, on its right node) is produced by the same thread; it re-reads two inputs of element k-1.
 template <bool LEFT>
 __global__ void __launch_bounds__(256) k_weakform(WeakOp w, const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int64_t cnt) {
-    const int64_t n = (int64_t)w.nh + (int64_t)w.m * w.q;
-    const int m = w.m, N = w.N;
-    // LEFT: x = output row (fast), y = vector ; RIGHT: x = vector (fast, a row of the panels), y = output column
-    const int64_t fx = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    for (int64_t sy = (int64_t)blockIdx.y * 8 + threadIdx.y; sy < (LEFT ? cnt : n); sy += (int64_t)gridDim.y * 8) {
-        const int64_t r = LEFT ? fx : sy, c = LEFT ? sy : fx;
-        if (r >= n || c >= cnt) continue;
-        const double *x = LEFT ? X + c * ldx : X + c;
-        const int64_t xs = LEFT ? 1 : ldx;
-        double acc = 0.0;
-        if (r < w.nh) {
-            const int nd = w.basis == POP_BASIS_C1 ? (int)r : (int)r + 1;
-            if (nd >= 1) {
-                const int k = nd - 1;
-                const double h = wf_h(w, k);
-                acc += 0.5 * h * x[(int64_t)k * xs];
-                if (N >= 2) acc += 0.5 * (h / 3) * x[((int64_t)m + k) * xs];
+    const int m = w.m, N = w.N, q = w.q;
+    const int64_t ix = (int64_t)blockIdx.x * 32 + threadIdx.x, iy = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    const int64_t kk = LEFT ? ix : iy, c = LEFT ? iy : ix;
+    if (kk >= m || c >= cnt) return;
+    const int k = (int)kk;
+    const double *x = LEFT ? X + c * ldx : X + c;
+    double *y = LEFT ? Y + c * ldy : Y + c;
+    const int64_t xs = LEFT ? 1 : ldx, ys = LEFT ? 1 : ldy;
+    const double h = wf_h(w, k);
+    const double x0 = x[(int64_t)k * xs];
+    const double x1 = N >= 2 ? x[((int64_t)m + k) * xs] : 0.0;
+    // hats: node nd carries hat nd (C1) or nd-1 (Dirichlet, interior nodes only)
+    const int hoff = w.basis == POP_BASIS_C1 ? 0 : -1;
+    {
+        const int nd = k, hi = nd + hoff;
+        if (hi >= 0 && hi < w.nh) {
+            double acc = 0.5 * h * x0 - 0.5 * (h / 3) * x1;               // left node of element k: (P_0 - P_1)/2
+            if (k >= 1) {
+                const double hl = wf_h(w, k - 1);
+                acc += 0.5 * hl * x[(int64_t)(k - 1) * xs];               // right node of element k-1: (P_0 + P_1)/2
+                if (N >= 2) acc += 0.5 * (hl / 3) * x[((int64_t)m + k - 1) * xs];
             }
-            if (nd < m) {
-                const int k = nd;
-                const double h = wf_h(w, k);
-                acc += 0.5 * h * x[(int64_t)k * xs];
-                if (N >= 2) acc -= 0.5 * (h / 3) * x[((int64_t)m + k) * xs];
-            }
-        } else {
-            const int64_t b = r - w.nh;
-            const int j = (int)(b / m) + 1, k = (int)(b % m);
-            const double h = wf_h(w, k), v = 1.0 / (2 * j + 1);
-            acc = (h / (2 * j - 1)) * x[((int64_t)(j - 1) * m + k) * xs];
-            if (j + 1 <= N - 1) acc -= (h / (2 * j + 3)) * x[((int64_t)(j + 1) * m + k) * xs];
-            acc *= v;
+            y[(int64_t)hi * ys] = acc;
         }
-        if (LEFT) Y[c * ldy + r] = acc;
-        else Y[r * ldy + c] = acc;
+    }
+    if (k == m - 1) {
+        const int hi = m + hoff;
+        if (hi >= 0 && hi < w.nh) y[(int64_t)hi * ys] = 0.5 * h * x0 + 0.5 * (h / 3) * x1;
+    }
+    // bubbles: y(j,k) = v_j [ g(j-1,k) x(j-1,k) - g(j+1,k) x(j+1,k) ],  g(a,k) = h/(2a+1),  v_j = 1/(2j+1)
+    double xa = x0, xb = x1;
+    const double *xp = x + ((int64_t)2 * m + k) * xs;
+    double *yp = y + ((int64_t)w.nh + k) * ys;
+    const int64_t xstep = (int64_t)m * xs, ystep = (int64_t)m * ys;
+    int j = 1;
+    for (; j + 4 <= q && j + 4 <= N - 2; j += 4) {       // four degrees per trip: the loads are issued together
+        double xn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xn[u] = xp[u * xstep];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j + u;
+            const double v = 1.0 / (2 * jj + 1);
+            yp[u * ystep] = v * ((h / (2 * jj - 1)) * xa - (h / (2 * jj + 3)) * xn[u]);
+            xa = xb;
+            xb = xn[u];
+        }
+        xp += 4 * xstep;
+        yp += 4 * ystep;
+    }
+    for (; j <= q; ++j) {
+        const double xc = j + 1 <= N - 1 ? *xp : 0.0;
+        const double v = 1.0 / (2 * j + 1);
+        *yp = v * ((h / (2 * j - 1)) * xa - (h / (2 * j + 3)) * xc);
+        xa = xb;
+        xb = xc;
+        xp += xstep;
+        yp += ystep;
     }
 }
 
@@ -91,10 +117,12 @@ extern "C" int pop_weakform_apply(pop_ctx *ctx, int basis, int m, int N, double 
     }
     const dim3 blk(32, 8);
     if (side == POP_LEFT) {
-        const dim3 grd((unsigned)((n + 31) / 32), (unsigned)std::min<int64_t>((cnt + 7) / 8, 16384));
+        POP_REQUIRE((cnt + 7) / 8 <= 65535, POP_ERR_DIM, "pop_weakform_apply: at most 524280 columns per call");
+        const dim3 grd((unsigned)((m + 31) / 32), (unsigned)((cnt + 7) / 8));
         k_weakform<true><<<grd, blk, 0, ctx->stream>>>(w, dX, ldx, dY, ldy, cnt);
     } else {
-        const dim3 grd((unsigned)((cnt + 31) / 32), (unsigned)std::min<int64_t>((n + 7) / 8, 16384));
+        POP_REQUIRE((m + 7) / 8 <= 65535, POP_ERR_DIM, "pop_weakform_apply: at most 524280 elements");
+        const dim3 grd((unsigned)((cnt + 31) / 32), (unsigned)((m + 7) / 8));
         k_weakform<false><<<grd, blk, 0, ctx->stream>>>(w, dX, ldx, dY, ldy, cnt);
     }
     ctx->launches++;
@@ -109,77 +137,84 @@ extern "C" int pop_weakform_apply(pop_ctx *ctx, int basis, int m, int N, double 
 #define AN_TILE 4
 // Shared memory (pp = p rounded up to 4, rows padded by 4 doubles against bank conflicts of the transposing stores):
 //   Tt[s][a] = T[a][s] ; Vt[s][t] = V[s][t] of the cell (t fastest) ; Wt[t][a] = (T V)[a][t]
-// 256 threads, each a 4x4 tile of a 64x64 product; two passes of p rank-1 updates from 128-bit shared-memory loads.
+// 256 threads, each a 4x4 tile of a 64x64 product: rows {2 ta, 2 ta + 1, 32 + 2 ta, 33 + 2 ta} (so the 16 lanes that
+// differ in ta read 16 consecutive 16-byte words: conflict-free 128-bit loads), columns 4 tb .. 4 tb + 3 (two values
+// per warp: broadcast).  Two passes of p rank-1 updates.  Persistent CTAs loop over the cells (x fastest, so the CTAs
+// that complete one 32 B sector of the interlaced output run at the same time); T is staged once per CTA.
 __global__ void __launch_bounds__(256, 2) k_analysis_2d(int n, int p, const double *__restrict__ T, const double *__restrict__ V, int64_t ldv,
                                                         double *__restrict__ F, int64_t ldf) {
     extern __shared__ __align__(16) double an_sm[];
-    const int pp = (p + 3) & ~3, ldp = pp + 4;
-    double *Tt = an_sm, *Vt = Tt + (size_t)pp * ldp, *Wt = Vt + (size_t)pp * ldp;
+    const int pp = (p + 3) & ~3, ldp = 68;   // p <= 64
+    double *Tt = an_sm, *Vt = Tt + (size_t)64 * ldp, *Wt = Vt + (size_t)64 * ldp;
     const int tid = threadIdx.x;
-    const int ci = blockIdx.x, cj = blockIdx.y;
-    // T is p x p column-major (T[a + p s]); transposed on the way in so that 4 consecutive a share a 32 B run
-    for (int e = tid; e < pp * pp; e += 256) {
-        const int a = e % pp, s = e / pp;
+    // T is p x p column-major (T[a + p s]); transposed on the way in; zero padding up to 64 x 64
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int a = e & 63, s = e >> 6;
         Tt[s * ldp + a] = (a < p && s < p) ? T[a + (size_t)p * s] : 0.0;
     }
-    // values of the cell: column t of the cell is p consecutive doubles (node s fastest)
-    const double *Vc = V + (int64_t)ci * p + (int64_t)cj * p * ldv;
-    for (int e = tid; e < pp * pp; e += 256) {
-        const int s = e % pp, t = e / pp;
-        Vt[s * ldp + t] = (s < p && t < p) ? Vc[s + (int64_t)t * ldv] : 0.0;
-    }
-    __syncthreads();
-    const int nt = pp / AN_TILE;            // tiles per dimension (<= 16)
-    const int ta = tid % 16, tb = tid / 16;
-    const bool on = ta < nt && tb < nt;
-    const int a0 = ta * AN_TILE, t0 = tb * AN_TILE;
-    double acc[AN_TILE][AN_TILE];
-#pragma unroll
-    for (int x = 0; x < AN_TILE; ++x)
-#pragma unroll
-        for (int y = 0; y < AN_TILE; ++y) acc[x][y] = 0.0;
-    if (on) {
-        // W[a][t] = sum_s T[a][s] V[s][t]
-        for (int s = 0; s < p; ++s) {
-            const double2 ta01 = *reinterpret_cast<const double2 *>(Tt + s * ldp + a0), ta23 = *reinterpret_cast<const double2 *>(Tt + s * ldp + a0 + 2);
-            const double2 vb01 = *reinterpret_cast<const double2 *>(Vt + s * ldp + t0), vb23 = *reinterpret_cast<const double2 *>(Vt + s * ldp + t0 + 2);
-            const double av[4] = {ta01.x, ta01.y, ta23.x, ta23.y}, bv[4] = {vb01.x, vb01.y, vb23.x, vb23.y};
-#pragma unroll
-            for (int x = 0; x < AN_TILE; ++x)
-#pragma unroll
-                for (int y = 0; y < AN_TILE; ++y) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
+    const int ta = tid & 15, tb = tid >> 4;
+    const int a0 = 2 * ta, a1 = 32 + 2 * ta, t0 = tb * AN_TILE;
+    const bool on = t0 < pp;
+    const int64_t ncell = (int64_t)n * n;
+    for (int64_t cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
+        const int ci = (int)(cell % n), cj = (int)(cell / n);
+        // values of the cell: column t of the cell is p consecutive doubles (node s fastest)
+        const double *Vc = V + (int64_t)ci * p + (int64_t)cj * p * ldv;
+        __syncthreads();   // the previous cell's second pass has read Vt/Wt
+        for (int e = tid; e < 64 * pp; e += 256) {
+            const int sI = e & 63, t = e >> 6;
+            Vt[sI * ldp + t] = (sI < p && t < p) ? Vc[sI + (int64_t)t * ldv] : 0.0;
         }
-#pragma unroll
-        for (int y = 0; y < AN_TILE; ++y) {
-            *reinterpret_cast<double2 *>(Wt + (t0 + y) * ldp + a0) = make_double2(acc[0][y], acc[1][y]);
-            *reinterpret_cast<double2 *>(Wt + (t0 + y) * ldp + a0 + 2) = make_double2(acc[2][y], acc[3][y]);
-        }
-    }
-    __syncthreads();
-    if (on) {
-        // C[a][b] = sum_t W[a][t] T[b][t]
-        const int b0 = t0;
+        __syncthreads();
+        double acc[AN_TILE][AN_TILE];
 #pragma unroll
         for (int x = 0; x < AN_TILE; ++x)
 #pragma unroll
             for (int y = 0; y < AN_TILE; ++y) acc[x][y] = 0.0;
-        for (int t = 0; t < p; ++t) {
-            const double2 wa01 = *reinterpret_cast<const double2 *>(Wt + t * ldp + a0), wa23 = *reinterpret_cast<const double2 *>(Wt + t * ldp + a0 + 2);
-            const double2 tb01 = *reinterpret_cast<const double2 *>(Tt + t * ldp + b0), tb23 = *reinterpret_cast<const double2 *>(Tt + t * ldp + b0 + 2);
-            const double av[4] = {wa01.x, wa01.y, wa23.x, wa23.y}, bv[4] = {tb01.x, tb01.y, tb23.x, tb23.y};
+        if (on) {
+            // W[a][t] = sum_s T[a][s] V[s][t]
+            for (int sI = 0; sI < p; ++sI) {
+                const double2 ta01 = *reinterpret_cast<const double2 *>(Tt + sI * ldp + a0), ta23 = *reinterpret_cast<const double2 *>(Tt + sI * ldp + a1);
+                const double2 vb01 = *reinterpret_cast<const double2 *>(Vt + sI * ldp + t0), vb23 = *reinterpret_cast<const double2 *>(Vt + sI * ldp + t0 + 2);
+                const double av[4] = {ta01.x, ta01.y, ta23.x, ta23.y}, bv[4] = {vb01.x, vb01.y, vb23.x, vb23.y};
+#pragma unroll
+                for (int x = 0; x < AN_TILE; ++x)
+#pragma unroll
+                    for (int y = 0; y < AN_TILE; ++y) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
+            }
+#pragma unroll
+            for (int y = 0; y < AN_TILE; ++y) {
+                *reinterpret_cast<double2 *>(Wt + (t0 + y) * ldp + a0) = make_double2(acc[0][y], acc[1][y]);
+                *reinterpret_cast<double2 *>(Wt + (t0 + y) * ldp + a1) = make_double2(acc[2][y], acc[3][y]);
+            }
+        }
+        __syncthreads();
+        if (on) {
+            // C[a][b] = sum_t W[a][t] T[b][t]
+            const int b0 = t0;
 #pragma unroll
             for (int x = 0; x < AN_TILE; ++x)
 #pragma unroll
-                for (int y = 0; y < AN_TILE; ++y) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
-        }
-        // interlaced store: degree a of cell ci at row ci + n a (neighbouring cells in x, i.e. neighbouring CTAs, complete the sector)
+                for (int y = 0; y < AN_TILE; ++y) acc[x][y] = 0.0;
+            for (int t = 0; t < p; ++t) {
+                const double2 wa01 = *reinterpret_cast<const double2 *>(Wt + t * ldp + a0), wa23 = *reinterpret_cast<const double2 *>(Wt + t * ldp + a1);
+                const double2 tb01 = *reinterpret_cast<const double2 *>(Tt + t * ldp + b0), tb23 = *reinterpret_cast<const double2 *>(Tt + t * ldp + b0 + 2);
+                const double av[4] = {wa01.x, wa01.y, wa23.x, wa23.y}, bv[4] = {tb01.x, tb01.y, tb23.x, tb23.y};
 #pragma unroll
-        for (int y = 0; y < AN_TILE; ++y)
+                for (int x = 0; x < AN_TILE; ++x)
 #pragma unroll
-            for (int x = 0; x < AN_TILE; ++x) {
-                const int a = a0 + x, b = b0 + y;
-                if (a < p && b < p) F[(int64_t)ci + (int64_t)n * a + ((int64_t)cj + (int64_t)n * b) * ldf] = acc[x][y];
+                    for (int y = 0; y < AN_TILE; ++y) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
             }
+            // interlaced store: degree a of cell ci at row ci + n a
+            double *Fc = F + (int64_t)ci + (int64_t)cj * ldf;
+#pragma unroll
+            for (int y = 0; y < AN_TILE; ++y)
+#pragma unroll
+                for (int x = 0; x < AN_TILE; ++x) {
+                    const int a = (x < 2 ? a0 : a1 - 2) + x, b = b0 + y;
+                    if (a < p && b < p) Fc[(int64_t)n * a + (int64_t)n * b * ldf] = acc[x][y];
+                }
+        }
     }
 }
 
@@ -189,15 +224,15 @@ extern "C" int pop_legendre_analysis_2d(pop_ctx *ctx, int n, int p, const double
     POP_REQUIRE(p <= 64, POP_ERR_DIM, "pop_legendre_analysis_2d: p = %d nodes per cell: the per-cell kernel holds p <= 64", p);
     const int64_t np = (int64_t)n * p;
     POP_REQUIRE(ldv >= np && ldf >= np, POP_ERR_DIM, "pop_legendre_analysis_2d: DimensionMismatch: panels need %lld rows", (long long)np);
-    POP_REQUIRE(n <= 65535, POP_ERR_DIM, "pop_legendre_analysis_2d: at most 65535 cells per dimension");
     double *dT = nullptr;
     int rc = pop_ctx_scratch(ctx, (size_t)p * p * sizeof(double), (void **)&dT);
     if (rc) return rc;
     POP_CUDA(cudaMemcpyAsync(dT, T_host, (size_t)p * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    const int pp = (p + 3) & ~3;
-    const size_t smem = (size_t)3 * pp * (pp + 4) * sizeof(double);
+    const size_t smem = (size_t)3 * 64 * 68 * sizeof(double);
     POP_CUDA(cudaFuncSetAttribute(k_analysis_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_analysis_2d<<<dim3((unsigned)n, (unsigned)n), 256, smem, ctx->stream>>>(n, p, dT, dV, ldv, dF, ldf);
+    const int64_t ncell = (int64_t)n * n;
+    const unsigned grid = (unsigned)std::min<int64_t>(ncell, (int64_t)2 * ctx->sm_count);
+    k_analysis_2d<<<grid, 256, smem, ctx->stream>>>(n, p, dT, dV, ldv, dF, ldf);
     ctx->launches++;
     POP_CUDA(cudaGetLastError());
     POP_CUDA(cudaStreamSynchronize(ctx->stream));   // T_host and the scratch copy may be reused at once
