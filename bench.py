@@ -317,6 +317,48 @@ def heat_case(P, torch, dist, rank, world, dev):
             "note": "32 B/entry/step = two fused solve+product passes; 2 distributed transposes per call"}
 
 
+def rhs_case(P, torch, dev):
+    """The callers' side of config 4 (examples/adi_poisson.jl:60-76,105): per-cell Legendre analysis of 8192 x 8192 values
+    (n = 128 cells, p = 64 nodes per cell and dimension), the weak form F = (Q'P) fp (Q'P)' and the row solve X / F."""
+    n, p = 128, 64
+    N = n * p
+    z, T = P.legendre_grid_transform(p)
+    g = torch.Generator(device=dev).manual_seed(7)
+    vals = torch.randn((N, N), generator=g, dtype=torch.float64, device=dev).t()
+    Q = P.DirichletPolynomial(np.linspace(-1, 1, n + 1))
+    KR = P.Block.oneto(p)
+    nq = Q.nh + Q.m * (p - 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        ts = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return float(np.median(ts[1:])), out
+
+    peak, _ = measured_peak()
+    ta, fp = timed(lambda: P.analysis_2d(vals, n, p, T))
+    tl, Z = timed(lambda: P.weakform_apply(Q, KR, fp, P.LEFT))
+    tr, F = timed(lambda: P.weakform_apply(Q, KR, Z, P.RIGHT))
+    del vals, fp, Z
+    Fs = P.reversecholesky(-P.weaklaplacian(Q)[KR, KR])
+    td, _ = timed(lambda: P.rdiv(F, Fs, overwrite=True))
+    gl, gr, gd = 8.0 * (N + nq) * N / tl / 1e9, 8.0 * (N + nq) * nq / tr / 1e9, 16.0 * nq * nq / td / 1e9
+    return {"workload": "right-hand side of BASELINE config 4 (examples/adi_poisson.jl:60-76,105,111): analysis_2D of 8192x8192 values, "
+                        "(Q'P) fp (Q'P)', X / reversecholesky(Delta)",
+            "analysis_2d": {"kernel": "k_analysis_2d (per-cell T V T', FP64 FMA)", "ms": ta * 1e3, "tflops_fp64": 4.0 * p * N * N / ta / 1e12,
+                            "bound": "fp64 pipe (4 p flop per value against 16 B)", "algorithmic_gbs": 16.0 * N * N / ta / 1e9},
+            "weakform_left": {"kernel": "k_weakform<true>", "ms": tl * 1e3, "achieved_gbs": gl, "frac_of_measured_hbm_peak": gl / peak},
+            "weakform_right": {"kernel": "k_weakform<false>", "ms": tr * 1e3, "achieved_gbs": gr, "frac_of_measured_hbm_peak": gr / peak},
+            "row_solve": {"kernel": "k_row1 (one-pass X / F, register-resident row blocks)", "ms": td * 1e3, "achieved_gbs": gd,
+                          "frac_of_measured_hbm_peak": gd / peak, "bytes_per_entry": 16}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -440,7 +482,13 @@ def main():
                "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps, "api": "pop_solve_host (ldiv(F, numpy array)), pinned host panel, chunked H2D/compute/D2H overlap"}
         del hB, hX
 
-    adi = heat = shifted = None
+    adi = heat = shifted = rhs = None
+    if not args.no_adi and rank == 0:
+        try:
+            rhs = rhs_case(P, torch, dev)
+        except Exception as ex:
+            rhs = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
     if not args.no_adi:
         try:
             adi = adi_case(P, torch, dist, rank, world, dev)
@@ -464,7 +512,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, one thread-block cluster per column)", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
-                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat, "shifted_batch": shifted}
+                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat, "shifted_batch": shifted, "rhs_pipeline": rhs}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         else:

@@ -188,6 +188,17 @@ int pop_legendre_analysis_2d(pop_ctx *ctx, int n, int p, const double *T_host, c
 int pop_weakform_apply(pop_ctx *ctx, int basis, int m, int N, double h, const double *h_elems, int side,
                        const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t cnt);
 
+/* Legendre coefficients of a continuous piecewise polynomial (P ordering, N degrees per element) -> coefficients in
+ * ContinuousPolynomial{1} / DirichletPolynomial blocks 1..N-1 (n = nh + m (N-2)): the `R \ dat` + interlacing of
+ * ContinuousPolynomialTransform (src/continuouspolynomial.jl:84-146, adaptivetransform_ldiv :186-213;
+ * src/dirichlet.jl:44-53,65-69 drops the end hats).  side LEFT: vectors are the columns of X ((m N) x cnt), RIGHT: the rows
+ * (cnt x (m N)); a 2D field takes one call per side.  max_jump (host, may be NULL) receives the largest mismatch between
+ * the values the two elements of an interior node imply (and, for DirichletPolynomial, the largest end value): the
+ * reference throws ArgumentError("Discontinuity in data ...") when it exceeds 1000 M eps (:105-107).  A non-NULL
+ * max_jump synchronises the stream. */
+int pop_legendre_to_c1(pop_ctx *ctx, int basis, int m, int N, int side, const double *dX, int64_t ldx, double *dY,
+                       int64_t ldy, int64_t cnt, double *max_jump);
+
 /* out-of-place transpose dst (cols x rows, ldd) <- src^T, src rows x cols (lds) */
 int pop_transpose(pop_ctx *ctx, const double *dsrc, int64_t lds, int64_t rows, int64_t cols,
                   double *ddst, int64_t ldd);
@@ -207,6 +218,11 @@ int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M
  * dims = 2: n x n field, U <- S^{-1} (M U M) S^{-1} (factored 2D extension). */
 int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt,
                    int nsteps, int dims, double *dU, int64_t ldu, int64_t nrhs);
+
+/* theta scheme (M + theta dt K) u' = (M - (1-theta) dt K) u with one reused factorisation: theta = 1 is pop_heat_steps,
+ * theta = 1/2 the trapezoid rule `A \ (B * u)`, A = M - h/2 Delta, B = M + h/2 Delta of examples/heat.jl:26-45. */
+int pop_heat_steps_theta(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt, double theta,
+                         int nsteps, int dims, double *dU, int64_t ldu, int64_t nrhs);
 
 /* ---- multi-GPU 2D drivers: one process per GPU, X distributed by column blocks ------------------
  * The x<->y switch between the row and column sweeps of examples/adi_poisson.jl:53-56 is a distributed

@@ -991,6 +991,28 @@ def weakform_rhs(basis: int, m: int, N: int, h, fp: np.ndarray) -> np.ndarray:
     return A @ fp @ A.T
 
 
+def c1_from_legendre(basis: int, m: int, N: int, Y: np.ndarray) -> np.ndarray:
+    """Coefficients in ContinuousPolynomial{1} / DirichletPolynomial blocks 1..N-1 of the continuous piecewise
+    polynomial whose Legendre coefficients (N degrees per element, P ordering) are the columns of Y: the
+    `Pl.R \\ dat` + interlacing of ContinuousPolynomialTransform (src/continuouspolynomial.jl:84-146,186-213).
+    Restated as the least-squares solution with the truncated conversion P \\ C (exact for data in its range), which
+    is independent of the back-substitution the CUDA kernel uses."""
+    R = lowering_dense(basis, m, N)
+    nh = m + 1 if basis == C1 else m - 1
+    R = R[:, :nh + m * (N - 2)]                 # W_N needs Legendre degree N: not representable with N degrees
+    return np.linalg.lstsq(R, np.asarray(Y, dtype=np.float64), rcond=None)[0]
+
+
+def heat_theta_dense(Md, Kd, u0, dt, theta, nsteps):
+    """u <- (M + theta dt K)^-1 (M - (1-theta) dt K) u, nsteps times (examples/heat.jl:26-45 for theta = 1/2, :58-63 for 1)."""
+    A = Md + theta * dt * Kd
+    B = Md - (1 - theta) * dt * Kd
+    u = np.array(u0, dtype=np.float64)
+    for _ in range(nsteps):
+        u = np.linalg.solve(A, B @ u)
+    return u
+
+
 def basis_eval_matrix(basis: int, points: np.ndarray, N: int, x: np.ndarray) -> np.ndarray:
     """Q[x, KR] / C[x, KR]: values of the basis functions (columns, arrowhead order) at the points x."""
     m = len(points) - 1

@@ -105,11 +105,13 @@ _PROTOS = {
     "pop_adi_poisson_dd": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "pop_legendre_analysis_2d": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, i64]),
     "pop_weakform_apply": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, C.c_int, vp, i64, vp, i64, i64]),
+    "pop_legendre_to_c1": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, i64, vp, i64, i64, vp]),
     "pop_transpose": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
     "pop_adi_num_iterations": (C.c_int, [C.c_double] * 5),
     "pop_adi_shifts": (C.c_int, [C.c_int] + [C.c_double] * 4 + [vp, vp]),
     "pop_adi_poisson": (C.c_int, [vp, vp, vp, vp, i64, vp, i64] + [C.c_double] * 5 + [C.c_int]),
     "pop_heat_steps": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.c_int, vp, i64, i64]),
+    "pop_heat_steps_theta": (C.c_int, [vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, i64, i64]),
 }
 EXPORTED = tuple(_PROTOS)
 

@@ -328,28 +328,42 @@ extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_a
 // ------------------------------------------------------------------------------------
 extern "C" int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt, int nsteps, int dims, double *dU,
                               int64_t ldu, int64_t nrhs) {
+    return pop_heat_steps_theta(ctx, K, M, dt, 1.0, nsteps, dims, dU, ldu, nrhs);
+}
+
+// theta scheme: (M + theta dt K) u_{k+1} = (M - (1-theta) dt K) u_k ; theta = 1: backward Euler (examples/heat.jl:58-63),
+// theta = 1/2: the trapezoid rule A \ (B u), A = M - h/2 Delta, B = M + h/2 Delta (examples/heat.jl:26-45)
+extern "C" int pop_heat_steps_theta(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt, double theta, int nsteps, int dims,
+                                    double *dU, int64_t ldu, int64_t nrhs) {
     POP_REQUIRE(ctx && K && M && dU, POP_ERR_ARG, "pop_heat_steps: null argument");
     POP_REQUIRE(dims == 1 || dims == 2, POP_ERR_ARG, "pop_heat_steps: dims must be 1 or 2");
     POP_REQUIRE(nsteps >= 0 && dt > 0, POP_ERR_ARG, "pop_heat_steps: need nsteps >= 0, dt > 0");
+    POP_REQUIRE(theta > 0 && theta <= 1, POP_ERR_ARG, "pop_heat_steps: theta must lie in (0, 1]");
     const int64_t n = K->n();
     if (dims == 2) nrhs = n;
     POP_REQUIRE(ldu >= n && nrhs >= 0, POP_ERR_DIM, "pop_heat_steps: DimensionMismatch");
     if (nsteps == 0 || nrhs == 0) return POP_OK;
-    pop_arrowhead *U = nullptr;
-    double one = 1.0;
-    int rc = pop_revchol_shifted_batch(ctx, M, K, &one, &dt, 1, &U, nullptr);   // S = M + dt*K
+    pop_arrowhead *U = nullptr, *Tm = nullptr;
+    double one = 1.0, sdt = theta * dt;
+    int rc = pop_revchol_shifted_batch(ctx, M, K, &one, &sdt, 1, &U, nullptr);   // S = M + theta*dt*K
     if (rc) return rc;
+    const pop_arrowhead *Top = M;                                                // right-hand-side operator M - (1-theta)*dt*K
+    if (theta < 1.0) {
+        rc = pop_axpby(ctx, 1.0, M, -(1.0 - theta) * dt, K, &Tm);
+        if (rc) { pop_arrowhead_free(ctx, U); return rc; }
+        Top = Tm;
+    }
     const int64_t ld = (n + 1) & ~(int64_t)1;
     double *buf = nullptr;
     cudaError_t e = cudaMalloc(&buf, (size_t)ld * nrhs * sizeof(double));
-    if (e != cudaSuccess) { pop_arrowhead_free(ctx, U); pop_set_error("pop_heat_steps: workspace: %s", cudaGetErrorString(e)); return POP_ERR_ALLOC; }
+    if (e != cudaSuccess) { pop_arrowhead_free(ctx, U); pop_arrowhead_free(ctx, Tm); pop_set_error("pop_heat_steps: workspace: %s", cudaGetErrorString(e)); return POP_ERR_ALLOC; }
     MulView mv;
-    pop_make_mulview(M, POP_SYM_UPPER, 0, &mv);
+    pop_make_mulview(Top, POP_SYM_UPPER, 0, &mv);
     do {
         if (dims == 1) {
             // v = M u;  (nsteps-1) x  v <- M (S^{-1} v)  in one pass each;  u = S^{-1} v
             if ((rc = pop_launch_mul(ctx, mv, 1.0, dU, 1, ldu, 0.0, buf, 1, ld, nrhs))) break;
-            for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, M, 0.0, buf, ld, buf, ld, nrhs);
+            for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, Top, 0.0, buf, ld, buf, ld, nrhs);
             if (rc) break;
             if ((rc = pop_solve(ctx, U, POP_LEFT, buf, ld, nrhs, POP_SOLVE_AUTO))) break;
             e = cudaMemcpy2DAsync(dU, ldu * 8, buf, ld * 8, n * 8, nrhs, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -363,7 +377,7 @@ extern "C" int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_ar
             double *oth = buf; int64_t ldo = ld;
             for (int pass = 0; pass < 2 && rc == POP_OK; ++pass) {
                 if ((rc = pop_launch_mul(ctx, mv, 1.0, cur, 1, ldc, 0.0, oth, 1, ldo, n))) break;
-                for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, M, 0.0, oth, ldo, oth, ldo, n);
+                for (int s = 0; s + 1 < nsteps && rc == POP_OK; ++s) rc = pop_solve_mul_axpy(ctx, U, Top, 0.0, oth, ldo, oth, ldo, n);
                 if (rc) break;
                 if ((rc = pop_solve(ctx, U, POP_LEFT, oth, ldo, n, POP_SOLVE_AUTO))) break;
                 if ((rc = pop_transpose(ctx, oth, ldo, n, n, cur, ldc))) break;
@@ -373,5 +387,6 @@ extern "C" int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_ar
     cudaStreamSynchronize(ctx->stream);
     cudaFree(buf);
     pop_arrowhead_free(ctx, U);
+    pop_arrowhead_free(ctx, Tm);
     return rc;
 }

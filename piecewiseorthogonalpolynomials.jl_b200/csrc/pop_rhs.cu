@@ -132,6 +132,130 @@ extern "C" int pop_weakform_apply(pop_ctx *ctx, int basis, int m, int N, double 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Legendre coefficients of a continuous piecewise polynomial -> its C1 / Dirichlet coefficients: the `R \ dat`
+// + hat / bubble interlacing of ContinuousPolynomialTransform (src/continuouspolynomial.jl:84-146) and
+// adaptivetransform_ldiv (:186-213); DirichletPolynomial drops the end hats (src/dirichlet.jl:44-53,65-69).
+// Per element, from the top degree down (W_{j+1} = (P_{j-1} - P_{j+1})/(2j+1) is the only bubble with degree j+1):
+//   b_j = (2a-1) ( b_{j+2}/(2a+3) - y_a ),  a = j+1 = N-1 .. 2 ;   t0 = y_0 - b_1/3,  t1 = y_1 - b_2/5
+//   hat on the left node = t0 - t1, on the right node = t0 + t1
+// Node 0 takes the left value of element 0, node k+1 the right value of element k (:103-111); the left values go to
+// `ul` so that the caller can check continuity like the reference does (:105-107).
+// ---------------------------------------------------------------------------------------------------
+template <bool LEFT>
+__global__ void __launch_bounds__(256) k_legendre_to_c1(WeakOp w, const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int64_t cnt,
+                                                        double *__restrict__ ul) {
+    const int m = w.m, N = w.N, q = w.q;   // q = N - 2 bubbles per element
+    const int64_t ix = (int64_t)blockIdx.x * 32 + threadIdx.x, iy = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    const int64_t kk = LEFT ? ix : iy, c = LEFT ? iy : ix;
+    if (kk >= m || c >= cnt) return;
+    const int k = (int)kk;
+    const double *x = LEFT ? X + c * ldx : X + c;
+    double *y = LEFT ? Y + c * ldy : Y + c;
+    const int64_t xs = LEFT ? 1 : ldx, ys = LEFT ? 1 : ldy;
+    const int64_t xstep = (int64_t)m * xs, ystep = (int64_t)m * ys;
+    double b1 = 0.0, b2 = 0.0;                   // b_{j+1}, b_{j+2}
+    const double *xp = x + ((int64_t)(N - 1) * m + k) * xs;
+    double *yp = y + ((int64_t)w.nh + (int64_t)(q - 1) * m + k) * ys;
+    int a = N - 1;
+    for (; a - 3 >= 2; a -= 4) {                 // four degrees per trip: the loads are issued together
+        double yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) yv[u] = xp[-u * xstep];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int aa = a - u;
+            const double bj = (2 * aa - 1) * (b2 / (2 * aa + 3) - yv[u]);
+            yp[-u * ystep] = bj;
+            b2 = b1;
+            b1 = bj;
+        }
+        xp -= 4 * xstep;
+        yp -= 4 * ystep;
+    }
+    for (; a >= 2; --a) {
+        const double bj = (2 * a - 1) * (b2 / (2 * a + 3) - *xp);
+        *yp = bj;
+        b2 = b1;
+        b1 = bj;
+        xp -= xstep;
+        yp -= ystep;
+    }
+    // now b1 = b_1 (if q >= 1), b2 = b_2 (if q >= 2)
+    const double t0 = x[(int64_t)k * xs] - b1 / 3, t1 = x[((int64_t)m + k) * xs] - b2 / 5;
+    const double uL = t0 - t1, uR = t0 + t1;
+    const int hoff = w.basis == POP_BASIS_C1 ? 0 : -1;
+    if (k == 0 && hoff == 0) y[0] = uL;
+    const int hi = k + 1 + hoff;
+    if (hi >= 0 && hi < w.nh) y[(int64_t)hi * ys] = uR;
+    if (ul) ul[c * (int64_t)(m + 1) + k] = uL;
+    if (ul && k == m - 1) ul[c * (int64_t)(m + 1) + m] = uR;     // the right end (a Dirichlet basis expects zero there)
+}
+
+// largest |right value of element k-1 - left value of element k| (and, for the Dirichlet basis, |end values|)
+__global__ void k_c1_jump(WeakOp w, const double *__restrict__ Y, int64_t ldy, int64_t cnt, bool left, const double *__restrict__ ul,
+                          unsigned long long *__restrict__ out) {
+    const int m = w.m;
+    double worst = 0.0;
+    const int64_t total = cnt * (int64_t)(m + 1);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e / (m + 1);
+        const int nd = (int)(e % (m + 1));
+        const double v = ul[e];
+        const int hi = nd + (w.basis == POP_BASIS_C1 ? 0 : -1);
+        double d;
+        if (hi >= 0 && hi < w.nh && nd >= 1 && nd < m) d = fabs((left ? Y[c * ldy + hi] : Y[(int64_t)hi * ldy + c]) - v);
+        else d = (w.basis == POP_BASIS_C1) ? 0.0 : fabs(v);
+        worst = fmax(worst, d);
+    }
+    for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like integers
+}
+
+extern "C" int pop_legendre_to_c1(pop_ctx *ctx, int basis, int m, int N, int side, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t cnt,
+                                  double *max_jump) {
+    POP_REQUIRE(ctx && dX && dY, POP_ERR_ARG, "pop_legendre_to_c1: null argument");
+    POP_REQUIRE(basis == POP_BASIS_C1 || basis == POP_BASIS_DIRICHLET, POP_ERR_ARG, "pop_legendre_to_c1: unknown basis %d", basis);
+    POP_REQUIRE(side == POP_LEFT || side == POP_RIGHT, POP_ERR_ARG, "pop_legendre_to_c1: bad side");
+    const int nh = basis == POP_BASIS_C1 ? m + 1 : m - 1;
+    POP_REQUIRE(m >= 1 && nh >= 1 && N >= 2, POP_ERR_DIM, "pop_legendre_to_c1: need m >= 1 elements with hats and N >= 2 Legendre degrees per element");
+    const int64_t n = (int64_t)nh + (int64_t)m * (N - 2), np = (int64_t)m * N;
+    POP_REQUIRE(cnt >= 0, POP_ERR_DIM, "pop_legendre_to_c1: negative count");
+    if (side == POP_LEFT) POP_REQUIRE(ldx >= np && ldy >= n, POP_ERR_DIM, "pop_legendre_to_c1: DimensionMismatch: X needs %lld rows, Y %lld", (long long)np, (long long)n);
+    else POP_REQUIRE(ldx >= std::max<int64_t>(cnt, 1) && ldy >= std::max<int64_t>(cnt, 1), POP_ERR_DIM, "pop_legendre_to_c1: leading dimensions smaller than the row count");
+    if (max_jump) *max_jump = 0.0;
+    if (cnt == 0) return POP_OK;
+    WeakOp w = {basis, m, N, nh, N - 2, 1.0, nullptr};
+    double *ul = nullptr;
+    unsigned long long *dmax = nullptr;
+    if (max_jump) {
+        cudaError_t e = cudaMallocAsync((void **)&ul, ((size_t)cnt * (m + 1) + 1) * sizeof(double), ctx->stream);
+        if (e != cudaSuccess) { pop_set_error("pop_legendre_to_c1: scratch: %s", cudaGetErrorString(e)); return POP_ERR_ALLOC; }
+        dmax = (unsigned long long *)(ul + (size_t)cnt * (m + 1));
+        POP_CUDA(cudaMemsetAsync(dmax, 0, sizeof(double), ctx->stream));
+    }
+    const dim3 blk(32, 8);
+    if (side == POP_LEFT) {
+        POP_REQUIRE((cnt + 7) / 8 <= 65535, POP_ERR_DIM, "pop_legendre_to_c1: at most 524280 columns per call");
+        k_legendre_to_c1<true><<<dim3((unsigned)((m + 31) / 32), (unsigned)((cnt + 7) / 8)), blk, 0, ctx->stream>>>(w, dX, ldx, dY, ldy, cnt, ul);
+    } else {
+        POP_REQUIRE((m + 7) / 8 <= 65535, POP_ERR_DIM, "pop_legendre_to_c1: at most 524280 elements");
+        k_legendre_to_c1<false><<<dim3((unsigned)((cnt + 31) / 32), (unsigned)((m + 7) / 8)), blk, 0, ctx->stream>>>(w, dX, ldx, dY, ldy, cnt, ul);
+    }
+    ctx->launches++;
+    POP_CUDA(cudaGetLastError());
+    if (max_jump) {
+        const int64_t total = cnt * (int64_t)(m + 1);
+        k_c1_jump<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1184), 256, 0, ctx->stream>>>(w, dY, ldy, cnt, side == POP_LEFT, ul, dmax);
+        ctx->launches++;
+        POP_CUDA(cudaGetLastError());
+        POP_CUDA(cudaMemcpyAsync(max_jump, dmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        POP_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFreeAsync(ul, ctx->stream);
+    }
+    return POP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // per-cell tensor Legendre analysis  C = T V T^T
 // ---------------------------------------------------------------------------------------------------
 #define AN_TILE 4

@@ -58,14 +58,15 @@ def adi_poisson(M, K, F, a, b, c=None, d=None, tol=1e-15, J=0):
     return X
 
 
-def heat_steps(M, K, U, dt, nsteps, dims=1):
-    """In place: nsteps of backward Euler with one factorisation of M + dt*K (K = -Delta)."""
+def heat_steps(M, K, U, dt, nsteps, dims=1, theta=1.0):
+    """In place: nsteps of the theta scheme (M + theta dt K) u' = (M - (1-theta) dt K) u with one factorisation (K = -Delta):
+    theta = 1 backward Euler (examples/heat.jl:58-63), theta = 1/2 the trapezoid rule (examples/heat.jl:26-45)."""
     Mb, Kb = _base(M), _base(K)
     p = _Panel(U, True)
     if not p.torch:
         raise TypeError("heat_steps works on device-resident (CUDA torch) fields")
     _bind_stream(Mb.ctx)
-    L.check(L.lib().pop_heat_steps(Mb.ctx.handle, Kb._h, Mb._h, float(dt), int(nsteps), int(dims), p.ptr, p.ld, p.cols), "heat")
+    L.check(L.lib().pop_heat_steps_theta(Mb.ctx.handle, Kb._h, Mb._h, float(dt), float(theta), int(nsteps), int(dims), p.ptr, p.ld, p.cols), "heat")
     return U
 
 

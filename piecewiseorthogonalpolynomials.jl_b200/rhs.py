@@ -82,3 +82,52 @@ def weakform_apply(Q: _Basis, KR: BlockRange, X, side=L.LEFT, ctx=None):
 def weakform_rhs(Q: _Basis, KR: BlockRange, fp, ctx=None):
     """F = (Q'P)[KR,KR] * fp * (Q'P)[KR,KR]'  (examples/adi_poisson.jl:105)."""
     return weakform_apply(Q, KR, weakform_apply(Q, KR, fp, L.LEFT, ctx), L.RIGHT, ctx)
+
+
+class DiscontinuityError(ValueError):
+    """ArgumentError("Discontinuity in data on order of ...") of src/continuouspolynomial.jl:105-107."""
+
+
+def legendre_to_c1(Q: _Basis, N: int, X, side=L.LEFT, check=True, ctx=None):
+    """Legendre coefficients (N degrees per element, P ordering; columns of X for side LEFT, rows for RIGHT) of a continuous
+    piecewise polynomial -> coefficients in Q's blocks 1..N-1: the `R \\ dat` + interlacing step of
+    ContinuousPolynomialTransform (src/continuouspolynomial.jl:84-146).  `check` reproduces the reference's continuity test."""
+    px = _Panel(X, False)
+    if not px.torch:
+        raise TypeError("legendre_to_c1 works on device-resident (CUDA torch) panels")
+    nP, n = Q.m * N, Q.nh + Q.m * (N - 2)
+    if (px.rows if side == L.LEFT else px.cols) != nP:
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: {N} Legendre degrees on {Q.m} elements are {nP} entries, panel is {px.rows}x{px.cols}")
+    cnt = px.cols if side == L.LEFT else px.rows
+    Y = _new_like(X, (n, cnt) if side == L.LEFT else (cnt, n))
+    py = _Panel(Y, True)
+    ctx = ctx or L.default_context()
+    _bind_stream(ctx)
+    jump = C.c_double(0.0)
+    L.check(L.lib().pop_legendre_to_c1(ctx.handle, Q.basis_id, Q.m, int(N), side, px.ptr, px.ld, py.ptr, py.ld, cnt,
+                                       C.byref(jump) if check else None), "transform")
+    if check:
+        scale = max(1.0, float(X.abs().max()))
+        if jump.value > 1000 * N * np.finfo(float).eps * scale:
+            raise DiscontinuityError(f"Discontinuity in data on order of {jump.value}.")
+    return Y
+
+
+def transform_2d(Q: _Basis, vals, p: int, T, check=True, ctx=None):
+    """plan_grid_transform(Q, Block(p-1, p-1)) * vals (src/continuouspolynomial.jl:148-160, test_continuouspolynomial.jl:29-33):
+    values on the p x p tensor grid of every cell -> coefficients in Q (x) Q, blocks 1..p-1 per dimension."""
+    fp = analysis_2d(vals, Q.m, p, T, ctx)
+    return legendre_to_c1(Q, p, legendre_to_c1(Q, p, fp, L.LEFT, check, ctx), L.RIGHT, check, ctx)
+
+
+def transform(Q: _Basis, f, p: int, kind="gauss", check=True, ctx=None):
+    """transform(Q, f)[Block.(1:p-1)] for a function of one variable (examples/heat.jl:41-47): f on the p nodes of every
+    cell, Legendre analysis per cell (O(m p^2), host), then the device conversion.  Returns a CUDA vector."""
+    import torch
+    z, T = legendre_grid_transform(p, kind)
+    x = cell_grid(Q.points, z)
+    vals = np.asarray([f(t) for t in x], dtype=np.float64).reshape(Q.m, p)           # [cell, node]
+    leg = (vals @ T.T).T.reshape(-1)                                                 # degree a of cell k at a*m + k
+    ctx = ctx or L.default_context()
+    dev = torch.from_numpy(np.ascontiguousarray(leg)).to(f"cuda:{ctx.device}")
+    return legendre_to_c1(Q, p, dev.reshape(-1, 1), L.LEFT, check, ctx)[:, 0]

@@ -77,6 +77,22 @@ def test_adi_poisson_example_end_to_end_oracle():
     assert np.abs(Ua - u(pts[:, None], pts[None, :])).max() < 1e-10
 
 
+def test_transform_reproduces_the_function_oracle():
+    # test_continuouspolynomial.jl:21-27: C[0.1,Block.(1:10)]' * (F * exp.(g)) ≈ exp(0.1) on r = range(-1,1;length=10)
+    r = np.linspace(-1, 1, 10)
+    m, N = 9, 11                                  # Block(10) of C <-> 11 Legendre degrees per element
+    z, T = O.legendre_grid_transform(N)
+    x = ((r[:-1] + r[1:])[:, None] / 2 + np.diff(r)[:, None] / 2 * z[None, :])
+    leg = (np.exp(x) @ T.T).T.reshape(-1)         # degree a of cell k at a*m + k
+    c = O.c1_from_legendre(O.C1, m, N, leg[:, None])[:, 0]
+    assert c.size == 91                           # transform(C,exp)[1:91]
+    assert abs(O.c1_evaluate(c, r, N - 1, 0.1) - np.exp(0.1)) < 1e-13
+    # round trip F \ (F * vals) ≈ vals: converting back with P\C and synthesising on the grid
+    R = O.lowering_dense(O.C1, m, N)[:, :c.size]
+    back = (R @ c).reshape(N, m)
+    assert np.abs(np.polynomial.legendre.legvander(z, N - 1) @ back - np.exp(x).T).max() < 1e-13
+
+
 # ------------------------------------------------------------------------------------------------ CUDA kernels
 def _gpu():
     import torch
@@ -161,3 +177,71 @@ def test_adi_poisson_example_end_to_end_gpu():
     E = O.basis_eval_matrix(O.DIRICHLET, r, p, pts)
     Ua = E @ Y.cpu().numpy() @ E.T
     assert np.abs(Ua - u(pts[:, None], pts[None, :])).max() < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis", ["c1", "dirichlet"])
+@pytest.mark.parametrize("m,N", [(2, 2), (3, 3), (4, 7), (9, 11), (33, 40)])
+def test_legendre_to_c1_kernel_vs_oracle(basis, m, N):
+    torch, P = _gpu()
+    bo = O.C1 if basis == "c1" else O.DIRICHLET
+    Q = P.ContinuousPolynomial(1, np.linspace(0, 1, m + 1)) if basis == "c1" else P.DirichletPolynomial(np.linspace(0, 1, m + 1))
+    n = Q.nh + m * (N - 2)
+    rng = np.random.default_rng(m + N)
+    c = rng.standard_normal((n, 6))
+    R = O.lowering_dense(bo, m, N)[:, :n]
+    Yl = R @ c                                    # Legendre coefficients of continuous piecewise polynomials
+    want = O.c1_from_legendre(bo, m, N, Yl)
+    assert relerr(want, c) < 1e-12
+    got = P.legendre_to_c1(Q, N, _dev(torch, Yl), P.LEFT)
+    assert relerr(got.cpu().numpy(), c) < TOL
+    gotr = P.legendre_to_c1(Q, N, _dev(torch, Yl.T.copy()), P.RIGHT)
+    assert relerr(gotr.cpu().numpy(), c.T) < TOL
+    # a jump at an interior node is reported like the reference's ArgumentError (src/continuouspolynomial.jl:105-107)
+    if m >= 2:
+        bad = Yl.copy()
+        bad[0, 0] += 0.5                           # degree 0 of element 0 only
+        with pytest.raises(P.DiscontinuityError):
+            P.legendre_to_c1(Q, N, _dev(torch, bad), P.LEFT)
+        P.legendre_to_c1(Q, N, _dev(torch, bad), P.LEFT, check=False)
+
+
+@pytest.mark.gpu
+def test_transform_and_trapezoid_heat_like_the_example():
+    """examples/heat.jl:26-47: c0 = transform(C, f)[K] for the piecewise initial condition, then 100 steps of the trapezoid
+    rule A \\ (B u), A = M - h/2 Delta, B = M + h/2 Delta, against the dense oracle; and backward Euler (:58-63)."""
+    torch, P = _gpu()
+    r = np.linspace(-1, 1, 4)
+    C1 = P.ContinuousPolynomial(1, r)
+    f = lambda x: np.exp(x + 1 / 3) if x < -1 / 3 else (9 * x * x if abs(x) <= 1 / 3 else np.exp(x - 1 / 3))
+    p = 41                                        # K = Block.(1:40)
+    c0 = P.transform(C1, f, p)
+    n = c0.numel()
+    assert n == 4 + 3 * 39
+    for xv in (-0.9, -0.2, 0.1, 0.77):
+        assert abs(O.c1_evaluate(c0.cpu().numpy(), r, p - 1, xv) - f(xv)) < 1e-12
+    KR = P.Block.oneto(p - 1)
+    M, K = P.grammatrix(C1)[KR, KR], -P.weaklaplacian(C1)[KR, KR]
+    Mo = O.assemble_mass(O.C1, 3, p - 1, 2 / 3)
+    Ko = O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.C1, 3, p - 1, 2 / 3), 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    for theta, steps in ((0.5, 100), (1.0, 100), (0.75, 7)):
+        U = c0.clone().reshape(-1, 1)
+        P.heat_steps(M, K, U, 1e-3, steps, theta=theta)
+        want = O.heat_theta_dense(Md, Kd, c0.cpu().numpy(), 1e-3, theta, steps)
+        assert relerr(U[:, 0].cpu().numpy(), want) < 1e-11, theta
+
+
+@pytest.mark.gpu
+def test_transform_2d_like_the_reference_test():
+    # test_continuouspolynomial.jl:29-33: C[0.1, Block.(1:10)]' * V * C[0.2, Block.(1:11)] ≈ exp(0.1*cos(0.2)) (square here)
+    torch, P = _gpu()
+    r = np.linspace(-1, 1, 10)
+    C1 = P.ContinuousPolynomial(1, r)
+    p = 12
+    z, T = P.legendre_grid_transform(p)
+    x = P.cell_grid(r, z)
+    vals = np.exp(x[:, None] * np.cos(x[None, :]))
+    V = P.transform_2d(C1, _dev(torch, vals), p, T).cpu().numpy()
+    E = O.basis_eval_matrix(O.C1, r, p - 1, np.array([0.1, 0.2]))
+    assert abs(E[0] @ V @ E[1] - np.exp(0.1 * np.cos(0.2))) < 1e-10
