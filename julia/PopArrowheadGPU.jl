@@ -162,4 +162,49 @@ function unpack_upper!(A::BBBArrowheadMatrix{Float64}, Ad, Au, Bp, Dp)
     A
 end
 
+
+# ---- callers' side of the ADI example (examples/adi_poisson.jl:60-76,105,111; examples/heat.jl:26-47) -------------
+# Device-resident panels are `CuArray`s or raw device pointers obtained elsewhere; the signatures below take pointers
+# and leading dimensions exactly like the header.
+
+"analysis_2D (examples/adi_poisson.jl:60-76): `T = plan * Matrix(I, p, p)` from `plan_grid_transform(legendre(0..dx), (p,p))`."
+analysis_2D_gpu(dV::Ptr{Float64}, ldv, dF::Ptr{Float64}, ldf, n::Integer, p::Integer, T::Matrix{Float64}) =
+    check(ccall((:pop_legendre_analysis_2d, libpop), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+                ctx(), n, p, T, dV, ldv, dF, ldf), "analysis_2D")
+
+basis_id(::ContinuousPolynomial{1}) = Cint(0)
+basis_id(::DirichletPolynomial) = Cint(1)
+
+"(Q'P)[KR,KR] X (side = POP_LEFT) or X (Q'P)[KR,KR]' (POP_RIGHT), examples/adi_poisson.jl:105; N = length(KR)."
+function weakform_apply_gpu(Q, N::Integer, side::Cint, dX::Ptr{Float64}, ldx, dY::Ptr{Float64}, ldy, cnt)
+    r = Q.points
+    m = length(r) - 1
+    hk = r isa AbstractRange ? C_NULL : pointer(collect(Float64, diff(r)))
+    check(ccall((:pop_weakform_apply, libpop), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64),
+                ctx(), basis_id(Q), m, N, Float64(r[2] - r[1]), hk, side, dX, ldx, dY, ldy, cnt), "weak form")
+end
+
+"Legendre coefficients -> C1 / Dirichlet coefficients (src/continuouspolynomial.jl:84-146); throws like the reference on a jump."
+function legendre_to_c1_gpu(Q, N::Integer, side::Cint, dX::Ptr{Float64}, ldx, dY::Ptr{Float64}, ldy, cnt; scale = 1.0)
+    m = length(Q.points) - 1
+    jump = Ref{Cdouble}(0.0)
+    check(ccall((:pop_legendre_to_c1, libpop), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Ref{Cdouble}),
+                ctx(), basis_id(Q), m, N, side, dX, ldx, dY, ldy, cnt, jump), "transform")
+    jump[] ≤ 1000 * N * eps() * scale || throw(ArgumentError("Discontinuity in data on order of $(jump[])."))
+end
+
+"theta scheme with one reused factorisation: theta = 1/2 is the trapezoid loop of examples/heat.jl:41-45."
+heat_steps_theta!(hK, hM, dt, theta, nsteps, dims, dU::Ptr{Float64}, ldu, nrhs) =
+    check(ccall((:pop_heat_steps_theta, libpop), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Ptr{Float64}, Int64, Int64),
+                ctx(), hK, hM, dt, theta, nsteps, dims, dU, ldu, nrhs), "heat")
+
+"grammatrix / weaklaplacian on a non-uniform grid straight on the device (one D block per element)."
+function assemble_mesh(Q, N::Integer)
+    hk = collect(Float64, diff(Q.points))
+    hm, hl = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pop_assemble_mesh, libpop), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}),
+                ctx(), basis_id(Q), length(hk), N, hk, hm, hl), "assemble")
+    hm[], hl[]
+end
+
 end # module
