@@ -61,7 +61,17 @@ extern "C" int pop_create(pop_ctx **out, int device, void *stream) {
     POP_CUDA(cudaMalloc(&ctx->d_info, 4096 * sizeof(int)));
     POP_CUDA(cudaMallocHost(&ctx->h_info, 4096 * sizeof(int)));
     for (int i = 0; i < 2; ++i) POP_CUDA(cudaStreamCreateWithFlags(&ctx->s_copy[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 12; ++i) POP_CUDA(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 32; ++i) POP_CUDA(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    {
+        // stream-ordered allocations (work panels, the host-panel mirror) stay in the pool between calls instead of going
+        // back to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return POP_OK;
 }
@@ -74,7 +84,7 @@ extern "C" int pop_destroy(pop_ctx *ctx) {
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(ctx->s_copy[i]);
-    for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 32; ++i) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return POP_OK;

@@ -26,15 +26,132 @@ __global__ void k_repitch(const double *__restrict__ src, int64_t lds, double *_
     }
 }
 
+#define POP_HOST_FLAT_NOFIT (1 << 20)
+// Contiguous host panel (n x nrhs, ldx == n): the panel crosses PCIe as FLAT blocks whose host addresses are 4 KiB
+// aligned, independent of the column boundaries (measured on this platform, tools/pcie: 48.5 GB/s each way for aligned
+// 32 MiB blocks with both directions busy, 43.3 GB/s when the host address is only 8-byte aligned, which is what column
+// chunks of an odd n give).  A device mirror of the whole panel receives the blocks; as soon as a block has landed, the
+// columns that are complete are re-pitched into the (even-pitch) work buffer, solved, re-pitched back, and every flat
+// block whose columns are all done goes home.  Copy streams and the compute stream only meet through events.
+static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, PanelOp &op, int64_t blk_bytes) {
+    const int64_t colb = n * 8, total = colb * nrhs;
+    const int64_t ldd = (n + 1) & ~(int64_t)1;
+    const int64_t A = 4096;
+    const int64_t off0 = (A - (int64_t)((uintptr_t)X % A)) % A;      // first aligned host address, relative to X
+    std::vector<int64_t> bnd;                                         // block boundaries (bytes)
+    bnd.push_back(0);
+    for (int64_t b = off0 + blk_bytes; b < total; b += blk_bytes) bnd.push_back(b);
+    bnd.push_back(total);
+    const int nblk = (int)bnd.size() - 1;
+    int64_t maxcols = 0;
+    for (int k = 0; k < nblk; ++k) maxcols = std::max(maxcols, (bnd[k + 1] - bnd[k]) / colb + 2);
+    maxcols = std::min(maxcols, nrhs);
+    char *dflat = nullptr;
+    const size_t mirror = ((size_t)total + 255) & ~(size_t)255;
+    cudaError_t e = cudaMallocAsync((void **)&dflat, mirror + (size_t)ldd * maxcols * 8, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return POP_HOST_FLAT_NOFIT;   // no room for the mirror: the caller falls back to column chunks
+    }
+    double *work = (double *)(dflat + mirror);
+    cudaEvent_t *h2d = ctx->ev, *cmp = ctx->ev + 8;
+    cudaEventRecord(ctx->ev[24], ctx->stream);                        // work queued earlier on the compute stream (and the allocation)
+    cudaStreamWaitEvent(ctx->s_copy[0], ctx->ev[24], 0);
+    cudaStreamWaitEvent(ctx->s_copy[1], ctx->ev[24], 0);
+    const bool trace = getenv("POP_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<int> tkind;
+    auto mark = [&](cudaStream_t st, int kind) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tev.push_back(ev);
+        tkind.push_back(kind);
+    };
+    mark(ctx->stream, -1);
+    int rc = POP_OK;
+    int64_t col_done = 0;      // columns [0, col_done) are solved
+    int blk_home = 0;          // flat blocks [0, blk_home) have been sent back
+    for (int k = 0; k < nblk && rc == POP_OK; ++k) {
+        mark(ctx->s_copy[0], 0);
+        e = cudaMemcpyAsync(dflat + bnd[k], (const char *)X + bnd[k], (size_t)(bnd[k + 1] - bnd[k]), cudaMemcpyHostToDevice, ctx->s_copy[0]);
+        if (e != cudaSuccess) { pop_set_error("host panel H2D: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
+        cudaEventRecord(h2d[k & 7], ctx->s_copy[0]);
+        mark(ctx->s_copy[0], 1);
+        const int64_t c_hi = k == nblk - 1 ? nrhs : bnd[k + 1] / colb;   // columns complete on the device
+        if (c_hi > col_done) {
+            cudaStreamWaitEvent(ctx->stream, h2d[k & 7], 0);
+            mark(ctx->stream, 2);
+            for (int64_t c0 = col_done; c0 < c_hi && rc == POP_OK; c0 += maxcols) {
+                const int64_t cnt = std::min(maxcols, c_hi - c0);
+                double *src = (double *)(dflat + c0 * colb);
+                k_repitch<<<592, 256, 0, ctx->stream>>>(src, n, work, ldd, n, cnt);
+                ctx->launches++;
+                rc = op.run(ctx, work, ldd, cnt);
+                if (rc) break;
+                k_repitch<<<592, 256, 0, ctx->stream>>>(work, ldd, src, n, n, cnt);
+                ctx->launches++;
+            }
+            if (rc) break;
+            col_done = c_hi;
+            cudaEventRecord(cmp[k & 7], ctx->stream);
+            mark(ctx->stream, 3);
+            // flat blocks whose bytes all belong to solved columns
+            int last = blk_home;
+            while (last < nblk && bnd[last + 1] <= col_done * colb) ++last;
+            if (last > blk_home) {
+                cudaStreamWaitEvent(ctx->s_copy[1], cmp[k & 7], 0);
+                for (int j = blk_home; j < last; ++j) {
+                    mark(ctx->s_copy[1], 4);
+                    e = cudaMemcpyAsync((char *)X + bnd[j], dflat + bnd[j], (size_t)(bnd[j + 1] - bnd[j]), cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+                    if (e != cudaSuccess) { pop_set_error("host panel D2H: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
+                    mark(ctx->s_copy[1], 5);
+                }
+                blk_home = last;
+            }
+        }
+    }
+    cudaStreamSynchronize(ctx->s_copy[0]);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaStreamSynchronize(ctx->s_copy[1]);
+    if (trace) {
+        static const char *names[] = {"H2D start", "H2D end", "compute start", "compute end", "D2H start", "D2H end"};
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float t;
+            cudaEventElapsedTime(&t, tev[0], tev[i]);
+            fprintf(stderr, "%8.3f ms  %s\n", t, names[tkind[i]]);
+        }
+        for (auto ev : tev) cudaEventDestroy(ev);
+    }
+    cudaFreeAsync(dflat, ctx->stream);
+    if (rc == POP_OK && e != cudaSuccess) { pop_set_error("host panel: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
+    return rc;
+}
+
 static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, double *X, int64_t ldx, PanelOp &op) {
     if (nrhs == 0 || n == 0) return POP_OK;
+    if (side == POP_LEFT && ldx == n) {
+        // contiguous panel: flat, address-aligned blocks through a device mirror (unless it would not fit)
+        int64_t blk = (int64_t)32 << 20;
+        if (const char *e = getenv("POP_HOST_CHUNK_MB")) blk = std::max<int64_t>(1, atoll(e)) << 20;
+        size_t free_b = 0, total_b = 0;
+        int use_flat = 1;
+        if (const char *e = getenv("POP_HOST_FLAT")) use_flat = atoi(e);
+        if (use_flat && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (size_t)n * nrhs * 8 < free_b / 2) {
+            const int rc = run_host_flat(ctx, n, nrhs, X, op, blk);
+            if (rc != POP_HOST_FLAT_NOFIT) return rc;
+        }
+        cudaGetLastError();
+    }
     // LEFT: panel = n x nrhs, chunks of columns.  RIGHT: panel = nrhs x n, chunks of rows.
     int64_t target = (int64_t)32 << 20;  // bytes per chunk (measured optimum of the H2D / compute / D2H pipeline)
     if (const char *e = getenv("POP_HOST_CHUNK_MB")) target = std::max<int64_t>(1, atoll(e)) << 20;
     int64_t per = std::max<int64_t>(1, target / (n * 8));
     if (side == POP_RIGHT) per = std::max<int64_t>(per, 32);
     per = std::min(per, nrhs);
-    const int nbuf = 3;
+    int nbuf = 3;
+    if (const char *e = getenv("POP_HOST_NBUF")) nbuf = std::min(std::max(atoi(e), 2), 8);
     const int64_t ldd = side == POP_LEFT ? ((n + 1) & ~(int64_t)1) : ((per + 1) & ~(int64_t)1);
     const size_t buf_doubles = side == POP_LEFT ? (size_t)ldd * per : (size_t)ldd * n;
     // a contiguous host panel whose pitch differs from the (even) device pitch crosses PCIe as ONE linear copy per
@@ -47,19 +164,31 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
         pop_set_error("host panel: device buffer of %zu bytes: %s", buf_doubles * nbuf * sizeof(double), cudaGetErrorString(e));
         return POP_ERR_ALLOC;
     }
-    cudaEvent_t *h2d = ctx->ev, *cmp = ctx->ev + 3, *d2h = ctx->ev + 6;
+    cudaEvent_t *h2d = ctx->ev, *cmp = ctx->ev + 8, *d2h = ctx->ev + 16;
+    // POP_HOST_TRACE=1: timed events around every copy and compute stage, printed after the call (debugging aid)
+    const bool trace = getenv("POP_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tev.push_back(ev);
+    };
+    mark(ctx->stream);
     int rc = POP_OK;
     int64_t done = 0;
     int it = 0;
     // make the copy streams wait for work already queued on the compute stream
-    cudaEventRecord(ctx->ev[9], ctx->stream);
-    cudaStreamWaitEvent(ctx->s_copy[0], ctx->ev[9], 0);
+    cudaEventRecord(ctx->ev[24], ctx->stream);
+    cudaStreamWaitEvent(ctx->s_copy[0], ctx->ev[24], 0);
     while (done < nrhs && rc == POP_OK) {
         const int64_t cnt = std::min(per, nrhs - done);
         const int b = it % nbuf;
         double *d = dbuf + (size_t)b * buf_doubles;
         double *stg = dbuf + (size_t)nbuf * buf_doubles + (size_t)b * stg_doubles;
         if (it >= nbuf) cudaStreamWaitEvent(ctx->s_copy[0], d2h[b], 0);
+        mark(ctx->s_copy[0]);
         if (linear)
             e = cudaMemcpyAsync(stg, X + done * ldx, (size_t)n * cnt * 8, cudaMemcpyHostToDevice, ctx->s_copy[0]);
         else if (side == POP_LEFT)
@@ -68,7 +197,9 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
             e = cudaMemcpy2DAsync(d, ldd * 8, X + done, ldx * 8, cnt * 8, n, cudaMemcpyHostToDevice, ctx->s_copy[0]);
         if (e != cudaSuccess) { pop_set_error("host panel H2D: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
         cudaEventRecord(h2d[b], ctx->s_copy[0]);
+        mark(ctx->s_copy[0]);
         cudaStreamWaitEvent(ctx->stream, h2d[b], 0);
+        mark(ctx->stream);
         if (linear) {
             k_repitch<<<592, 256, 0, ctx->stream>>>(stg, n, d, ldd, n, cnt);
             ctx->launches++;
@@ -80,7 +211,9 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
             ctx->launches++;
         }
         cudaEventRecord(cmp[b], ctx->stream);
+        mark(ctx->stream);
         cudaStreamWaitEvent(ctx->s_copy[1], cmp[b], 0);
+        mark(ctx->s_copy[1]);
         if (linear)
             e = cudaMemcpyAsync(X + done * ldx, stg, (size_t)n * cnt * 8, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
         else if (side == POP_LEFT)
@@ -89,12 +222,22 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
             e = cudaMemcpy2DAsync(X + done, ldx * 8, d, ldd * 8, cnt * 8, n, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
         if (e != cudaSuccess) { pop_set_error("host panel D2H: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
         cudaEventRecord(d2h[b], ctx->s_copy[1]);
+        mark(ctx->s_copy[1]);
         done += cnt;
         ++it;
     }
     cudaStreamSynchronize(ctx->s_copy[0]);
     cudaStreamSynchronize(ctx->stream);
     e = cudaStreamSynchronize(ctx->s_copy[1]);
+    if (trace && tev.size() > 1) {
+        // per chunk: [H2D start, H2D end, compute start, compute end, D2H start, D2H end] relative to the call's start
+        for (size_t i = 1; i + 5 < tev.size() + 1 && i + 5 <= tev.size() - 0; i += 6) {
+            float t[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[i + k]);
+            fprintf(stderr, "chunk %2zu: H2D %7.3f-%7.3f  compute %7.3f-%7.3f  D2H %7.3f-%7.3f ms\n", (i - 1) / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (auto ev : tev) cudaEventDestroy(ev);
+    }
     cudaFreeAsync(dbuf, ctx->stream);
     if (rc == POP_OK && e != cudaSuccess) { pop_set_error("host panel: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
     return rc;

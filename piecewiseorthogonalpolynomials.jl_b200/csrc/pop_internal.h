@@ -70,7 +70,7 @@ struct pop_ctx {
     int *h_info;      // pinned mirror
     // streams/events for the chunked host variants
     cudaStream_t s_copy[2];
-    cudaEvent_t ev[12];
+    cudaEvent_t ev[32];   // [0,8) H2D done, [8,16) compute done, [16,24) D2H done, 24: misc
 };
 
 int pop_ctx_scratch(pop_ctx *ctx, size_t bytes, void **out);

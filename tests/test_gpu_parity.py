@@ -418,6 +418,30 @@ def test_element_decomposed_row_half_step_and_adi(basis, m, N):
     dd.close()
 
 
+@pytest.mark.parametrize("basis,m,N,nrhs", [("c1", 64, 40, 300), ("dirichlet", 65, 33, 257), ("c1", 7, 5, 3)])
+def test_host_panels_flat_and_chunked(basis, m, N, nrhs, monkeypatch):
+    """pop_solve_host / pop_trsm_host on host buffers: the flat address-aligned pipeline (contiguous panels), its fall-back
+    to column chunks, several block sizes, a host base address that is only 8-byte aligned; all equal to the device path."""
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    F = P.reversecholesky(-Lp + 1.25 * M)
+    n = Mo.n
+    rng = np.random.default_rng(17)
+    Bm = rng.standard_normal((n, nrhs))
+    want = host(P.ldiv(F, dev(Bm)))
+    for flat, mb in (("1", "1"), ("1", "32"), ("0", "1")):
+        monkeypatch.setenv("POP_HOST_FLAT", flat)
+        monkeypatch.setenv("POP_HOST_CHUNK_MB", mb)
+        assert np.array_equal(P.ldiv(F, np.asfortranarray(Bm)), want), (flat, mb)
+        # a panel that starts 8 bytes into an aligned allocation
+        raw = np.zeros(n * nrhs + 1)
+        Xo = raw[1:].reshape((n, nrhs), order="F")
+        Xo[...] = Bm
+        P.ldiv(F, Xo, overwrite=True)
+        assert np.array_equal(Xo, want) and raw[0] == 0.0, (flat, mb)
+        U = F.U
+        assert relerr(P.ldiv(U, np.asfortranarray(Bm)), host(P.ldiv(U, dev(Bm)))) < 1e-15
+
+
 @pytest.mark.parametrize("basis", ["c1", "dirichlet"])
 def test_nonuniform_mesh_assembly_factor_solve(basis):
     """grammatrix / weaklaplacian on a non-uniform mesh (pop_assemble_mesh, one D block per element),

@@ -11,10 +11,11 @@ n = F.factor.n
 hB = torch.randn((nrhs, n), dtype=torch.float64).pin_memory()
 hX = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
 Xh = hX.numpy().T
-for mb in (8, 16, 32, 48, 96, 192):
+for nbuf, mb in ((3, 32), (4, 32), (6, 32), (4, 16), (6, 16), (8, 8), (4, 64), (3, 16)):
     os.environ["POP_HOST_CHUNK_MB"] = str(mb)
+    os.environ["POP_HOST_NBUF"] = str(nbuf)
     best = 1e9
     for _ in range(4):
         hX.copy_(hB); torch.cuda.synchronize()
         t0 = time.perf_counter(); P.ldiv(F, Xh, overwrite=True); best = min(best, time.perf_counter() - t0)
-    print(f"chunk {mb} MB: {best * 1e3:.1f} ms  {n * nrhs / best / 1e9:.2f} G unknown*RHS/s", flush=True)
+    print(f"{nbuf} buffers, chunk {mb} MB: {best * 1e3:.1f} ms  {n * nrhs / best / 1e9:.2f} G unknown*RHS/s", flush=True)
