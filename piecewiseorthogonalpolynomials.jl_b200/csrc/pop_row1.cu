@@ -9,12 +9,12 @@
 #include "pop_row.h"
 #include "pop_row1.cuh"
 
-static r1_kernel_t r1_kernel(int jmax, int rb, int npar) {
+static r1_kernel_t r1_kernel(int jmax, int rb, int npar, bool has1) {
     switch (jmax) {
-        case 16: return r1_kernel_r16(rb, npar);
-        case 32: return r1_kernel_r32(rb, npar);
-        case 48: return r1_kernel_r48(rb, npar);
-        case 64: return r1_kernel_r64(rb, npar);
+        case 16: return r1_kernel_r16(rb, npar, has1);
+        case 32: return r1_kernel_r32(rb, npar, has1);
+        case 48: return r1_kernel_r48(rb, npar, has1);
+        case 64: return r1_kernel_r64(rb, npar, has1);
     }
     return nullptr;
 }
@@ -64,7 +64,7 @@ static int row1_launch(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     if (!rb) return POP_ROW1_UNSUPPORTED;
     // the kernel addresses the degrees of an element with 32-bit offsets
     if ((int64_t)rows * op.m * op.ld >= ((int64_t)1 << 31) || (int64_t)rows * op.m * std::max<int64_t>(op.ldf, 1) >= ((int64_t)1 << 31)) return POP_ROW1_UNSUPPORTED;
-    r1_kernel_t kern = r1_kernel(rows, rb, npar);
+    r1_kernel_t kern = r1_kernel(rows, rb, npar, op.has1 != 0);
     if (!kern) return POP_ROW1_UNSUPPORTED;
     const int mlc = op.m / cs;
     const int nthr = (npar * mlc * rb + 31) & ~31;
@@ -106,7 +106,7 @@ static int row1_launch(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     cfg.numAttrs = 1;
     // persistent clusters: as many as are co-resident (queried once per shape)
     static int cached_key[6] = {0, 0, 0, 0, 0, 0}, cached_ncl = 0;
-    const int key[6] = {rows, rb, npar, cs, nthr, (int)smem};
+    const int key[6] = {rows, rb, npar * 2 + (op.has1 != 0), cs, nthr, (int)smem};
     int ncl = cached_ncl;
     if (!std::equal(key, key + 6, cached_key) || ncl <= 0) {
         cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count));

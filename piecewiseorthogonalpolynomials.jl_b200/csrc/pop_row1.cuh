@@ -41,10 +41,10 @@ struct R1Params {
 
 typedef void (*r1_kernel_t)(const R1Params);
 // jmax = chain class (16, 32, 48, 64); npar = 2: two threads per (element, row), even / odd degrees (needs decoupled chains)
-r1_kernel_t r1_kernel_r16(int rb, int npar);
-r1_kernel_t r1_kernel_r32(int rb, int npar);
-r1_kernel_t r1_kernel_r48(int rb, int npar);
-r1_kernel_t r1_kernel_r64(int rb, int npar);
+r1_kernel_t r1_kernel_r16(int rb, int npar, bool has1);
+r1_kernel_t r1_kernel_r32(int rb, int npar, bool has1);
+r1_kernel_t r1_kernel_r48(int rb, int npar, bool has1);
+r1_kernel_t r1_kernel_r64(int rb, int npar, bool has1);
 // largest block of a kernel whose threads keep `rows` chain entries in registers
 __host__ __device__ constexpr int r1_tmax(int rows) { return rows <= 32 ? 512 : rows <= 48 ? 320 : 256; }
 
@@ -96,10 +96,10 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // ROWS chain entries per thread; NPAR = 2: thread (par, e, r) owns the degrees j = 2i + par of element e in row r
 // (the even and odd degree chains decouple when the first super-diagonal of every D block is zero, true for
 // K + sigma M); NPAR = 1 handles the general two-band case.
-template <int ROWS, int RB, int NPAR>
+template <int ROWS, int RB, int NPAR, bool HAS1>
 __global__ void __launch_bounds__(r1_tmax(ROWS), 1) k_row1(const __grid_constant__ R1Params P) {
+    static_assert(!(HAS1 && NPAR == 2), "split chains need a zero first super-diagonal");
     extern __shared__ __align__(16) unsigned char r1_smem_raw[];
-    constexpr bool HAS1 = NPAR == 1;
     constexpr int JMAX = ROWS * NPAR;
     constexpr int JSAFE = JMAX - 16;   // degrees j < JSAFE exist for every q of the class (JMAX-16 < q <= JMAX)
     constexpr int NBI = (R1_NBMAX + NPAR - 1) / NPAR;
@@ -514,18 +514,19 @@ __global__ void __launch_bounds__(r1_tmax(ROWS), 1) k_row1(const __grid_constant
     }
 }
 
-// one translation unit per chain class JMAX: NPAR = 1 (general) and NPAR = 2 (split chains) variants
+// one translation unit per chain class JMAX: one thread per chain with / without the first super-diagonal, and the
+// split-chain variant
 template <int JMAX>
-static r1_kernel_t r1_pick(int rb, int npar) {
+static r1_kernel_t r1_pick(int rb, int npar, bool has1) {
     if (npar == 2) {
-        if (rb == 16) return k_row1<JMAX / 2, 16, 2>;
-        if (rb == 8) return k_row1<JMAX / 2, 8, 2>;
+        if (rb == 16) return k_row1<JMAX / 2, 16, 2, false>;
+        if (rb == 8) return k_row1<JMAX / 2, 8, 2, false>;
         return nullptr;
     }
-    if (rb == 16) return k_row1<JMAX, 16, 1>;
-    if (rb == 8) return k_row1<JMAX, 8, 1>;
+    if (rb == 16) return has1 ? k_row1<JMAX, 16, 1, true> : k_row1<JMAX, 16, 1, false>;
+    if (rb == 8) return has1 ? k_row1<JMAX, 8, 1, true> : k_row1<JMAX, 8, 1, false>;
     return nullptr;
 }
 #define R1_DEFINE_CLASS(JMAX) \
-    r1_kernel_t r1_kernel_r##JMAX(int rb, int npar) { return r1_pick<JMAX>(rb, npar); }
+    r1_kernel_t r1_kernel_r##JMAX(int rb, int npar, bool has1) { return r1_pick<JMAX>(rb, npar, has1); }
 #endif  // __CUDACC__

@@ -501,6 +501,26 @@ def test_rdiv_one_pass_rows(basis, m, N, nrows):
             P.rdiv(dev(R), F, algo=P.SOLVE_FUSED)
 
 
+@pytest.mark.parametrize("lower", [True, False])
+def test_rdiv_one_pass_general_bands(lower, monkeypatch):
+    """X / F with a shared D block whose FIRST super-diagonal is non-zero (test_arrowhead.jl:96): the one-pass row kernel
+    keeps the whole chain on one thread (no even/odd split) and applies both bands."""
+    rng = np.random.default_rng(31)
+    Ao = random_general(rng, 14, 11, nB=2, nC=0, lower_B=lower, lD=0, diag1=True, same_D=True)
+    for k in range(Ao.m):
+        Ao.D[k] += 5 * np.eye(Ao.q)
+    A = packed_to_product(P, O.pack(Ao), uniform=True)
+    F = P.reversecholesky(P.Symmetric(A))
+    Ssym = O.symmetric_from_upper(Ao).to_dense()
+    R = rng.standard_normal((21, Ao.n))
+    want = np.linalg.solve(Ssym, R.T).T
+    monkeypatch.setenv("POP_ROW1_STRICT", "1")
+    for cs in ("1", "0"):
+        monkeypatch.setenv("POP_ROW1_CS", cs)
+        assert relerr(host(P.rdiv(dev(R), F, algo=P.SOLVE_FUSED)), want) < 1e-11
+    assert relerr(host(P.rdiv(dev(R), F, algo=P.SOLVE_STAGED)), want) < 1e-11
+
+
 @pytest.mark.parametrize("basis,m,N,cs,rb", [
     ("dirichlet", 8, 12, 2, 16), ("dirichlet", 8, 12, 4, 16), ("dirichlet", 8, 12, 8, 16), ("c1", 8, 9, 4, 16), ("c1", 8, 9, 8, 8),
     ("dirichlet", 16, 9, 8, 8), ("dirichlet", 12, 20, 4, 16), ("c1", 6, 21, 2, 8), ("dirichlet", 8, 40, 4, 16), ("c1", 4, 64, 2, 16),

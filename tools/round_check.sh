@@ -11,4 +11,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --c
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fused2 -s 3 -c 1 -f -o gpurun_out/prof_bench_fused2_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-adi > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+timeout 200 ncu --set full --clock-control none --import-source on -k "regex:k_analysis_2d|k_weakform" -c 12 -f -o gpurun_out/prof_rhs_$TAG \
+    env RHS_CPU=0 python tools/prof_rhs.py > gpurun_out/ncu_rhs_$TAG.log 2>&1; echo "ncu rhs rc=$?"
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_row1 -s 6 -c 1 -f -o gpurun_out/prof_row1_$TAG \
+    python tools/row1_check.py 128 64 > gpurun_out/ncu_row1_$TAG.log 2>&1; echo "ncu row1 rc=$?"
+timeout 100 python tools/prof_rhs.py > gpurun_out/prof_rhs_$TAG.log 2>&1
+timeout 100 python tools/row1_check.py 128 64 --adi > gpurun_out/row1_check_$TAG.log 2>&1
 head -c 1500 gpurun_out/bench_$TAG.json
