@@ -44,6 +44,7 @@ struct pop_dd {
     double *pconst;  // [2][world]
     double *work;    // nrows x nloc work panel (leading dimension ld)
     bool hats_merged;   // the hat phase runs as ONE kernel (k_row_hats): tile fits, grid co-resident
+    int hats_ny;        // lanes over the hats in k_row_hats (block = 32 rows x hats_ny)
     size_t hats_smem;
     bool hats_planned;
 };
@@ -251,7 +252,8 @@ __global__ void k_dd_pconst(DDBounds bd, const double *const *__restrict__ ptrs,
 
 // ---- K1: backward bubble sweep along the rows:  z_j = (b_j - w1_j z_{j+1} - w2_j z_{j+2}) rd_j ------------
 // thread <-> (row r, local element kl); the 32 lanes of a warp are 32 consecutive rows.
-__global__ void __launch_bounds__(256) k_row_bwd(RowOp op, double *__restrict__ X, DDPeers peers, DDSync sy) {
+template <int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_row_bwd(RowOp op, double *__restrict__ X, DDPeers peers, DDSync sy) {
     __shared__ double srd[POP_DD_MAXQ], sw1[POP_DD_MAXQ], sw2[POP_DD_MAXQ];
     const int q = op.q;
     for (int j = threadIdx.y * 32 + threadIdx.x; j < q; j += 256) {
@@ -267,19 +269,19 @@ __global__ void __launch_bounds__(256) k_row_bwd(RowOp op, double *__restrict__ 
         const int64_t js = (int64_t)op.ml * op.ld;
         double z1 = 0.0, z2 = 0.0;
         int j = q - 1;
-        for (; j >= 7; j -= 8) {
-            double v[8];
+        for (; j >= DEPTH - 1; j -= DEPTH) {
+            double v[DEPTH];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j - u) * js];
+            for (int u = 0; u < DEPTH; ++u) v[u] = p[(int64_t)(j - u) * js];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < DEPTH; ++u) {
                 const double t = (v[u] - sw1[j - u] * z1 - sw2[j - u] * z2) * srd[j - u];
                 z2 = z1;
                 z1 = t;
                 v[u] = t;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) p[(int64_t)(j - u) * js] = v[u];
+            for (int u = 0; u < DEPTH; ++u) p[(int64_t)(j - u) * js] = v[u];
         }
         for (; j >= 0; --j) {
             const double t = (p[(int64_t)j * js] - sw1[j] * z1 - sw2[j] * z2) * srd[j];
@@ -424,8 +426,8 @@ __global__ void __launch_bounds__(128) k_row_hat_c(RowOp op, double *__restrict_
 }
 
 // ---- K2 (merged): the whole hat phase of 32 rows in one block ------------------------------------------------
-// Block = 32 rows x 4 lanes of hats.  The hat right-hand sides of the 32 rows are gathered into a shared-memory
-// tile [nhl][32] by all 128 threads; the recurrences then run on the tile (lane x of warp 0 owns row x: no global
+// Block = 32 rows x ny lanes of hats (ny = 16: the gather is latency-bound, see profiles/r1_row1.txt).  The hat right-hand
+// sides of the 32 rows are gathered into a shared-memory tile [nhl][32] by all threads; the recurrences then run on the tile (lane x of warp 0 owns row x: no global
 // latency inside the dependent chains); the two segment-map exchanges use flags PER ROW BLOCK, so a block only
 // waits for the same rows of its peers; the result leaves through all 128 threads again.  With peers the grid
 // must be co-resident (checked by the host; the per-kernel path above is the fallback).
@@ -455,13 +457,14 @@ __device__ __forceinline__ void dd_block_exchange(const DDPeers &peers, int worl
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) k_row_hats(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ hx,
+__global__ void __launch_bounds__(1024) k_row_hats(RowOp op, double *__restrict__ X, DDPeers peers, const double *__restrict__ pc, double *__restrict__ hx,
                                                   DDSync sy, unsigned long long epB, unsigned long long epC) {
     extern __shared__ double sm_h[];
     const int nhl = op.nhl, nhlp = (nhl + 1) & ~1;
     double *s_rd = sm_h, *s_cdn = s_rd + nhlp, *s_cup = s_cdn + nhlp, *tile = s_cup + nhlp;
     const int x = threadIdx.x, y = threadIdx.y, t = y * 32 + x;
-    for (int u = t; u < nhl; u += 128) {
+    const int ny = blockDim.y, nthr = 32 * ny;   // 32 rows x ny lanes over the hats
+    for (int u = t; u < nhl; u += nthr) {
         const int i = op.hA + u;
         const double rdv = op.rdA[i];
         s_rd[u] = rdv;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(128) k_row_hats(RowOp op, double *__restrict__
     // gather: hat right-hand sides minus the couplings to the (backward-swept) bubbles
     if (rv) {
         const double *inA = peers.inbA[me];
-        for (int u = y; u < nhl; u += 4) {
+        for (int u = y; u < nhl; u += ny) {
             const int i = op.hA + u;
             double v = X[r + (int64_t)u * op.ld];
             for (int b = 0; b < op.nb; ++b)
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(128) k_row_hats(RowOp op, double *__restrict__
     }
     __syncthreads();
     if (rv)
-        for (int u = y; u < nhl; u += 4) {
+        for (int u = y; u < nhl; u += ny) {
             const double h = tile[u * 32 + x];
             X[r + (int64_t)u * op.ld] = h;
             hx[(size_t)(u + 1) * op.nrows + r] = h;
@@ -705,9 +708,11 @@ static void dd_plan_hats(pop_ctx *ctx, pop_dd *d) {
         cudaGetLastError();
         return;
     }
+    d->hats_ny = 16;
+    if (const char *e = getenv("POP_DD_HATS_NY")) d->hats_ny = std::min(std::max(atoi(e), 1), 32);
     if (d->world > 1) {
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row_hats, 128, smem) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row_hats, 32 * d->hats_ny, smem) != cudaSuccess) {
             cudaGetLastError();
             return;
         }
@@ -759,10 +764,24 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
         ctx->launches++;
         pc = d->pconst;
     }
-    k_row_bwd<<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sync(0, epA, 0));
+    {
+        static int bv = -1;
+        if (bv < 0) {
+            bv = 4;   // measured (profiles/r1_row1.txt): blocks of 4 degrees at 40 registers, 6 CTAs/SM
+            if (const char *e = getenv("POP_DD_BWD_VARIANT")) bv = atoi(e);
+        }
+        const DDSync sy = sync(0, epA, 0);
+        switch (bv) {
+            case 1: k_row_bwd<4, 4><<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sy); break;
+            case 2: k_row_bwd<8, 3><<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sy); break;
+            case 3: k_row_bwd<16, 2><<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sy); break;
+            case 4: k_row_bwd<4, 6><<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sy); break;
+            default: k_row_bwd<8, 1><<<grd2, blk2, 0, ctx->stream>>>(op, R, peers, sy); break;
+        }
+    }
     ctx->launches++;
     if (d->hats_merged) {
-        k_row_hats<<<(unsigned)((d->nrows + 31) / 32), dim3(32, 4), d->hats_smem, ctx->stream>>>(op, R, peers, pc, d->hx, sync(epA, 0, 0), epB, epC);
+        k_row_hats<<<(unsigned)((d->nrows + 31) / 32), dim3(32, d->hats_ny), d->hats_smem, ctx->stream>>>(op, R, peers, pc, d->hx, sync(epA, 0, 0), epB, epC);
         ctx->launches++;
     } else {
         k_row_hat_gather<<<grdh, blk2, 0, ctx->stream>>>(op, R, peers, sync(epA, 0, 0));
