@@ -483,7 +483,7 @@ def main():
         del hB, hX
 
     adi = heat = shifted = rhs = None
-    if not args.no_adi and rank == 0:
+    if not args.no_adi and world == 1:                   # single-GPU secondary object (the scaling runs skip it)
         try:
             rhs = rhs_case(P, torch, dev)
         except Exception as ex:
