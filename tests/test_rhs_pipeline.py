@@ -93,6 +93,27 @@ def test_transform_reproduces_the_function_oracle():
     assert np.abs(np.polynomial.legendre.legvander(z, N - 1) @ back - np.exp(x).T).max() < 1e-13
 
 
+import os  # noqa: E402
+
+RG = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rhs_golden.npz"))
+
+
+def test_oracle_reproduces_rhs_fixtures():
+    """tests/golden/rhs_golden.npz (generator beside it) was produced without the closed forms: quadrature of the basis,
+    direct projection, synthesis of known coefficients."""
+    for name, basis in (("wf_c1_uniform", O.C1), ("wf_dirichlet_graded", O.DIRICHLET)):
+        pts, N = RG[f"{name}/points"], int(RG[f"{name}/N"])
+        assert relerr(O.weakform_rhs(basis, len(pts) - 1, N, np.diff(pts), RG[f"{name}/fp"]), RG[f"{name}/F"]) < 1e-13
+    r, N = RG["transform_exp/points"], int(RG["transform_exp/N"])
+    z, T = O.legendre_grid_transform(N + 1)
+    x = (r[:-1] + r[1:])[:, None] / 2 + np.diff(r)[:, None] / 2 * z[None, :]
+    leg = (np.exp(x) @ T.T).T.reshape(-1)
+    # interpolation at 11 nodes per element against the exact expansion: equal up to the truncation of exp at degree 10
+    assert np.abs(O.c1_from_legendre(O.C1, len(r) - 1, N + 1, leg[:, None])[:, 0] - RG["transform_exp/c"]).max() < 1e-12
+    n, p = int(RG["analysis/n"]), int(RG["analysis/p"])
+    assert relerr(O.analysis_2d(RG["analysis/vals"], n, p, O.legendre_grid_transform(p)[1]), RG["analysis/F"]) < 1e-13
+
+
 # ------------------------------------------------------------------------------------------------ CUDA kernels
 def _gpu():
     import torch
@@ -245,3 +266,19 @@ def test_transform_2d_like_the_reference_test():
     V = P.transform_2d(C1, _dev(torch, vals), p, T).cpu().numpy()
     E = O.basis_eval_matrix(O.C1, r, p - 1, np.array([0.1, 0.2]))
     assert abs(E[0] @ V @ E[1] - np.exp(0.1 * np.cos(0.2))) < 1e-10
+
+
+@pytest.mark.gpu
+def test_kernels_reproduce_rhs_fixtures():
+    torch, P = _gpu()
+    for name, basis in (("wf_c1_uniform", "c1"), ("wf_dirichlet_graded", "dirichlet")):
+        pts, N = RG[f"{name}/points"], int(RG[f"{name}/N"])
+        Q = P.ContinuousPolynomial(1, pts) if basis == "c1" else P.DirichletPolynomial(pts)
+        F = P.weakform_rhs(Q, P.Block.oneto(N), _dev(torch, RG[f"{name}/fp"]))
+        assert relerr(F.cpu().numpy(), RG[f"{name}/F"]) < TOL
+    r, N = RG["transform_exp/points"], int(RG["transform_exp/N"])
+    c = P.transform(P.ContinuousPolynomial(1, r), np.exp, N + 1)
+    assert np.abs(c.cpu().numpy() - RG["transform_exp/c"]).max() < 1e-12
+    n, p = int(RG["analysis/n"]), int(RG["analysis/p"])
+    F = P.analysis_2d(_dev(torch, RG["analysis/vals"]), n, p, P.legendre_grid_transform(p)[1])
+    assert relerr(F.cpu().numpy(), RG["analysis/F"]) < TOL
