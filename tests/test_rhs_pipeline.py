@@ -282,3 +282,25 @@ def test_kernels_reproduce_rhs_fixtures():
     n, p = int(RG["analysis/n"]), int(RG["analysis/p"])
     F = P.analysis_2d(_dev(torch, RG["analysis/vals"]), n, p, P.legendre_grid_transform(p)[1])
     assert relerr(F.cpu().numpy(), RG["analysis/F"]) < TOL
+
+
+@pytest.mark.gpu
+def test_theta_scheme_two_dimensions():
+    """pop_heat_steps_theta with dims = 2: U <- G U G', G = (M + theta dt K)^-1 (M - (1-theta) dt K) (the factored 2D extension
+    of examples/heat.jl:26-45), against the dense oracle."""
+    torch, P = _gpu()
+    m, N = 5, 9
+    Q = P.DirichletPolynomial(np.linspace(-1, 1, m + 1))
+    KR = P.Block.oneto(N)
+    M, K = P.grammatrix(Q)[KR, KR], -P.weaklaplacian(Q)[KR, KR]
+    Mo = O.assemble_mass(O.DIRICHLET, m, N, 2 / m)
+    Ko = O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.DIRICHLET, m, N, 2 / m), 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    n = Md.shape[0]
+    U0 = np.random.default_rng(5).standard_normal((n, n))
+    for theta in (0.5, 1.0):
+        G = np.linalg.solve(Md + theta * 1e-2 * Kd, Md - (1 - theta) * 1e-2 * Kd)
+        want = np.linalg.matrix_power(G, 6) @ U0 @ np.linalg.matrix_power(G, 6).T
+        U = _dev(torch, U0)
+        P.heat_steps(M, K, U, 1e-2, 6, dims=2, theta=theta)
+        assert relerr(U.cpu().numpy(), want) < 1e-11, theta
