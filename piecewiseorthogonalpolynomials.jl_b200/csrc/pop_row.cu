@@ -338,6 +338,8 @@ __global__ void __launch_bounds__(256) k_row_hat_gather(RowOp op, double *__rest
         s_cdn[u] = (i < op.nh - 1 ? op.offA[i] : 0.0) * rdv;                                              \
         s_cup[u] = (i > 0 ? op.offA[i - 1] : 0.0) * rdv;                                                  \
     }                                                                                                     \
+    (void)s_cdn;                                                                                          \
+    (void)s_cup;                                                                                          \
     __syncthreads();
 
 template <bool DOWN, bool STORE>

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "pop_row.h"
 #include "pop_row1.cuh"
@@ -105,8 +106,10 @@ static int row1_launch(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // persistent clusters: as many as are co-resident (queried once per shape)
+    static std::mutex plan_mu;
     static int cached_key[6] = {0, 0, 0, 0, 0, 0}, cached_ncl = 0;
     const int key[6] = {rows, rb, npar * 2 + (op.has1 != 0), cs, nthr, (int)smem};
+    std::lock_guard<std::mutex> lk(plan_mu);
     int ncl = cached_ncl;
     if (!std::equal(key, key + 6, cached_key) || ncl <= 0) {
         cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count));
