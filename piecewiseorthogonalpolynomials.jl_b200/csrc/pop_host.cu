@@ -38,9 +38,29 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
     const int64_t ldd = (n + 1) & ~(int64_t)1;
     const int64_t A = 4096;
     const int64_t off0 = (A - (int64_t)((uintptr_t)X % A)) % A;      // first aligned host address, relative to X
-    std::vector<int64_t> bnd;                                         // block boundaries (bytes)
+    // block boundaries (bytes): full blocks of blk_bytes in the middle, ramped up from / down to an eighth of a block at the
+    // ends so that the first columns are solved and the last block is on its way home after an eighth of a block time
+    std::vector<int64_t> bnd;
     bnd.push_back(0);
-    for (int64_t b = off0 + blk_bytes; b < total; b += blk_bytes) bnd.push_back(b);
+    {
+        const int64_t U = std::max<int64_t>(A, (blk_bytes / 8) & ~(A - 1));        // ramp unit, a multiple of 4 KiB
+        const int64_t nu = (total - off0 + U - 1) / U;                             // units to cover
+        std::vector<int64_t> sizes;                                                // in units
+        if (nu >= 1 + 2 + 4 + 8 + 4 + 2 + 1) {
+            const int64_t head[3] = {1, 2, 4}, tail[3] = {4, 2, 1};
+            int64_t left = nu - 14;
+            for (int i = 0; i < 3; ++i) sizes.push_back(head[i]);
+            while (left > 0) { sizes.push_back(std::min<int64_t>(8, left)); left -= 8; }
+            for (int i = 0; i < 3; ++i) sizes.push_back(tail[i]);
+        } else {
+            for (int64_t left = nu; left > 0; left -= 8) sizes.push_back(std::min<int64_t>(8, left));
+        }
+        int64_t b = off0;
+        for (size_t i = 0; i + 1 < sizes.size(); ++i) {
+            b += sizes[i] * U;
+            if (b < total) bnd.push_back(b);
+        }
+    }
     bnd.push_back(total);
     const int nblk = (int)bnd.size() - 1;
     int64_t maxcols = 0;

@@ -1,4 +1,4 @@
-"""e2e solve through pop_solve_host (pinned host panel) for a few chunk sizes."""
+"""e2e solve through pop_solve_host (pinned host panel): the flat address-aligned pipeline against the column-chunk one."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,11 +11,10 @@ n = F.factor.n
 hB = torch.randn((nrhs, n), dtype=torch.float64).pin_memory()
 hX = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
 Xh = hX.numpy().T
-for nbuf, mb in ((3, 32), (4, 32), (6, 32), (4, 16), (6, 16), (8, 8), (4, 64), (3, 16)):
-    os.environ["POP_HOST_CHUNK_MB"] = str(mb)
-    os.environ["POP_HOST_NBUF"] = str(nbuf)
-    best = 1e9
-    for _ in range(4):
+for flat in ("1", "0", "1"):
+    os.environ["POP_HOST_FLAT"] = flat
+    ts = []
+    for _ in range(6):
         hX.copy_(hB); torch.cuda.synchronize()
-        t0 = time.perf_counter(); P.ldiv(F, Xh, overwrite=True); best = min(best, time.perf_counter() - t0)
-    print(f"{nbuf} buffers, chunk {mb} MB: {best * 1e3:.1f} ms  {n * nrhs / best / 1e9:.2f} G unknown*RHS/s", flush=True)
+        t0 = time.perf_counter(); P.ldiv(F, Xh, overwrite=True); ts.append(time.perf_counter() - t0)
+    print(f"flat={flat}: " + " ".join(f"{t * 1e3:.1f}" for t in ts) + f" ms -> median of last 4 {np.median(ts[2:]) * 1e3:.2f} ms, {n * nrhs / np.median(ts[2:]) / 1e9:.2f} G unknown*RHS/s", flush=True)
