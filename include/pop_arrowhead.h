@@ -224,6 +224,16 @@ int pop_heat_steps(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M,
 int pop_heat_steps_theta(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, double dt, double theta,
                          int nsteps, int dims, double *dU, int64_t ldu, int64_t nrhs);
 
+/* ---- eigenvalues ----------------------------------------------------------------------
+ * eigvals(Symmetric(A)) and eigvals(Symmetric(A), Symmetric(B)) of src/arrowhead.jl:536-537, and the dense
+ * `A = U \ (U \ M)'; eigmin(A), eigmax(A)` of examples/adi_poisson.jl:91-94, by Lanczos with full
+ * re-orthogonalisation on the arrowhead kernels.  UB = NULL: spectrum of Symmetric(A); otherwise UB is the
+ * reverse-Cholesky factor of B and the spectrum is that of the pencil A x = lambda B x.  k steps (k <= 0 or
+ * k >= n: n steps = every eigenvalue with its multiplicity); theta receives the Ritz values in ascending order,
+ * resid (may be NULL) the bounds |lambda - theta_i| <= resid_i, *k_out their number. */
+int pop_eigvals_lanczos(pop_ctx *ctx, const pop_arrowhead *A, const pop_arrowhead *UB, int k, uint64_t seed,
+                        double *theta, double *resid, int *k_out);
+
 /* ---- multi-GPU 2D drivers: one process per GPU, X distributed by column blocks ------------------
  * The x<->y switch between the row and column sweeps of examples/adi_poisson.jl:53-56 is a distributed
  * transpose: one kernel transposes tiles through shared memory and stores them into the owning

@@ -33,6 +33,26 @@ int oracle_num_threads(void) {
 #endif
 }
 
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* B <- A' for a column-major rows x cols matrix A (the X' of X / F = (F \ X')', examples/adi_poisson.jl:54). */
+void oracle_transpose(const double *A, int64_t lda, int64_t rows, int64_t cols, double *B, int64_t ldb) {
+    const int64_t T = 32;
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int64_t c0 = 0; c0 < cols; c0 += T)
+        for (int64_t r0 = 0; r0 < rows; r0 += T) {
+            int64_t c1 = c0 + T < cols ? c0 + T : cols, r1 = r0 + T < rows ? r0 + T : rows;
+            for (int64_t c = c0; c < c1; ++c)
+                for (int64_t r = r0; r < r1; ++r) B[c + r * ldb] = A[r + c * lda];
+        }
+}
+
 /* In place on upper data: Ad[nh], Au[nh-1], B[nB][3][m], D[uD+1][q][m].  Returns 0 or the 1-based
  * index of a non-positive pivot. */
 int oracle_revchol(int m, int nh, int q, int nB, int uD, double *Ad, double *Au, double *B, double *D) {

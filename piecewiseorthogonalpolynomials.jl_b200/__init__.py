@@ -9,7 +9,7 @@ from .arrowhead import (BBBArrowheadMatrix, LowerTriangular, ReverseCholesky, Sy
                         reversecholesky_shifted)
 from .bases import Block, BlockRange, ContinuousPolynomial, DirichletPolynomial, LazyArrowhead, grammatrix, weaklaplacian
 from .drivers import (DistMatrix, ElementDecomposition, adi_poisson_dd, dd_columns, DistTranspose, adi_poisson_p2p, heat_steps_p2p, adi_num_iterations, adi_poisson, adi_poisson_distributed, adi_shifts, heat_steps,
-                      shard_bounds, spectrum_bounds)
+                      shard_bounds, spectrum_bounds, eigvals)
 from .rhs import (DiscontinuityError, analysis_2d, cell_grid, legendre_grid_transform, legendre_to_c1, transform, transform_2d,
                   weakform_apply, weakform_rhs)
 from ._lib import LEFT, RIGHT

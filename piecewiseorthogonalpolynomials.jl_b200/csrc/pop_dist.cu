@@ -228,7 +228,40 @@ __global__ void k_dist_wait(volatile unsigned long long *flags, int world, unsig
     __threadfence_system();
 }
 
+// After the final stream synchronisation of a distributed driver: did a spin-wait on a peer run into its bound?
+// (the kernels then carried on with incomplete data: the result must not be handed back as POP_OK)
+static int dist_check_timeout(pop_ctx *ctx, pop_dist *d, const char *who) {
+    if (d->world == 1) return POP_OK;
+    unsigned long long mark = 0;
+    POP_CUDA(cudaMemcpyAsync(&mark, d->flags + POP_DIST_MAXWORLD, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mark == 0) return POP_OK;
+    cudaMemsetAsync(d->flags + POP_DIST_MAXWORLD, 0, 8, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    pop_set_error("%s: rank %d timed out waiting for a peer at exchange epoch %llu; the result is incomplete", who, d->rank, mark);
+    return POP_ERR_CUDA;
+}
+
+// `handshake`: before the first tile is pushed, every rank announces that its kernels queued so far -- the ones that
+// read or write the destination buffer -- have completed, and waits for the same announcement of all peers.  Needed
+// whenever the peers' destination buffer was last touched by work that no earlier exchange epoch orders (the first
+// exchange of a driver call, the heat driver's passes); inside the ADI loop the epoch of the previous transpose already
+// says that the peer has finished reading the buffer, and the handshake is skipped.
+static int dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int dst_which, bool handshake);
+static void dist_handshake(pop_ctx *ctx, pop_dist *d) {
+    if (d->world == 1) return;
+    const unsigned long long ep0 = ++d->epoch;   // "the kernels I queued so far are done: my buffers are free"
+    DistFlags fl0 = {};
+    for (int r = 0; r < d->world; ++r) fl0.f[r] = d->peer_flags[r];
+    k_dist_signal<<<1, 32, 0, ctx->stream>>>(fl0, d->world, d->rank, ep0);
+    k_dist_wait<<<1, 32, 0, ctx->stream>>>(d->flags, d->world, ep0);
+    ctx->launches += 2;
+}
 extern "C" int pop_dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int dst_which) {
+    return dist_transpose(ctx, d, src_which, dst_which, true);
+}
+
+static int dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int dst_which, bool handshake) {
     POP_REQUIRE(ctx && d, POP_ERR_ARG, "pop_dist_transpose: null argument");
     POP_REQUIRE(d->opened, POP_ERR_ARG, "pop_dist_transpose: peers not opened (pop_dist_open)");
     POP_REQUIRE(src_which >= 0 && src_which < POP_DIST_NBUF && dst_which >= 0 && dst_which < POP_DIST_NBUF && src_which != dst_which,
@@ -244,6 +277,7 @@ extern "C" int pop_dist_transpose(pop_ctx *ctx, pop_dist *d, int src_which, int 
     dim3 block(32, 8);
     if (!pull || d->world == 1) {
         // PUSH: transpose my tiles and store them into the owners' buffers; then tell everybody and wait for everybody
+        if (handshake) dist_handshake(ctx, d);
         for (int r = 0; r < d->world; ++r) peers.dst[r] = d->peer_buf[r][dst_which];
         dim3 grid((unsigned)((d->wmax + 31) / 32), (unsigned)((wme + 63) / 64), (unsigned)d->world);
         k_dist_transpose<<<grid, block, 0, ctx->stream>>>(d->buf[src_which], d->ld, wme, d->lo[d->rank], peers, d->rank, d->world);
@@ -387,12 +421,13 @@ extern "C" int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhe
             // W <- T2_j (S1_j^{-1} W) - F^T/q_j   (my columns of R2^T), then V <- transpose (my columns of R2)
             mark();
             if (nchunks > 1) {
+                if (j == 0) dist_handshake(ctx, d);
                 if ((rc = dist_half_step(ctx, d, fac[2 * j], top[2 * j + 1], -1.0 / q[j], Ft, 0, 1, nchunks))) break;
                 mark();
             } else {
                 if ((rc = pop_solve_mul_axpy(ctx, fac[2 * j], top[2 * j + 1], -1.0 / q[j], Ft, ld, W, ld, w))) break;
                 mark();
-                if ((rc = pop_dist_transpose(ctx, d, 0, 1))) break;
+                if ((rc = dist_transpose(ctx, d, 0, 1, j == 0))) break;
             }
             mark();
             if (j + 1 < J) {
@@ -403,7 +438,7 @@ extern "C" int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhe
                 }
                 if ((rc = pop_solve_mul_axpy(ctx, fac[2 * j + 1], top[2 * j + 2], -1.0 / p[j + 1], Fl, ld, V, ld, w))) break;
                 mark();
-                if ((rc = pop_dist_transpose(ctx, d, 1, 0))) break;
+                if ((rc = dist_transpose(ctx, d, 1, 0, j == 0))) break;
             } else {
                 if ((rc = pop_solve(ctx, fac[2 * j + 1], POP_LEFT, V, ld, w, POP_SOLVE_AUTO))) break;
             }
@@ -426,6 +461,7 @@ extern "C" int pop_adi_poisson_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhe
         for (auto ev : evs) cudaEventDestroy(ev);
     }
     cleanup();
+    if (rc == POP_OK) rc = dist_check_timeout(ctx, d, "pop_adi_poisson_dist");
     return rc;
 }
 
@@ -445,7 +481,7 @@ extern "C" int pop_heat_steps_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhea
     pop_arrowhead *U = nullptr;
     double one = 1.0;
     int rc = pop_revchol_shifted_batch(ctx, M, K, &one, &dt, 1, &U, nullptr);   // S = M + dt*K
-    if (rc) return rc;
+    if (rc) { pop_arrowhead_free(ctx, U); return rc; }
     const int64_t ld = d->ld;
     const int64_t w = d->lo[d->rank + 1] - d->lo[d->rank];
     MulView mv;
@@ -465,6 +501,7 @@ extern "C" int pop_heat_steps_dist(pop_ctx *ctx, pop_dist *d, const pop_arrowhea
     if (rc == POP_OK && e != cudaSuccess) { pop_set_error("pop_heat_steps_dist: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; }
     cudaStreamSynchronize(ctx->stream);
     pop_arrowhead_free(ctx, U);
+    if (rc == POP_OK) rc = dist_check_timeout(ctx, d, "pop_heat_steps_dist");
     return rc;
 }
 

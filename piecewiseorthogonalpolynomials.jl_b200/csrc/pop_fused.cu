@@ -684,13 +684,12 @@ int pop_launch_solve_fused(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrow
     POP_REQUIRE(pl.ok, POP_ERR_DIM, "fused solve: shape not supported (n=%lld, uD=%d)", (long long)U->n(), U->d.uD);
     // TMA bulk copies need 16 B aligned column starts
     if ((ldx & 1) || ((uintptr_t)X & 15)) {
+        // nothing is touched before the error: the caller (pop_solve_mul_axpy) routes unaligned panels to the staged path
+        POP_REQUIRE(!T, POP_ERR_DIM, "fused solve+product needs an even leading dimension and a 16-byte aligned panel");
         TriView up, lo;
         pop_make_triview(U, POP_UPPER, 0, 0, &up);
         pop_make_triview(U, POP_UPPER, 1, 0, &lo);
-        int rc = pop_launch_solve_staged(ctx, up, lo, X, 1, ldx, nrhs);
-        if (rc || !T) return rc;
-        pop_set_error("fused solve+product needs an even leading dimension and a 16-byte aligned panel");
-        return POP_ERR_DIM;
+        return pop_launch_solve_staged(ctx, up, lo, X, 1, ldx, nrhs);
     }
     FusedParams P = {};
     pop_make_triview(U, POP_UPPER, 0, 0, &P.up);

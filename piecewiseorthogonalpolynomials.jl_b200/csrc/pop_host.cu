@@ -509,7 +509,7 @@ extern "C" int pop_heat_steps_theta(pop_ctx *ctx, const pop_arrowhead *K, const 
     pop_arrowhead *U = nullptr, *Tm = nullptr;
     double one = 1.0, sdt = theta * dt;
     int rc = pop_revchol_shifted_batch(ctx, M, K, &one, &sdt, 1, &U, nullptr);   // S = M + theta*dt*K
-    if (rc) return rc;
+    if (rc) { pop_arrowhead_free(ctx, U); return rc; }
     const pop_arrowhead *Top = M;                                                // right-hand-side operator M - (1-theta)*dt*K
     if (theta < 1.0) {
         rc = pop_axpby(ctx, 1.0, M, -(1.0 - theta) * dt, K, &Tm);

@@ -820,6 +820,23 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
     return POP_OK;
 }
 
+// After the final stream synchronisation of a driver: did a bounded spin-wait on a peer give up?  (dd_wait_all,
+// dd_block_exchange record the epoch in the error slot and carry on with incomplete data.)
+static int dd_check_timeout(pop_ctx *ctx, pop_dd *d, const char *who) {
+    if (d->world == 1 || d->fake_peers) return POP_OK;
+    size_t oA, oB, oC, oD, oF;
+    dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
+    unsigned long long *slot = (unsigned long long *)((char *)d->slab + oF) + POP_DD_MAXWORLD;
+    unsigned long long mark = 0;
+    POP_CUDA(cudaMemcpyAsync(&mark, slot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mark == 0) return POP_OK;
+    cudaMemsetAsync(slot, 0, 8, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    pop_set_error("%s: rank %d timed out waiting for a peer at exchange epoch %llu; the result is incomplete", who, d->rank, mark);
+    return POP_ERR_CUDA;
+}
+
 // exposed for tests / drivers: one row half step on a caller-owned local panel
 extern "C" int pop_dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, const pop_arrowhead *T, double gamma, const double *dF,
                                     int64_t ldf, double *dR, int64_t ldr) {
@@ -827,7 +844,12 @@ extern "C" int pop_dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead
     POP_REQUIRE(d->opened, POP_ERR_ARG, "pop_dd_row_half_step: peers not opened");
     POP_REQUIRE(ldr == d->ld, POP_ERR_DIM, "pop_dd_row_half_step: the panel must use the leading dimension pop_dd_ld()");
     POP_REQUIRE(!(T && gamma != 0.0) || (dF && ldf >= d->nrows), POP_ERR_DIM, "pop_dd_row_half_step: F panel missing or too small");
-    return dd_row_half_step(ctx, d, U, T, gamma, dF, ldf, dR, nullptr);
+    int rc = dd_row_half_step(ctx, d, U, T, gamma, dF, ldf, dR, nullptr);
+    if (rc == POP_OK && d->world > 1 && !d->fake_peers) {
+        POP_CUDA(cudaStreamSynchronize(ctx->stream));
+        rc = dd_check_timeout(ctx, d, "pop_dd_row_half_step");
+    }
+    return rc;
 }
 
 __global__ void k_dd_scale_copy(const double *__restrict__ src, int64_t lds, double *__restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, double s) {
@@ -920,5 +942,6 @@ extern "C" int pop_adi_poisson_dd(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *
     cudaFreeAsync((void *)dptrs, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     cleanup();
+    if (rc == POP_OK) rc = dd_check_timeout(ctx, d, "pop_adi_poisson_dd");
     return rc;
 }

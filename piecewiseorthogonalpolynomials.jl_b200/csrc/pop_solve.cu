@@ -331,7 +331,10 @@ extern "C" int pop_solve_mul_axpy(pop_ctx *ctx, const pop_arrowhead *U, const po
     if (nrhs == 0) return POP_OK;
     if ((!Tm || gamma == 0.0 || (!(ldf & 1) && !((uintptr_t)dF & 15))) && pop_fused2_supported(ctx, U, Tm, ldr, dR))
         return pop_launch_solve_fused2(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
-    if (pop_fused_supported(ctx, U, Tm)) return pop_launch_solve_fused(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
+    // the shared-memory fused kernel moves columns by TMA bulk copies: 16-byte aligned column starts for R and F, or the
+    // staged path below (never a half-updated panel and an error)
+    const bool aligned = !(ldr & 1) && !((uintptr_t)dR & 15) && (!Tm || gamma == 0.0 || (!(ldf & 1) && !((uintptr_t)dF & 15)));
+    if (aligned && pop_fused_supported(ctx, U, Tm)) return pop_launch_solve_fused(ctx, U, Tm, gamma, dF, ldf, dR, ldr, nrhs);
     // staged fallback: solve, then R <- T*X + gamma*F through a scratch copy
     TriView up, lo;
     pop_make_triview(U, POP_UPPER, 0, 0, &up);

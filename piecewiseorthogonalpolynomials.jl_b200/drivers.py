@@ -70,30 +70,47 @@ def heat_steps(M, K, U, dt, nsteps, dims=1, theta=1.0):
     return U
 
 
-def spectrum_bounds(M, K, iters=200, seed=0):
-    """(a, b) with a <= lambda(K^{-1} M) <= b: b by power iteration on K^{-1}M, a = 1/lambda_max(M^{-1}K)
-    by power iteration on M^{-1}K, both through reverse-Cholesky solves on the device; widened by 1e-6
-    relative so the interval encloses the spectrum (ADI converges for any enclosing interval)."""
-    import torch
-    from .arrowhead import ldiv, mul, reversecholesky
-    Ms, Ks = (M if isinstance(M, Symmetric) else Symmetric(M)), (K if isinstance(K, Symmetric) else Symmetric(K))
-    FM, FK = reversecholesky(Ms), reversecholesky(Ks)
-    n = Ms.n
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    dev = f"cuda:{_base(M).ctx.device}"
+def eigvals(A, B=None, k=None, seed=0, return_residuals=False):
+    """eigvals(Symmetric(A)) / eigvals(Symmetric(A), Symmetric(B)) (src/arrowhead.jl:536-537) by Lanczos with full
+    re-orthogonalisation on the arrowhead kernels (csrc/pop_eig.cu).  k=None: all n eigenvalues; k << n: k Ritz values
+    (the extreme ones converge first) with residual bounds |lambda - theta_i| <= resid_i."""
+    from .arrowhead import reversecholesky
+    Ab = _base(A)
+    n = Ab.n
+    kk = n if k is None else int(min(k, n))
+    UB = None
+    if B is not None:
+        UB = B.factor if hasattr(B, "factor") else reversecholesky(B if isinstance(B, Symmetric) else Symmetric(B)).factor
+    theta = np.zeros(kk)
+    resid = np.zeros(kk)
+    kout = C.c_int(0)
+    L.check(L.lib().pop_eigvals_lanczos(Ab.ctx.handle, Ab._h, UB._h if UB is not None else None, kk, int(seed),
+                                        theta.ctypes.data_as(C.c_void_p), resid.ctypes.data_as(C.c_void_p), C.byref(kout)), "eigvals")
+    theta, resid = theta[:kout.value], resid[:kout.value]
+    return (theta, resid) if return_residuals else theta
 
-    def power(applyA, solveB):
-        x = torch.randn(n, generator=g, dtype=torch.float64).to(dev)
-        lam = 0.0
-        for _ in range(iters):
-            y = ldiv(solveB, mul(applyA, x))
-            lam = float(torch.dot(x, y) / torch.dot(x, x))
-            x = y / torch.linalg.norm(y)
-        return lam
 
-    b = power(Ms, FK)          # lambda_max(K^{-1} M)
-    lmax = power(Ks, FM)       # lambda_max(M^{-1} K)
-    return (1.0 / lmax) * (1 - 1e-6), b * (1 + 1e-6)
+def spectrum_bounds(M, K, k=160, seed=0, rtol=1e-6, iters=None):
+    """(a, b) with a <= lambda(K^{-1} M) <= b, the ADI interval the reference takes from a dense eigmin/eigmax
+    (examples/adi_poisson.jl:91-94).  b = lambda_max of the pencil (M, K) and 1/a = lambda_max of the pencil (K, M), both
+    from Lanczos on the arrowhead kernels; each Ritz value is moved outwards by its residual bound (a Ritz value lies
+    inside the spectrum, an eigenvalue lies within the residual of it) and by `rtol`, so the interval encloses the
+    spectrum.  The number of Lanczos steps doubles until the residual of the extreme Ritz value is below 1e-3 of it."""
+    n = _base(M).n
+
+    def lam_max(A, B):
+        from .arrowhead import reversecholesky
+        FB = reversecholesky(B if isinstance(B, Symmetric) else Symmetric(_base(B)))
+        kk = min(k, n)
+        while True:
+            th, rs = eigvals(A, FB, k=kk, seed=seed, return_residuals=True)
+            if rs[-1] <= 1e-3 * abs(th[-1]) or kk >= n:
+                return (th[-1] + rs[-1]) * (1 + rtol)
+            kk = min(2 * kk, n)
+
+    b = lam_max(M, K)
+    lmax = lam_max(K, M)
+    return 1.0 / lmax, b
 
 
 # --------------------------------------------------------------------------------------

@@ -191,7 +191,7 @@ def test_adi_poisson_example_end_to_end_gpu():
     assert relerr(F.cpu().numpy(), Fo) < TOL
     M = P.grammatrix(Q)[KR, KR]
     Kh = -P.weaklaplacian(Q)[KR, KR]
-    a, b = P.spectrum_bounds(M, Kh, iters=400)
+    a, b = P.spectrum_bounds(M, Kh)
     X = P.adi_poisson(M, Kh, F, a, b)
     Y = P.rdiv(X, P.reversecholesky(Kh))                            # Y = (U' \ (U \ X'))'
     pts = np.linspace(-1, 1, 41)

@@ -61,7 +61,7 @@ def main():
         L.check(L.lib().pop_dd_row_half_step(ctx.handle, dd._h, Fs.factor._h, T.data._h, -0.4, Fl.data_ptr(), Fl.stride(1), Rl.data_ptr(), Rl.stride(1)), "row half step")
         torch.cuda.synchronize()
         e_half = float(torch.linalg.norm(Rl - want[:, cols]) / torch.linalg.norm(want))
-        a, b = P.spectrum_bounds(M, K, iters=300)
+        a, b = P.spectrum_bounds(M, K)
         J = P.adi_num_iterations(a, b, -b, -a, 1e-15)
         Xref = P.adi_poisson(M, K, Ffull, a, b, J=J)
         Xl = P.adi_poisson_dd(M, K, Fl, a, b, J=J, dd=dd)

@@ -48,7 +48,7 @@ def main():
     grid.transpose(0, 1)
     torch.cuda.synchronize()
     err_t = float(torch.linalg.norm(grid.buffer(1) - Ffull.t()[:, lo:hi]) / torch.linalg.norm(Ffull))
-    a, b = P.spectrum_bounds(M, K, iters=300)
+    a, b = P.spectrum_bounds(M, K)
     J = P.adi_num_iterations(a, b, -b, -a, 1e-15)
     Xref = P.adi_poisson(M, K, Ffull, a, b, J=J)
     Xp = P.adi_poisson_p2p(M, K, _cm(Ffull[:, lo:hi], dev), a, b, J=J, grid=grid)
