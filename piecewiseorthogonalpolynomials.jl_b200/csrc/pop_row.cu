@@ -732,6 +732,8 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
     if (rc) return rc;
     if (d->world == 1) {
         // one GPU: the row block stays on chip for the whole half step (pop_row1.cuh), one pass over HBM
+        rc = pop_row2_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R);
+        if (rc != POP_ROW1_UNSUPPORTED) return rc;
         rc = pop_row1_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R);
         if (rc != POP_ROW1_UNSUPPORTED) return rc;
     }

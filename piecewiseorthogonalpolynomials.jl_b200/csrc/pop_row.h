@@ -32,3 +32,7 @@ struct RowOp {
 int pop_row1_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R);
 // X / F on a row panel (nrhs x n): POP_OK, an error, or POP_ROW1_UNSUPPORTED
 int pop_row1_solve_right(pop_ctx *ctx, const pop_arrowhead *U, double *dX, int64_t ldx, int64_t nrhs);
+
+// Single-pass row half step on ONE GPU with TMA tensor traffic and a cluster-wide hat broadcast (pop_row2.cu); same
+// contract as pop_row1_half_step.  Tried first; the older kernels are the fallback for the shapes it does not cover.
+int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R);

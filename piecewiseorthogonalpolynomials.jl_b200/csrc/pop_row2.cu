@@ -1,0 +1,843 @@
+// k_row2 -- single-pass row half step of the 2D ADI on ONE GPU (24 B per entry):
+//     rows of R  <-  T (S^{-1} r) + gamma f ,   S = U U^T      (X / F followed by X * A, examples/adi_poisson.jl:54)
+//
+// A block of 8 consecutive rows of the n x n panel (every memory access is a 64 B run; two neighbouring blocks fill a
+// 128 B line) is owned by a thread-block CLUSTER of cs CTAs for the whole half step.  CTA c owns the mesh elements
+// [c*mlc, (c+1)*mlc) of the row direction and their hats.  All global traffic is TMA TENSOR traffic
+// (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG / UTMAPF) issued by one thread:
+//   * the bubble part of the panel is a 3-D tensor (row, element, degree); the next block lands in a shared-memory
+//     buffer [degree][element][row] while the current one is worked on in REGISTERS: thread (parity, element, row)
+//     keeps the even or the odd degrees of its element's chain (the chains decouple: the first super-diagonal of
+//     every D block of K + sigma M is zero) between the backward sweep (src/arrowhead.jl:439-441), the hat solve
+//     (:449-453, :472-477) and the forward sweep (:480-482);
+//   * F streams through a ring of 8-degree chunks (prefetched into L2 one block ahead), each chunk is overwritten in
+//     place by the result T x + gamma f and leaves by a TMA store.
+// The hat system of the 8 rows couples the CTAs.  Every CTA broadcasts, with ONE bulk copy per peer through
+// distributed shared memory (cp.async.bulk.shared::cluster + mbarrier complete_tx), the right-hand sides of its hats
+// with the couplings of its own elements taken off, plus the few backward-swept bubble values of its two edge
+// elements; every CTA then solves the whole bidiagonal pair for the 8 rows redundantly (4 lanes per row, segmented
+// affine scan) -- one exchange per block, no cluster barrier in the steady state, no second round for the product.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "pop_ptx.cuh"
+#include "pop_row.h"
+
+#define R2_RB 8          // rows per block
+#define R2_NBMAX 4       // coupling blocks (factor and product)
+#define R2_MAXCS 8
+#define R2_NS_MAX 8
+
+struct R2Params {
+    CUtensorMap mapX3, mapXh, mapF3, mapFh;   // bubbles (row, element, degree) and hats (row, hat) of the panel and of F
+    // factor U (upper data, shared D block)
+    const double *rd, *w2;         // [q]
+    const double *S;               // [nb][3][m]
+    const double *rdA, *offA;      // [nh], [nh-1]
+    int nb;
+    // product operator T = Symmetric(upper data); nbT < 0: plain solve
+    const double *t0, *t2;
+    const double *Ts;
+    const double *TAd, *TAu;
+    int nbT;
+    double gamma;
+    int useF;
+    double *X;
+    const double *F;
+    int64_t ld, ldf, nrows;
+    int m, nh, q;
+    int cs, mlc, nch, ns, nblk, pf_dist;
+    int pairing;                   // clusters 2p and 2p+1 work on the row blocks 2b and 2b+1 at the same time (the two halves of every 128 B line)
+    int hf_rows;                   // rows of HF: entry 0, the hats, zero pads up to 4*lp+1 and m+2
+    int lp;                        // hats per scan segment (8 segments; tables and HF are padded to 8*lp)
+    // shared-memory offsets (bytes)
+    int o_in, o_inh, o_fh, o_ring, o_mb, o_hf, o_ct, o_tab, o_ttab, o_ftab, o_hrd, o_hcd, o_hcu, o_ss, o_st, total;
+    int mbw;                       // doubles per mailbox message
+    long long *dbg;                // POP_ROW2_TRACE: phase time stamps of CTA 0 (clock64), [block][10]
+};
+
+// ---- TMA tensor helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Shared-memory layout.  Everything whose size follows from (CH, DC, mlc) comes first, so that a kernel instantiated for
+// a fixed mlc addresses it with compile-time offsets; the arrays that depend on nh, m, cs and on the number of ring slots
+// follow (their offsets travel in R2Params).
+struct R2Fixed {
+    int in, inh, fh, ct, tab, ttab, ftab, ss, st, ring, cb, hbs;
+};
+__host__ __device__ constexpr int r2_al(int x) { return (x + 127) / 128 * 128; }
+__host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc) {
+    R2Fixed f = {};
+    const int nchmax = (2 * ch + dc - 1) / dc;
+    f.cb = dc * mlc * R2_RB * 8;
+    f.hbs = r2_al((mlc + 1) * R2_RB * 8);
+    int o = 256;                                 // mbarriers
+    f.in = o; o += nchmax * f.cb;
+    f.inh = o; o += 2 * f.hbs;
+    f.fh = o; o += 2 * f.hbs;
+    f.ct = o; o += r2_al(4 * mlc * R2_RB * 8);
+    f.tab = o; o += r2_al((2 * ch + 2) * 16);
+    f.ttab = o; o += r2_al((2 * ch + 2) * 16);
+    f.ftab = o; o += r2_al((2 * ch + 2) * 16);
+    f.ss = o; o += r2_al(R2_NBMAX * 3 * mlc * 8);
+    f.st = o; o += r2_al(R2_NBMAX * 3 * mlc * 8);
+    f.ring = o;
+    return f;
+}
+
+// shared-memory accesses of the hot loops by 32-bit address (no generic 64-bit pointers in the register-critical code)
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// CH chain entries per thread: thread (par, e, r) owns the degrees j = 2 i + par, i < CH, of element e in row r.
+// DC degrees per TMA box / ring slot (8, or 4 when shared memory is short: more, smaller slots).
+// Threads [0, 16 mlc) compute; one more warp (the last) is the TMA PRODUCER: it alone issues and waits for the tensor
+// copies, and meets the compute threads only through mbarriers (no block-wide barrier on the data path).
+#define R2_BAR_COMPUTE 1   // named barrier of the compute threads
+#define R2_STAMP(slot) do { if (P.dbg && blockIdx.x == 0 && tid == 0 && t < 64) P.dbg[t * 10 + (slot)] = clock64(); } while (0)
+#define R2_BAR_HATS 2      // compute threads + the two hat warps
+#define R2_COMPUTE_SLOTS 512   // threads [0, 512): compute (the first 16 mlc of them work), [512, 640): producer warp group
+// MLC > 0: elements per CTA fixed at compile time (every hot shared-memory address is then one register plus an immediate).
+template <int CH, int DC, int MLC>
+__global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Params P) {
+    extern __shared__ __align__(128) unsigned char r2_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(r2_raw);
+    uint64_t *barIN = bars;            // the row block has landed (producer arrive + bytes)
+    uint64_t *barINfree = bars + 1;    // every compute thread has copied its part of the row block into registers
+    uint64_t *barMB = bars + 2;        // [2] the peers' messages of a block (by block parity)
+    uint64_t *barF = bars + 4;         // [ns] slot holds F of its chunk (bytes), or is free for output (producer arrive)
+    uint64_t *barR = bars + 4 + R2_NS_MAX;   // [ns] every compute thread has written its results into the slot
+    const int tid = threadIdx.x;
+    const int cs = P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch, ns = P.ns;
+    const int nthr = 16 * mlc;         // compute threads
+    const R2Fixed LF = r2_fixed(CH, DC, mlc);   // compile-time constants when MLC > 0
+    const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const int m = P.m, nh = P.nh, q = P.q;
+    const bool mul = P.nbT >= 0;
+    const bool useF = P.useF != 0;
+    double *IN = reinterpret_cast<double *>(r2_raw + LF.in);
+    double *INH = reinterpret_cast<double *>(r2_raw + LF.inh);     // [2][(mlc+1)*8]
+    double *FH = reinterpret_cast<double *>(r2_raw + LF.fh);       // [2][(mlc+1)*8]
+    double *RING = reinterpret_cast<double *>(r2_raw + LF.ring);   // [ns][DC][mlc][8]
+    double *MB = reinterpret_cast<double *>(r2_raw + P.o_mb);       // [2][cs][mbw]
+    double *HF = reinterpret_cast<double *>(r2_raw + P.o_hf);       // [m+3][8], entry i+1 = hat i, zeros around
+    double *ct = reinterpret_cast<double *>(r2_raw + LF.ct);       // [3][mlc][8] (both parities summed); later xb [4][mlc][8]
+    double2 *tab = reinterpret_cast<double2 *>(r2_raw + LF.tab);   // (rd_j, w2_j)
+    double2 *ttab = reinterpret_cast<double2 *>(r2_raw + LF.ttab); // (t0_j, t2_j)
+    double2 *ftab = reinterpret_cast<double2 *>(r2_raw + LF.ftab); // (rd_j, w2_{j-2}): the forward sweep's pair
+    double *hrd = reinterpret_cast<double *>(r2_raw + P.o_hrd);     // [nh]
+    double *hcd = reinterpret_cast<double *>(r2_raw + P.o_hcd);     // off(i,i+1) rd_i
+    double *hcu = reinterpret_cast<double *>(r2_raw + P.o_hcu);     // off(i-1,i) rd_i
+    double *sS = reinterpret_cast<double *>(r2_raw + LF.ss);       // [4][3][mlc]
+    double *sT = reinterpret_cast<double *>(r2_raw + LF.st);       // [4][3][mlc]
+    const int CBD = LF.cb / 8;                // doubles per chunk of DC degrees
+    const int HBD = (mlc + 1) * R2_RB;        // doubles per hat box
+    const int HBS = LF.hbs / 8;               // distance of the two parity buffers (TMA destinations: 128 B aligned)
+    const int mbw = P.mbw;
+    const int k0 = rank * mlc;
+    const int hA = k0, hB = rank == cs - 1 ? nh : min(nh, k0 + mlc);
+    const int nhl = max(hB - hA, 0);
+    const bool producer = tid >= nthr;   // set-up: everybody but the compute threads idles
+
+    // ---- one-time set-up ------------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(barIN, 1);
+        mbar_init(barINfree, (uint32_t)(nthr / 32));   // one arrival per compute warp
+        mbar_init(barMB, 1);
+        mbar_init(barMB + 1, 1);
+        for (int s = 0; s < ns; ++s) {
+            mbar_init(barF + s, 1);
+            mbar_init(barR + s, (uint32_t)(nthr / 32));
+        }
+        fence_mbar_init();
+    }
+    if (!producer) {
+        for (int j = tid; j < 2 * CH + 2; j += nthr) {
+            const bool in = j < q;
+            tab[j] = make_double2(in ? P.rd[j] : 0.0, (in && P.w2 && j + 2 < q) ? P.w2[j] : 0.0);
+            ttab[j] = make_double2((in && mul) ? P.t0[j] : 0.0, (in && mul && P.t2 && j + 2 < q) ? P.t2[j] : 0.0);
+            ftab[j] = make_double2(in ? P.rd[j] : 0.0, (in && P.w2 && j >= 2) ? P.w2[j - 2] : 0.0);
+        }
+        for (int i = tid; i < 8 * P.lp; i += nthr) {   // padded to 8 scan segments of lp hats: zeros behind the last hat
+            const double rdv = i < nh ? P.rdA[i] : 0.0;
+            hrd[i] = rdv;
+            hcd[i] = (i < nh - 1 ? P.offA[i] : 0.0) * rdv;
+            hcu[i] = (i > 0 && i < nh ? P.offA[i - 1] : 0.0) * rdv;
+        }
+        for (int x = tid; x < R2_NBMAX * 3 * mlc; x += nthr) {
+            const int b = x / (3 * mlc), t = (x / mlc) % 3, e = x % mlc;
+            sS[x] = b < P.nb ? P.S[((size_t)b * 3 + t) * m + k0 + e] : 0.0;
+            sT[x] = (mul && b < P.nbT) ? P.Ts[((size_t)b * 3 + t) * m + k0 + e] : 0.0;
+        }
+        for (int x = tid; x < P.hf_rows * R2_RB; x += nthr)   // zero pads around the hats: entry 0 and everything behind hat nh-1
+            if (x < R2_RB || x >= (nh + 1) * R2_RB) HF[x] = 0.0;
+    }
+    __syncthreads();
+    if (cs > 1) {   // every CTA's mbarriers are initialised before a peer sends to them
+        cluster_arrive();
+        cluster_wait();
+    }
+
+    // row blocks of this cluster: block t is number bbase + t * bstride.  With pairing, two clusters walk through
+    // neighbouring row blocks side by side, so that both 64 B halves of every 128 B line are requested within
+    // microseconds of each other (the second request hits L2 instead of fetching the line from HBM again).
+    const int ncl = gridDim.x / cs, cl = blockIdx.x / cs;
+    int bbase, bstride, nloc;
+    if (P.pairing) {
+        const int npt = (P.nblk + 1) / 2, npc = ncl / 2;
+        const int per = (npt + npc - 1) / npc;
+        const int p0 = (cl >> 1) * per, p1 = min(npt, p0 + per);
+        bbase = 2 * p0 + (cl & 1);
+        bstride = 2;
+        nloc = max(p1 - p0, 0);
+        if (nloc > 0 && bbase + 2 * (nloc - 1) >= P.nblk) --nloc;
+    } else {
+        const int per = (P.nblk + ncl - 1) / ncl;
+        bbase = cl * per;
+        bstride = 1;
+        nloc = max(min(P.nblk, bbase + per) - bbase, 0);
+    }
+    const int gtot = nloc * nch;                     // chunks of this CTA over the whole kernel
+
+    // Register budget (5 warps per scheduler: 96 registers each at launch): the producer warp group (threads 512 .. 639:
+    // the TMA producer lane and the two hat warps) hands registers back to the CTA pool, the four compute warp groups take
+    // 112 each from it: 4 warps x (96 - 32) released = 16 warps x (112 - 96) taken -- the pool holds nothing else)
+    if (tid >= R2_COMPUTE_SLOTS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        // =========================== TMA producer (one lane) =====================================================
+        if (tid == R2_COMPUTE_SLOTS && nloc > 0) {
+            const uint32_t in_bytes = (uint32_t)((nch * CBD + HBD * (useF ? 2 : 1)) * 8);
+            auto issue_in = [&](int t) {   // block t of this cluster -> IN, INH[t&1] (, FH[t&1])
+                const int row0 = (bbase + t * bstride) * R2_RB;
+                mbar_expect_tx(barIN, in_bytes);
+                for (int c = nch - 1; c >= 0; --c) tma_load_3d(IN + c * CBD, &P.mapX3, row0, k0, DC * c, barIN);
+                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, row0, hA, barIN);
+                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, row0, hA, barIN);
+            };
+            int gf = 0, tf = 0, cf = 0, sf = 0;      // next F chunk to request: index, its block, its chunk, its slot
+            auto feed = [&]() {                      // slot sf is free: request F of chunk gf into it, or hand it to the compute threads
+                if (gf < gtot) {
+                    if (useF) {
+                        mbar_expect_tx(barF + sf, (uint32_t)(CBD * 8));
+                        tma_load_3d(RING + sf * CBD, &P.mapF3, (bbase + tf * bstride) * R2_RB, k0, DC * cf, barF + sf);
+                    } else {
+                        mbar_arrive(barF + sf);
+                    }
+                }
+                ++gf;
+                if (++cf == nch) { cf = 0; ++tf; }
+                if (++sf == ns) sf = 0;
+            };
+            issue_in(0);
+            for (int i = 0; i < ns; ++i) feed();
+            int s = 0;
+            uint32_t phs = 0;
+            for (int t = 0; t < nloc; ++t) {
+                const int row0 = (bbase + t * bstride) * R2_RB;
+                mbar_wait(barINfree, (uint32_t)t & 1u);
+                if (t + 1 < nloc) issue_in(t + 1);
+                if (useF && P.pf_dist > 0 && t + P.pf_dist < nloc)   // F of a later block on its way into L2
+                    for (int c = 0; c < nch; ++c) tma_prefetch_3d(&P.mapF3, (bbase + (t + P.pf_dist) * bstride) * R2_RB, k0, DC * c);
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(barR + s, phs);            // the results of chunk (t, c) are in slot s
+                    tma_store_3d(&P.mapX3, row0, k0, DC * c, RING + s * CBD);
+                    tma_commit();
+                    if (++s == ns) { s = 0; phs ^= 1u; }
+                    if (t > 0 || c > 0) {                // the previous store has left its slot: reuse it
+                        tma_wait_read<1>();
+                        feed();
+                    }
+                }
+            }
+            tma_wait_all();
+        }
+        __syncwarp();
+        if (tid >= R2_COMPUTE_SLOTS + 32 && tid < R2_COMPUTE_SLOTS + 96) {
+            // =========================== two hat warps ===========================================================
+            // The two bidiagonal recurrences of the hat block (src/arrowhead.jl:453, :472) for the 8 rows of the block:
+            // each warp takes 4 rows, lane = seg*4 + row, segment seg of 8 owns the hats [seg*lp, (seg+1)*lp) (tables padded
+            // with zeros).  Both recurrences h_i = y_i - c_i h_next are affine in the incoming value: every segment builds
+            // its map (A, B), the maps are composed across the 8 segments by shuffles, then the segment re-runs with the
+            // exact incoming value -- and builds the map of the second recurrence in the same pass.  (These warps run
+            // on 32 registers: the compute warps need the rest.)
+            const int lane = tid & 31, rr = (lane & 3) + 4 * ((tid - R2_COMPUTE_SLOTS - 32) >> 5), seg = lane >> 2;
+            const int lp = P.lp;
+            double *col = HF + R2_RB + rr + seg * lp * R2_RB;
+            const double *cd = hcd + seg * lp, *cu = hcu + seg * lp, *rdp = hrd + seg * lp;
+            for (int t = 0; t < nloc; ++t) {
+                named_bar_sync(R2_BAR_HATS, nthr + 64);
+                // pass 1, descending: map of h_i = ytil_i - cd_i h_{i+1}
+                double A = 1.0, Bv = 0.0;
+                for (int i0 = lp - 4; i0 >= 0; i0 -= 4) {
+                    double y[4], c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        y[u] = col[(i0 + 3 - u) * R2_RB];
+                        c[u] = cd[i0 + 3 - u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        Bv = fma(-c[u], Bv, y[u]);
+                        A *= -c[u];
+                    }
+                }
+                double inc = 0.0;
+                {
+                    double res = 0.0;   // value leaving the segments above, built from the top
+#pragma unroll
+                    for (int s2 = 7; s2 >= 0; --s2) {
+                        const double As = __shfl_sync(POP_FULL_MASK, A, s2 * 4 + (lane & 3)), Bs = __shfl_sync(POP_FULL_MASK, Bv, s2 * 4 + (lane & 3));
+                        if (s2 == seg) inc = res;
+                        res = fma(As, res, Bs);
+                    }
+                }
+                // pass 2, descending: the final h_i; at the same time the map of the ascending recurrence
+                // x_i = h_i rd_i - cu_i x_{i-1}, composed from the top:  G <- G o f_i,  f_i(x) = h_i rd_i - cu_i x
+                double h = inc;
+                A = 1.0;
+                Bv = 0.0;
+                for (int i0 = lp - 2; i0 >= 0; i0 -= 2) {
+                    double y[2], c[2], c2[2], rd[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        y[u] = col[(i0 + 1 - u) * R2_RB];
+                        c[u] = cd[i0 + 1 - u];
+                        c2[u] = cu[i0 + 1 - u];
+                        rd[u] = rdp[i0 + 1 - u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        h = fma(-c[u], h, y[u]);
+                        col[(i0 + 1 - u) * R2_RB] = h;
+                        Bv = fma(A, h * rd[u], Bv);
+                        A *= -c2[u];
+                    }
+                }
+                {
+                    double res = 0.0;   // value entering from the segments below, built from the bottom
+                    inc = 0.0;
+#pragma unroll
+                    for (int s2 = 0; s2 < 8; ++s2) {
+                        const double As = __shfl_sync(POP_FULL_MASK, A, s2 * 4 + (lane & 3)), Bs = __shfl_sync(POP_FULL_MASK, Bv, s2 * 4 + (lane & 3));
+                        if (s2 == seg) inc = res;
+                        res = fma(As, res, Bs);
+                    }
+                }
+                // pass 3, ascending: the final x_i
+                h = inc;
+                for (int i0 = 0; i0 < lp; i0 += 4) {
+                    double y[4], c2[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        y[u] = col[(i0 + u) * R2_RB] * rdp[i0 + u];
+                        c2[u] = cu[i0 + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        h = fma(-c2[u], h, y[u]);
+                        col[(i0 + u) * R2_RB] = h;
+                    }
+                }
+                __syncwarp();
+                named_bar_sync(R2_BAR_HATS, nthr + 64);
+            }
+        }
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+      if (tid < nthr) {
+        // =========================== compute threads ============================================================
+        const int par = tid / (mlc * R2_RB);          // 0 / 1
+        const int tp = tid - par * mlc * R2_RB;
+        const int e = tp / R2_RB, r = tp % R2_RB;
+        const int k = k0 + e;
+        // 32-bit shared addresses of this thread's entries: one base register, the rest are immediates when MLC > 0
+        const uint32_t sbase = smem_u32(r2_raw);
+        const uint32_t off_er = sbase + (uint32_t)(((par * mlc + e) * R2_RB + r) * 8);   // (parity, element, row) inside a [degree][element][row] box
+        const uint32_t dstride = (uint32_t)(2 * mlc * R2_RB * 8);                       // two degrees further
+        const uint32_t a_tab = sbase + LF.tab + par * 16, a_ttab = sbase + LF.ttab + par * 16, a_ftab = sbase + LF.ftab + par * 16;
+        const uint32_t a_in = off_er + LF.in, a_ring = off_er + LF.ring;
+        const uint32_t a_ss = sbase + LF.ss + (par * 3 * mlc + e) * 8, a_st = sbase + LF.st + (par * 3 * mlc + e) * 8;
+        const uint32_t a_hf = sbase + P.o_hf + (k * R2_RB + r) * 8;
+        int s = 0;             // ring slot of the next chunk
+        uint32_t phs = 0;      // its phase
+        for (int t = 0; t < nloc; ++t) {
+            const int pb = t & 1;
+            const uint32_t phMB = (uint32_t)(t >> 1) & 1u;
+            const int row0 = (bbase + t * bstride) * R2_RB;
+            const double *inh = INH + pb * HBS, *fh = FH + pb * HBS;
+            double *mbme = MB + ((size_t)pb * cs + rank) * mbw;
+            // ---- A: the row block, shared memory -> registers --------------------------------------------------
+            R2_STAMP(0);
+            mbar_wait(barIN, (uint32_t)t & 1u);
+            R2_STAMP(1);
+            double z[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) z[i] = (MLC || (2 * i + par) < DC * nch) ? lds_f64(a_in + (uint32_t)i * dstride) : 0.0;   // degrees >= q arrive as zeros (TMA fill)
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(barINfree);
+            // ---- B: backward sweep  z_j = (b_j - w2_j z_{j+2}) rd_j ; couplings of my elements to the hats ------
+            R2_STAMP(2);
+            {
+                double2 ca = lds_v2f64(a_tab + (CH - 1) * 32), cb = lds_v2f64(a_tab + (CH - 2) * 32);   // coefficients two steps ahead
+#pragma unroll
+                for (int i = CH - 1; i >= 0; --i) {
+                    const double2 cf = ca;
+                    ca = cb;
+                    if (i >= 2) cb = lds_v2f64(a_tab + (i - 2) * 32);
+                    double v = z[i];
+                    if (i + 1 < CH) v = fma(-cf.y, z[i + 1], v);
+                    z[i] = v * cf.x;
+                }
+            }
+            {
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int b = 2 * ii + par;
+                    const uint32_t sb = a_ss + ii * 6 * mlc * 8;
+                    c0 = fma(lds_f64(sb), z[ii], c0);
+                    c1 = fma(lds_f64(sb + mlc * 8), z[ii], c1);
+                    c2 = fma(lds_f64(sb + 2 * mlc * 8), z[ii], c2);
+                    // the backward-swept coupled bubbles of my two edge elements travel with the message
+                    if (e == 0) mbme[(mlc + 2) * R2_RB + (0 * R2_NBMAX + b) * R2_RB + r] = z[ii];
+                    if (e == mlc - 1) mbme[(mlc + 2) * R2_RB + (1 * R2_NBMAX + b) * R2_RB + r] = z[ii];
+                }
+                // the couplings of both parities of an (element, row) are summed in shared memory: odd degrees first
+                if (par == 1) {
+                    ct[(0 * mlc + e) * R2_RB + r] = c0;
+                    ct[(1 * mlc + e) * R2_RB + r] = c1;
+                    ct[(2 * mlc + e) * R2_RB + r] = c2;
+                }
+                named_bar_sync(R2_BAR_COMPUTE, nthr);
+                if (par == 0) {
+                    ct[(0 * mlc + e) * R2_RB + r] += c0;
+                    ct[(1 * mlc + e) * R2_RB + r] += c1;
+                    ct[(2 * mlc + e) * R2_RB + r] += c2;
+                }
+            }
+            named_bar_sync(R2_BAR_COMPUTE, nthr);
+            // ---- C: my message: hat right-hand sides minus the couplings of MY elements, for hats k0-1 .. k0+mlc --
+            R2_STAMP(3);
+            if (tid < (mlc + 2) * R2_RB) {
+                const int u = tid / R2_RB - 1, rr = tid % R2_RB;
+                double v = (u >= 0 && u < nhl) ? inh[u * R2_RB + rr] : 0.0;
+#pragma unroll
+                for (int tt = 0; tt < 3; ++tt) {
+                    const int el = u + 1 - tt;   // slot tt of element el couples to hat el + tt - 1
+                    if (el >= 0 && el < mlc) v -= ct[(tt * mlc + el) * R2_RB + rr];
+                }
+                mbme[tid] = v;
+            }
+            if (cs > 1) {
+                fence_proxy_async();
+                named_bar_sync(R2_BAR_COMPUTE, nthr);
+                if (tid < cs && tid != rank) dsmem_bulk_copy(mapa_u32(mbme, tid), mbme, (uint32_t)(mbw * 8), mapa_u32(barMB + pb, tid));
+                if (tid == 0) mbar_expect_tx(barMB + pb, (uint32_t)(mbw * 8 * (cs - 1)));
+                mbar_wait_cluster(barMB + pb, phMB);
+            } else {
+                named_bar_sync(R2_BAR_COMPUTE, nthr);
+            }
+            // ---- D: the whole hat system of the 8 rows, redundantly in every CTA ---------------------------------
+            R2_STAMP(4);
+            {
+                const double *mbp = MB + (size_t)pb * cs * mbw;
+                for (int x = tid; x < nh * R2_RB; x += nthr) {
+                    const int i = x / R2_RB, rr = x % R2_RB;
+                    const int c = min(i / mlc, cs - 1), u = i - c * mlc;
+                    double v = mbp[c * mbw + (u + 1) * R2_RB + rr];
+                    if (u == 0 && c > 0) v += mbp[(c - 1) * mbw + (mlc + 1) * R2_RB + rr];
+                    if (u == mlc - 1 && c < cs - 1) v += mbp[(c + 1) * mbw + rr];
+                    HF[(i + 1) * R2_RB + rr] = v * hrd[i];
+                }
+            }
+            R2_STAMP(5);
+            named_bar_sync(R2_BAR_HATS, nthr + 64);   // the right-hand sides are assembled: the hat warps take over
+            named_bar_sync(R2_BAR_HATS, nthr + 64);   // ... and have solved the hat systems of the 8 rows
+            // ---- E: correct the coupled bubbles (:475-477), forward sweep (:480-482), product, output ------------
+            R2_STAMP(6);
+            const double h0 = lds_f64(a_hf), h1 = lds_f64(a_hf + R2_RB * 8), h2 = lds_f64(a_hf + 2 * R2_RB * 8);
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const uint32_t sb = a_ss + ii * 6 * mlc * 8;
+                double v = z[ii];
+                v = fma(-lds_f64(sb), h0, v);
+                v = fma(-lds_f64(sb + mlc * 8), h1, v);
+                v = fma(-lds_f64(sb + 2 * mlc * 8), h2, v);
+                z[ii] = v;
+            }
+            {
+                double2 ca = lds_v2f64(a_ftab), cb = lds_v2f64(a_ftab + 32);   // (rd_j, w2_{j-2}) two steps ahead
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const double2 cf = ca;
+                    ca = cb;
+                    if (i + 2 < CH) cb = lds_v2f64(a_ftab + (i + 2) * 32);
+                    double v = z[i];
+                    if (i >= 1) v = fma(-cf.y, z[i - 1], v);
+                    z[i] = v * cf.x;
+                }
+            }
+            double *xb = ct;   // [4][mlc][8]: x of the coupled bubbles, for the hat rows of the product
+            if (mul) {
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) xb[((2 * ii + par) * mlc + e) * R2_RB + r] = z[ii];
+            }
+            // chunk cc holds the chain entries i = cc*DC/2 .. (cc+1)*DC/2 - 1 (registers are indexed statically)
+            R2_STAMP(7);
+#pragma unroll
+            for (int cc = 0; cc < (2 * CH + DC - 1) / DC; ++cc) {
+                if (cc < nch) {
+                    const uint32_t slot = a_ring + s * (uint32_t)(CBD * 8);
+                    // this chunk's product coefficients (t0_j, t2_j), t2_{j-2}: loaded before the wait for F
+                    double2 tc[DC / 2];
+                    double tm[DC / 2];
+                    if (mul) {
+#pragma unroll
+                        for (int i4 = 0; i4 < DC / 2; ++i4) {
+                            const int i = (DC / 2) * cc + i4;
+                            if (i < CH) {
+                                tc[i4] = lds_v2f64(a_ttab + i * 32);
+                                tm[i4] = i >= 1 ? lds_v2f64(a_ttab + (i - 1) * 32).y : 0.0;
+                            }
+                        }
+                    }
+                    mbar_wait(barF + s, phs);      // F of this chunk has landed / the slot is free
+#pragma unroll
+                    for (int i4 = 0; i4 < DC / 2; ++i4) {
+                        const int i = (DC / 2) * cc + i4;
+                        if (i < CH) {
+                            const uint32_t sp = slot + i4 * dstride;
+                            double out;
+                            if (mul) {
+                                double acc = tc[i4].x * z[i];
+                                if (i + 1 < CH) acc = fma(tc[i4].y, z[i + 1], acc);
+                                if (i >= 1) acc = fma(tm[i4], z[i - 1], acc);
+                                if (i < 2) {
+                                    const uint32_t tb = a_st + i * 6 * mlc * 8;
+                                    acc = fma(lds_f64(tb), h0, acc);
+                                    acc = fma(lds_f64(tb + mlc * 8), h1, acc);
+                                    acc = fma(lds_f64(tb + 2 * mlc * 8), h2, acc);
+                                }
+                                out = useF ? fma(P.gamma, lds_f64(sp), acc) : acc;
+                            } else {
+                                out = z[i];
+                            }
+                            sts_f64(sp, out);
+                        }
+                    }
+                    fence_proxy_async();           // my writes are visible to the TMA store
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(barR + s);
+                    if (++s == ns) { s = 0; phs ^= 1u; }
+                }
+            }
+            R2_STAMP(8);
+            named_bar_sync(R2_BAR_COMPUTE, nthr);   // xb complete
+            // hat rows: x = h (plain solve) or T_A h + sum_b T_b x_b + gamma f, for my hats
+            if (tid < nhl * R2_RB) {
+                const int u = tid / R2_RB, rr = tid % R2_RB, i = hA + u;
+                const int64_t rw = (int64_t)row0 + rr;
+                const double hc = HF[(i + 1) * R2_RB + rr];
+                double out = hc;
+                if (mul) {
+                    const double hp = HF[i * R2_RB + rr], hn = HF[(i + 2) * R2_RB + rr];
+                    double acc = P.TAd[i] * hc;
+                    if (i + 1 < nh) acc = fma(P.TAu[i], hn, acc);
+                    if (i > 0) acc = fma(P.TAu[i - 1], hp, acc);
+                    const double *mbp = MB + (size_t)pb * cs * mbw;
+#pragma unroll
+                    for (int tt = 0; tt < 3; ++tt) {
+                        const int el = u + 1 - tt, kk = k0 + el;   // slot tt of element kk couples to hat i
+                        if (kk < 0 || kk >= m) continue;
+                        if (el >= 0 && el < mlc) {
+                            for (int b = 0; b < P.nbT; ++b) acc = fma(sT[(b * 3 + tt) * mlc + el], xb[(b * mlc + el) * R2_RB + rr], acc);
+                        } else {
+                            // an edge element of a neighbour CTA: its x_b follow from its backward-swept z_b (in the
+                            // neighbour's message) and the hats, exactly as its owner computes them
+                            const int nbr = el < 0 ? rank - 1 : rank + 1, side = el < 0 ? 1 : 0;
+                            const double *zz = mbp + nbr * mbw + (mlc + 2) * R2_RB + side * R2_NBMAX * R2_RB + rr;
+                            const double g0 = HF[kk * R2_RB + rr], g1 = HF[(kk + 1) * R2_RB + rr], g2 = HF[(kk + 2) * R2_RB + rr];
+                            double xs[R2_NBMAX];
+#pragma unroll
+                            for (int b = 0; b < R2_NBMAX; ++b) {
+                                double v = zz[b * R2_RB];
+                                if (b < P.nb) {
+                                    const double *sg = P.S + (size_t)b * 3 * m + kk;
+                                    v = fma(-__ldg(sg), g0, v);
+                                    v = fma(-__ldg(sg + m), g1, v);
+                                    v = fma(-__ldg(sg + 2 * m), g2, v);
+                                }
+                                if (b >= 2) v = fma(-tab[b - 2].y, xs[b - 2], v);
+                                xs[b] = v * tab[b].x;
+                            }
+#pragma unroll
+                            for (int b = 0; b < R2_NBMAX; ++b)
+                                if (b < P.nbT) acc = fma(__ldg(P.Ts + ((size_t)b * 3 + tt) * m + kk), xs[b], acc);
+                        }
+                    }
+                    out = useF ? fma(P.gamma, fh[u * R2_RB + rr], acc) : acc;
+                }
+                if (rw < P.nrows) P.X[rw + (int64_t)i * P.ld] = out;
+            }
+            named_bar_sync(R2_BAR_COMPUTE, nthr);   // HF, ct / xb and the mailboxes of this parity are rewritten by later blocks
+            R2_STAMP(9);
+        }
+      }
+    }
+    __syncthreads();
+    if (cs > 1) {   // no CTA exits while a peer may still send into its shared memory
+        cluster_arrive();
+        cluster_wait();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_t r2_encoder() {
+    static encode_tiled_t fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_t>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+static int r2_env(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// bubbles of a panel as (row, element, degree), hats as (row, hat); boxes (8, mlc, 8) and (8, mlc + 1)
+static bool r2_make_maps(encode_tiled_t enc, const double *base, int64_t ld, int64_t nrows, int m, int nh, int q, int mlc, int dc, CUtensorMap *m3, CUtensorMap *mh) {
+    const CUtensorMapL2promotion promo = r2_env("POP_ROW2_L2PROMO", 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)nrows, (cuuint64_t)m, (cuuint64_t)q};
+        cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)ld * 8 * (cuuint64_t)m};
+        cuuint32_t box[3] = {R2_RB, (cuuint32_t)mlc, (cuuint32_t)dc};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc(m3, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)(base + (int64_t)nh * ld), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)nrows, (cuuint64_t)std::max(nh, 1)};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+        cuuint32_t box[2] = {R2_RB, (cuuint32_t)(mlc + 1)};
+        cuuint32_t es[2] = {1, 1};
+        if (enc(mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+typedef void (*r2_kernel_t)(const R2Params);
+static r2_kernel_t r2_kernel(int ch, int dc, int mlc) {
+    if (mlc == 32 && ch == 32) return dc == 8 ? k_row2<32, 8, 32> : k_row2<32, 4, 32>;   // the ADI shapes (m = 128: cluster of 4, m = 256: of 8)
+    switch (ch) {
+        case 8: return dc == 8 ? k_row2<8, 8, 0> : k_row2<8, 4, 0>;
+        case 16: return dc == 8 ? k_row2<16, 8, 0> : k_row2<16, 4, 0>;
+        case 24: return dc == 8 ? k_row2<24, 8, 0> : k_row2<24, 4, 0>;
+        case 32: return dc == 8 ? k_row2<32, 8, 0> : k_row2<32, 4, 0>;
+    }
+    return nullptr;
+}
+
+static int r2_align(int x, int a) { return (x + a - 1) / a * a; }
+
+// POP_OK, an error, or POP_ROW1_UNSUPPORTED (the caller falls back to the older row kernels)
+int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R) {
+    if (op.world != 1 || r2_env("POP_ROW2", 1) == 0) return POP_ROW1_UNSUPPORTED;
+    const bool strict = r2_env("POP_ROW2_STRICT", 0) != 0;
+    auto unsupported = [&](const char *why) -> int {
+        if (strict) {
+            pop_set_error("pop_row2: %s (m=%d q=%d nh=%d)", why, op.m, op.q, op.nh);
+            return POP_ERR_DIM;
+        }
+        return POP_ROW1_UNSUPPORTED;
+    };
+    if (op.has1) return unsupported("the first super-diagonal of a D block is not zero");
+    if (op.q < 2 || op.q > 64 || op.nb > R2_NBMAX || op.nbT > R2_NBMAX) return unsupported("chain length / coupling blocks out of range");
+    if ((op.ld & 1) || ((uintptr_t)R & 15)) return unsupported("panel not 16-byte aligned with an even leading dimension");
+    const bool useF = op.nbT >= 0 && F != nullptr && op.gamma != 0.0;
+    if (useF && ((op.ldf & 1) || ((uintptr_t)F & 15))) return unsupported("F not 16-byte aligned with an even leading dimension");
+    encode_tiled_t enc = r2_encoder();
+    if (!enc) return unsupported("cuTensorMapEncodeTiled is not available");
+    const int ch = op.q <= 16 ? 8 : op.q <= 32 ? 16 : op.q <= 48 ? 24 : 32;
+    const int want_cs = r2_env("POP_ROW2_CS", 0);
+    int cs = 0;
+    for (int c = 1; c <= R2_MAXCS; c <<= 1) {
+        if (want_cs && c != want_cs) continue;
+        if (op.m % c) continue;
+        const int mlc = op.m / c;
+        if (mlc < 1 || 16 * mlc > 512) continue;
+        if (c > 1 && mlc < 2) continue;
+        cs = c;
+        break;
+    }
+    if (!cs) return unsupported("no cluster size with m % cs == 0 and 16 * m / cs <= 512 threads");
+    const int mlc = op.m / cs;
+    if (mlc + 1 > 256) return unsupported("hat box too wide");
+    const int nthr = 16 * mlc;
+    if (nthr % 32) return unsupported("elements per CTA must be even");   // whole warps: the named barrier and the hat scan need them
+    R2Params P;
+    memset(&P, 0, sizeof(P));
+    P.mbw = (mlc + 2) * R2_RB + 2 * R2_NBMAX * R2_RB;
+    const int lp = (((op.nh + 7) / 8) + 3) & ~3;            // hats per scan segment (8 segments), a multiple of 4
+    const int hf_rows = std::max(8 * lp + 2, op.m + 3);
+    // behind the ring: HF, the padded hat tables, the mailboxes
+    const int tail = r2_align(hf_rows * R2_RB * 8, 128) + 3 * r2_align(8 * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
+    // chunks of 8 degrees if four ring slots of that size fit, else chunks of 4
+    int dc = 0, nch = 0, ns = 0;
+    R2Fixed LF = {};
+    const int want_dc = r2_env("POP_ROW2_DC", 0);
+    for (int cand = 8; cand >= 4 && !dc; cand >>= 1) {
+        if (want_dc && cand != want_dc) continue;
+        const R2Fixed f = r2_fixed(ch, cand, mlc);
+        const int left = ctx->max_smem_optin - f.ring - tail;
+        const int slots = left >= 0 ? std::min(left / f.cb, R2_NS_MAX) : 0;
+        if (slots >= (cand == 8 ? 4 : 3)) { dc = cand; nch = (op.q + cand - 1) / cand; ns = slots; LF = f; }
+    }
+    if (!dc) return unsupported("shared memory too small for the row block and the ring");
+    if (const int w = r2_env("POP_ROW2_NS", 0)) ns = std::max(3, std::min(ns, w));
+    P.ns = ns;
+    int o = LF.ring + ns * LF.cb;
+    P.o_hf = o; o += r2_align(hf_rows * R2_RB * 8, 128);
+    P.o_hrd = o; o += r2_align(8 * lp * 8, 128);
+    P.o_hcd = o; o += r2_align(8 * lp * 8, 128);
+    P.o_hcu = o; o += r2_align(8 * lp * 8, 128);
+    P.o_mb = o; o += r2_align(2 * cs * P.mbw * 8, 128);
+    P.total = o;
+    if ((size_t)P.total > (size_t)ctx->max_smem_optin) return unsupported("shared memory too small");
+    P.lp = lp;
+    P.hf_rows = hf_rows;
+    P.pf_dist = r2_env("POP_ROW2_PF", 0);   // L2 prefetch distance of F in row blocks (0: off)
+
+    if (!r2_make_maps(enc, R, op.ld, op.nrows, op.m, op.nh, op.q, mlc, dc, &P.mapX3, &P.mapXh)) return unsupported("cuTensorMapEncodeTiled rejected the panel");
+    if (useF) {
+        if (!r2_make_maps(enc, F, op.ldf, op.nrows, op.m, op.nh, op.q, mlc, dc, &P.mapF3, &P.mapFh)) return unsupported("cuTensorMapEncodeTiled rejected F");
+    } else {
+        P.mapF3 = P.mapX3;
+        P.mapFh = P.mapXh;
+    }
+    P.rd = op.rd; P.w2 = op.w2; P.S = op.S; P.rdA = op.rdA; P.offA = op.offA; P.nb = op.nb;
+    P.t0 = op.t0; P.t2 = op.t2; P.Ts = op.Ts; P.TAd = op.TAd; P.TAu = op.TAu; P.nbT = op.nbT;
+    P.gamma = op.gamma;
+    P.useF = useF ? 1 : 0;
+    P.X = R; P.F = F; P.ld = op.ld; P.ldf = op.ldf; P.nrows = op.nrows;
+    P.m = op.m; P.nh = op.nh; P.q = op.q;
+    P.cs = cs; P.mlc = mlc; P.nch = nch;
+    P.nblk = (int)((op.nrows + R2_RB - 1) / R2_RB);
+
+    r2_kernel_t kern = r2_kernel(ch, dc, mlc);
+    POP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.total));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(640);   // 512 compute slots (16 mlc of them work) + the TMA producer warp group
+    cfg.dynamicSmemBytes = (size_t)P.total;
+    cfg.stream = ctx->stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static std::mutex plan_mu;
+    static int cached_key[5] = {0, 0, 0, 0, -1}, cached_ncl = 0;
+    const int key[5] = {ch * 16 + dc + (mlc == 32 ? 1024 : 0), cs, nthr, P.total, ctx->device};
+    int ncl;
+    {
+        std::lock_guard<std::mutex> lk(plan_mu);
+        ncl = cached_ncl;
+        if (!std::equal(key, key + 5, cached_key) || ncl <= 0) {
+            cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count));
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, (const void *)kern, &cfg) != cudaSuccess || nc <= 0) {
+                cudaGetLastError();
+                return unsupported("no co-resident cluster");
+            }
+            ncl = nc;
+            std::copy(key, key + 5, cached_key);
+            cached_ncl = ncl;
+        }
+    }
+    if (const int cap = r2_env("POP_ROW2_NCL", 0)) ncl = std::min(ncl, cap);
+    ncl = std::min(ncl, P.nblk);
+    P.pairing = (ncl >= 2 && r2_env("POP_ROW2_PAIR", 1)) ? 1 : 0;
+    if (P.pairing) ncl &= ~1;
+    cfg.gridDim = dim3((unsigned)(ncl * cs));
+    if (r2_env("POP_ROW2_VERBOSE", 0))
+        fprintf(stderr, "pop_row2: chain %d per thread, cluster %d x %d threads, %d B smem, ring %d slots of %d degrees, %d clusters, %d row blocks, F %d\n", ch, cs, nthr, P.total, ns, dc, ncl,
+                P.nblk, P.useF);
+    long long *dbg = nullptr;
+    if (r2_env("POP_ROW2_TRACE", 0)) {
+        POP_CUDA(cudaMalloc(&dbg, 64 * 10 * sizeof(long long)));
+        POP_CUDA(cudaMemset(dbg, 0, 64 * 10 * sizeof(long long)));
+        P.dbg = dbg;
+    }
+    POP_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    ctx->launches++;
+    if (dbg) {   // debugging aid: phase durations of CTA 0 in SM clock cycles
+        long long h[64 * 10];
+        POP_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        static const char *names[8] = {"wait IN", "IN->regs", "backward", "msg+exchange", "assemble", "hat scan", "corr+fwd", "chunks"};
+        double sum[10] = {0};
+        int nb = 0;
+        for (int t = 2; t < 64 && h[t * 10 + 9]; ++t, ++nb) {
+            for (int i = 0; i < 9; ++i) sum[i] += (double)(h[t * 10 + i + 1] - h[t * 10 + i]);
+        }
+        if (nb) {
+            fprintf(stderr, "pop_row2 trace (CTA 0, thread 0, mean SM cycles over %d row blocks):", nb);
+            for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %.0f |", names[i], sum[i] / nb);
+            fprintf(stderr, " hat rows + end %.0f | block %.0f\n", sum[8] / nb, (double)(h[(2 + nb - 1) * 10 + 9] - h[2 * 10]) / nb);
+        }
+    }
+    return POP_OK;
+}

@@ -526,6 +526,7 @@ def test_rdiv_one_pass_general_bands(lower, monkeypatch):
     R = rng.standard_normal((21, Ao.n))
     want = np.linalg.solve(Ssym, R.T).T
     monkeypatch.setenv("POP_ROW1_STRICT", "1")
+    monkeypatch.setenv("POP_ROW2", "0")           # this test is about csrc/pop_row1.cuh
     for cs in ("1", "0"):
         monkeypatch.setenv("POP_ROW1_CS", cs)
         assert relerr(host(P.rdiv(dev(R), F, algo=P.SOLVE_FUSED)), want) < 1e-11
@@ -560,6 +561,7 @@ def test_one_pass_row_half_step(basis, m, N, cs, rb, monkeypatch):
     Fd.copy_(torch.from_numpy(Fm).cuda())
     _bind_stream(M.data.ctx)
     got = {}
+    monkeypatch.setenv("POP_ROW2", "0")           # this test is about csrc/pop_row1.cuh (k_row2 has its own below)
     for mode in ("one-pass", "one-pass-direct-f", "one-pass-unsplit", "two-pass"):
         monkeypatch.setenv("POP_ROW1", "0" if mode == "two-pass" else "2")    # 2: also for the half step with the product
         monkeypatch.setenv("POP_ROW1_NPAR", "1" if mode == "one-pass-unsplit" else "2")   # 2: even/odd degree chains on two threads
@@ -579,6 +581,60 @@ def test_one_pass_row_half_step(basis, m, N, cs, rb, monkeypatch):
     assert relerr(got["one-pass"], got["two-pass"]) < 1e-13
     assert relerr(got["one-pass-unsplit"], got["two-pass"]) < 1e-13
     assert np.array_equal(got["one-pass"], got["one-pass-direct-f"])
+    dd.close()
+
+
+@pytest.mark.parametrize("basis,m,N,cs", [
+    ("dirichlet", 8, 12, 1), ("dirichlet", 8, 12, 2), ("dirichlet", 8, 12, 4), ("c1", 8, 9, 4), ("c1", 8, 9, 1), ("dirichlet", 16, 9, 8),
+    ("dirichlet", 12, 20, 2), ("c1", 6, 21, 1), ("dirichlet", 8, 40, 4), ("c1", 4, 64, 2), ("dirichlet", 8, 65, 4), ("dirichlet", 6, 33, 1),
+    ("dirichlet", 32, 17, 1), ("c1", 32, 5, 2), ("dirichlet", 64, 7, 8), ("c1", 16, 3, 2)])
+def test_single_pass_tma_row_half_step(basis, m, N, cs, monkeypatch):
+    """csrc/pop_row2.cu (k_row2): the single-pass row half step with TMA tensor traffic and the cluster-wide hat broadcast,
+    for every chain class and cluster size: half step with product and gamma F, product alone, plain X / F
+    (examples/adi_poisson.jl:54), against the oracle's dense algebra and the two-pass row kernels of pop_row.cu."""
+    from pop_b200 import _lib as L
+    from pop_b200.arrowhead import _bind_stream
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    n = Mo.n
+    rng = np.random.default_rng(12)
+    Rm, Fm = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    if basis == "c1":
+        Kd = Kd + 0.3 * Md
+        K = K + 0.3 * M
+    Sd, Td = Kd + 3.7 * Md, 0.5 * Md - Kd
+    Xd = np.linalg.solve(Sd, Rm.T).T
+    dd = P.ElementDecomposition(M)
+    Fs = P.reversecholesky(K + 3.7 * M)
+    T = 0.5 * M - K
+    R, Fd = dd.panel(), dd.panel()
+    Fd.copy_(torch.from_numpy(Fm).cuda())
+    ctx = M.data.ctx
+    _bind_stream(ctx)
+    got = {}
+    for mode in ("tma", "tma4", "two-pass"):
+        monkeypatch.setenv("POP_ROW2", "0" if mode == "two-pass" else "1")
+        monkeypatch.setenv("POP_ROW2_DC", "4" if mode == "tma4" else "8")     # degrees per TMA box / ring slot
+        monkeypatch.setenv("POP_ROW2_NS", "3" if mode == "tma4" else "0")     # the shortest ring
+        monkeypatch.setenv("POP_ROW1", "0")
+        monkeypatch.setenv("POP_ROW2_CS", str(cs))
+        monkeypatch.setenv("POP_ROW2_STRICT", "1")    # the forced plan must apply: no silent fallback
+        for what, Top, gamma, Fp, want in (("half step", T, -0.4, Fd, Xd @ Td - 0.4 * Fm), ("product", T, 0.0, None, Xd @ Td), ("solve", None, 0.0, None, Xd)):
+            R.copy_(torch.from_numpy(Rm).cuda())
+            L.check(L.lib().pop_dd_row_half_step(ctx.handle, dd._h, Fs.factor._h, Top.data._h if Top is not None else None, gamma,
+                                                 Fp.data_ptr() if Fp is not None else None, Fp.stride(1) if Fp is not None else 0, R.data_ptr(), R.stride(1)))
+            torch.cuda.synchronize()
+            got[mode, what] = host(R)
+            assert relerr(got[mode, what], want) < TOL, (mode, what)
+    for what in ("half step", "product", "solve"):
+        assert relerr(got["tma", what], got["two-pass", what]) < 1e-13, what
+        assert np.array_equal(got["tma", what], got["tma4", what]), what
+    # the same kernel behind pop_solve(side = RIGHT) on a row panel with fewer rows than columns (ragged last row block)
+    monkeypatch.setenv("POP_ROW2", "1")
+    Rp = rng.standard_normal((13, n))
+    assert relerr(host(P.rdiv(dev(Rp), Fs, algo=P.SOLVE_FUSED)), np.linalg.solve(Sd, Rp.T).T) < TOL
     dd.close()
 
 
