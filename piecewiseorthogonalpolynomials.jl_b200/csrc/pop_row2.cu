@@ -50,7 +50,7 @@ struct R2Params {
     const double *F;
     int64_t ld, ldf, nrows;
     int m, nh, q;
-    int cs, mlc, nch, ns, nblk, pf_dist;
+    int cs, mlc, nch, nblk, pf_dist;
     int pairing;                   // clusters 2p and 2p+1 work on the row blocks 2b and 2b+1 at the same time (the two halves of every 128 B line)
     int hf_rows;                   // rows of HF: entry 0, the hats, zero pads up to 4*lp+1 and m+2
     int lp;                        // hats per scan segment (8 segments; tables and HF are padded to 8*lp)
@@ -99,7 +99,7 @@ __host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc) {
     const int nchmax = (2 * ch + dc - 1) / dc;
     f.cb = dc * mlc * R2_RB * 8;
     f.hbs = r2_al((mlc + 1) * R2_RB * 8);
-    int o = 256;                                 // mbarriers
+    int o = 1024;                                // mbarriers
     f.in = o; o += nchmax * f.cb;
     f.inh = o; o += 2 * f.hbs;
     f.fh = o; o += 2 * f.hbs;
@@ -139,13 +139,15 @@ template <int CH, int DC, int MLC>
 __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Params P) {
     extern __shared__ __align__(128) unsigned char r2_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(r2_raw);
-    uint64_t *barIN = bars;            // the row block has landed (producer arrive + bytes)
-    uint64_t *barINfree = bars + 1;    // every compute thread has copied its part of the row block into registers
+    constexpr int NCM = (2 * CH + DC - 1) / DC;   // chunk regions of the row block buffer
+    uint64_t *barH = bars;             // [2] the hats of a block (and of F) have landed (by block parity)
     uint64_t *barMB = bars + 2;        // [2] the peers' messages of a block (by block parity)
-    uint64_t *barF = bars + 4;         // [ns] slot holds F of its chunk (bytes), or is free for output (producer arrive)
-    uint64_t *barR = bars + 4 + R2_NS_MAX;   // [ns] every compute thread has written its results into the slot
+    uint64_t *barX = bars + 4;         // [NCM] chunk c of the row block has landed (bytes)
+    uint64_t *barXfree = barX + NCM;   // [NCM] every compute warp has taken chunk c into registers: its region is free
+    uint64_t *barF = barXfree + NCM;   // [NCM] F of chunk c has landed in region c (bytes)
+    uint64_t *barR = barF + NCM;       // [NCM] every compute warp has written its results of chunk c into region c
     const int tid = threadIdx.x;
-    const int cs = P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch, ns = P.ns;
+    const int cs = P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch;
     const int nthr = 16 * mlc;         // compute threads
     const R2Fixed LF = r2_fixed(CH, DC, mlc);   // compile-time constants when MLC > 0
     const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
@@ -155,7 +157,6 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     double *IN = reinterpret_cast<double *>(r2_raw + LF.in);
     double *INH = reinterpret_cast<double *>(r2_raw + LF.inh);     // [2][(mlc+1)*8]
     double *FH = reinterpret_cast<double *>(r2_raw + LF.fh);       // [2][(mlc+1)*8]
-    double *RING = reinterpret_cast<double *>(r2_raw + LF.ring);   // [ns][DC][mlc][8]
     double *MB = reinterpret_cast<double *>(r2_raw + P.o_mb);       // [2][cs][mbw]
     double *HF = reinterpret_cast<double *>(r2_raw + P.o_hf);       // [m+3][8], entry i+1 = hat i, zeros around
     double *ct = reinterpret_cast<double *>(r2_raw + LF.ct);       // [3][mlc][8] (both parities summed); later xb [4][mlc][8]
@@ -178,13 +179,15 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
 
     // ---- one-time set-up ------------------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(barIN, 1);
-        mbar_init(barINfree, (uint32_t)(nthr / 32));   // one arrival per compute warp
+        mbar_init(barH, 1);
+        mbar_init(barH + 1, 1);
         mbar_init(barMB, 1);
         mbar_init(barMB + 1, 1);
-        for (int s = 0; s < ns; ++s) {
-            mbar_init(barF + s, 1);
-            mbar_init(barR + s, (uint32_t)(nthr / 32));
+        for (int c = 0; c < NCM; ++c) {
+            mbar_init(barX + c, 1);
+            mbar_init(barXfree + c, (uint32_t)(nthr / 32));   // one arrival per compute warp
+            mbar_init(barF + c, 1);
+            mbar_init(barR + c, (uint32_t)(nthr / 32));
         }
         fence_mbar_init();
     }
@@ -234,7 +237,6 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         bstride = 1;
         nloc = max(min(P.nblk, bbase + per) - bbase, 0);
     }
-    const int gtot = nloc * nch;                     // chunks of this CTA over the whole kernel
 
     // Register budget (5 warps per scheduler: 96 registers each at launch): the producer warp group (threads 512 .. 639:
     // the TMA producer lane and the two hat warps) hands registers back to the CTA pool, the four compute warp groups take
@@ -243,47 +245,61 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // =========================== TMA producer (one lane) =====================================================
         if (tid == R2_COMPUTE_SLOTS && nloc > 0) {
-            const uint32_t in_bytes = (uint32_t)((nch * CBD + HBD * (useF ? 2 : 1)) * 8);
-            auto issue_in = [&](int t) {   // block t of this cluster -> IN, INH[t&1] (, FH[t&1])
-                const int row0 = (bbase + t * bstride) * R2_RB;
-                mbar_expect_tx(barIN, in_bytes);
-                for (int c = nch - 1; c >= 0; --c) tma_load_3d(IN + c * CBD, &P.mapX3, row0, k0, DC * c, barIN);
-                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, row0, hA, barIN);
-                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, row0, hA, barIN);
+            // The row block buffer IN is time-multiplexed: chunk c of X(t) lives in region NCM-1-c until the backward sweep
+            // has taken it into registers; F(t) of chunk r then lands in region r (requested as the regions drain, i.e. a
+            // whole hat phase before it is needed), is overwritten in place by the results and leaves by a TMA store; as
+            // soon as the store has read region r, chunk NCM-1-r of X(t+1) is requested into it.  The backward sweep
+            // walks the chunks downwards and the output phase upwards, so both find their data in the order of arrival.
+            const uint32_t cbytes = (uint32_t)(CBD * 8);
+            auto load_x = [&](int t, int c) {      // chunk c of block t -> region NCM-1-c
+                mbar_expect_tx(barX + c, cbytes);
+                tma_load_3d(IN + (NCM - 1 - c) * CBD, &P.mapX3, (bbase + t * bstride) * R2_RB, k0, DC * c, barX + c);
             };
-            int gf = 0, tf = 0, cf = 0, sf = 0;      // next F chunk to request: index, its block, its chunk, its slot
-            auto feed = [&]() {                      // slot sf is free: request F of chunk gf into it, or hand it to the compute threads
-                if (gf < gtot) {
-                    if (useF) {
-                        mbar_expect_tx(barF + sf, (uint32_t)(CBD * 8));
-                        tma_load_3d(RING + sf * CBD, &P.mapF3, (bbase + tf * bstride) * R2_RB, k0, DC * cf, barF + sf);
-                    } else {
-                        mbar_arrive(barF + sf);
-                    }
-                }
-                ++gf;
-                if (++cf == nch) { cf = 0; ++tf; }
-                if (++sf == ns) sf = 0;
+            auto load_h = [&](int t) {             // hats of block t (and of F)
+                mbar_expect_tx(barH + (t & 1), (uint32_t)(HBD * 8 * (useF ? 2 : 1)));
+                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, (bbase + t * bstride) * R2_RB, hA, barH + (t & 1));
+                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, (bbase + t * bstride) * R2_RB, hA, barH + (t & 1));
             };
-            issue_in(0);
-            for (int i = 0; i < ns; ++i) feed();
-            int s = 0;
-            uint32_t phs = 0;
+            load_h(0);
+            for (int c = nch - 1; c >= 0; --c) load_x(0, c);
             for (int t = 0; t < nloc; ++t) {
                 const int row0 = (bbase + t * bstride) * R2_RB;
-                mbar_wait(barINfree, (uint32_t)t & 1u);
-                if (t + 1 < nloc) issue_in(t + 1);
-                if (useF && P.pf_dist > 0 && t + P.pf_dist < nloc)   // F of a later block on its way into L2
-                    for (int c = 0; c < nch; ++c) tma_prefetch_3d(&P.mapF3, (bbase + (t + P.pf_dist) * bstride) * R2_RB, k0, DC * c);
-                for (int c = 0; c < nch; ++c) {
-                    mbar_wait(barR + s, phs);            // the results of chunk (t, c) are in slot s
-                    tma_store_3d(&P.mapX3, row0, k0, DC * c, RING + s * CBD);
-                    tma_commit();
-                    if (++s == ns) { s = 0; phs ^= 1u; }
-                    if (t > 0 || c > 0) {                // the previous store has left its slot: reuse it
-                        tma_wait_read<1>();
-                        feed();
+                const uint32_t ph = (uint32_t)t & 1u;
+                const bool more = t + 1 < nloc;
+                // phase 1: regions drain (backward sweep) -> F(t) in, or X(t+1) where the region never holds results
+                if (useF)
+                    for (int r = 0; r < NCM - nch && r < nch; ++r) {   // regions that never hold X (q below the class maximum)
+                        mbar_expect_tx(barF + r, cbytes);
+                        tma_load_3d(IN + r * CBD, &P.mapF3, row0, k0, DC * r, barF + r);
                     }
+                for (int c = nch - 1; c >= 0; --c) {
+                    const int r = NCM - 1 - c;
+                    mbar_wait(barXfree + c, ph);
+                    if (r < nch) {
+                        if (useF) {
+                            mbar_expect_tx(barF + r, cbytes);
+                            tma_load_3d(IN + r * CBD, &P.mapF3, row0, k0, DC * r, barF + r);
+                        }
+                    } else if (more) {
+                        load_x(t + 1, c);
+                    }
+                }
+                if (more) load_h(t + 1);
+                // phase 2: results out, X(t+1) in behind them
+                for (int r = 0; r < nch; ++r) {
+                    mbar_wait(barR + r, ph);
+                    tma_store_3d(&P.mapX3, row0, k0, DC * r, IN + r * CBD);
+                    tma_commit();
+                    if (r >= 1) {
+                        tma_wait_read<1>();            // the store of region r-1 has read it
+                        const int c = NCM - 1 - (r - 1);
+                        if (more && c < nch) load_x(t + 1, c);
+                    }
+                }
+                tma_wait_read<0>();
+                {
+                    const int c = NCM - 1 - (nch - 1);
+                    if (more && c < nch) load_x(t + 1, c);
                 }
             }
             tma_wait_all();
@@ -392,40 +408,53 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         const uint32_t off_er = sbase + (uint32_t)(((par * mlc + e) * R2_RB + r) * 8);   // (parity, element, row) inside a [degree][element][row] box
         const uint32_t dstride = (uint32_t)(2 * mlc * R2_RB * 8);                       // two degrees further
         const uint32_t a_tab = sbase + LF.tab + par * 16, a_ttab = sbase + LF.ttab + par * 16, a_ftab = sbase + LF.ftab + par * 16;
-        const uint32_t a_in = off_er + LF.in, a_ring = off_er + LF.ring;
+        const uint32_t a_in = off_er + LF.in;
         const uint32_t a_ss = sbase + LF.ss + (par * 3 * mlc + e) * 8, a_st = sbase + LF.st + (par * 3 * mlc + e) * 8;
         const uint32_t a_hf = sbase + P.o_hf + (k * R2_RB + r) * 8;
-        int s = 0;             // ring slot of the next chunk
-        uint32_t phs = 0;      // its phase
         for (int t = 0; t < nloc; ++t) {
             const int pb = t & 1;
             const uint32_t phMB = (uint32_t)(t >> 1) & 1u;
             const int row0 = (bbase + t * bstride) * R2_RB;
             const double *inh = INH + pb * HBS, *fh = FH + pb * HBS;
             double *mbme = MB + ((size_t)pb * cs + rank) * mbw;
-            // ---- A: the row block, shared memory -> registers --------------------------------------------------
+            // ---- A+B: the row block, shared memory -> registers, chunk by chunk from the top degrees down, and the
+            //      backward sweep  z_j = (b_j - w2_j z_{j+2}) rd_j  on the way
             R2_STAMP(0);
-            mbar_wait(barIN, (uint32_t)t & 1u);
-            R2_STAMP(1);
             double z[CH];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) z[i] = (MLC || (2 * i + par) < DC * nch) ? lds_f64(a_in + (uint32_t)i * dstride) : 0.0;   // degrees >= q arrive as zeros (TMA fill)
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(barINfree);
-            // ---- B: backward sweep  z_j = (b_j - w2_j z_{j+2}) rd_j ; couplings of my elements to the hats ------
-            R2_STAMP(2);
             {
                 double2 ca = lds_v2f64(a_tab + (CH - 1) * 32), cb = lds_v2f64(a_tab + (CH - 2) * 32);   // coefficients two steps ahead
 #pragma unroll
-                for (int i = CH - 1; i >= 0; --i) {
-                    const double2 cf = ca;
-                    ca = cb;
-                    if (i >= 2) cb = lds_v2f64(a_tab + (i - 2) * 32);
-                    double v = z[i];
-                    if (i + 1 < CH) v = fma(-cf.y, z[i + 1], v);
-                    z[i] = v * cf.x;
+                for (int cc = NCM - 1; cc >= 0; --cc) {
+                    if (cc < nch) {
+                        mbar_wait(barX + cc, (uint32_t)t & 1u);
+                        if (cc == NCM - 1) R2_STAMP(1);
+#pragma unroll
+                        for (int i4 = DC / 2 - 1; i4 >= 0; --i4) {
+                            const int i = (DC / 2) * cc + i4;
+                            if (i < CH) z[i] = lds_f64(a_in + (uint32_t)((NCM - 1 - cc) * (LF.cb)) + (uint32_t)i4 * dstride);
+                        }
+                        __syncwarp();
+                        if ((tid & 31) == 0) mbar_arrive(barXfree + cc);
+                    } else {
+#pragma unroll
+                        for (int i4 = 0; i4 < DC / 2; ++i4)
+                            if ((DC / 2) * cc + i4 < CH) z[(DC / 2) * cc + i4] = 0.0;
+                    }
+#pragma unroll
+                    for (int i4 = DC / 2 - 1; i4 >= 0; --i4) {
+                        const int i = (DC / 2) * cc + i4;
+                        if (i < CH) {
+                            const double2 cf = ca;
+                            ca = cb;
+                            if (i >= 2) cb = lds_v2f64(a_tab + (i - 2) * 32);
+                            double v = z[i];
+                            if (i + 1 < CH) v = fma(-cf.y, z[i + 1], v);
+                            z[i] = v * cf.x;
+                        }
+                    }
                 }
             }
+            R2_STAMP(2);
             {
                 double c0 = 0.0, c1 = 0.0, c2 = 0.0;
 #pragma unroll
@@ -455,6 +484,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             named_bar_sync(R2_BAR_COMPUTE, nthr);
             // ---- C: my message: hat right-hand sides minus the couplings of MY elements, for hats k0-1 .. k0+mlc --
             R2_STAMP(3);
+            mbar_wait(barH + pb, phMB);   // the hats of this block (loaded a block ahead)
             if (tid < (mlc + 2) * R2_RB) {
                 const int u = tid / R2_RB - 1, rr = tid % R2_RB;
                 double v = (u >= 0 && u < nhl) ? inh[u * R2_RB + rr] : 0.0;
@@ -524,7 +554,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
 #pragma unroll
             for (int cc = 0; cc < (2 * CH + DC - 1) / DC; ++cc) {
                 if (cc < nch) {
-                    const uint32_t slot = a_ring + s * (uint32_t)(CBD * 8);
+                    const uint32_t slot = a_in + (uint32_t)(cc * LF.cb);   // region cc: F of this chunk in, results out
                     // this chunk's product coefficients (t0_j, t2_j), t2_{j-2}: loaded before the wait for F
                     double2 tc[DC / 2];
                     double tm[DC / 2];
@@ -538,7 +568,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                             }
                         }
                     }
-                    mbar_wait(barF + s, phs);      // F of this chunk has landed / the slot is free
+                    if (useF) mbar_wait(barF + cc, (uint32_t)t & 1u);      // F of this chunk has landed
 #pragma unroll
                     for (int i4 = 0; i4 < DC / 2; ++i4) {
                         const int i = (DC / 2) * cc + i4;
@@ -564,8 +594,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     }
                     fence_proxy_async();           // my writes are visible to the TMA store
                     __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(barR + s);
-                    if (++s == ns) { s = 0; phs ^= 1u; }
+                    if ((tid & 31) == 0) mbar_arrive(barR + cc);
                 }
             }
             R2_STAMP(8);
@@ -733,21 +762,13 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     const int hf_rows = std::max(8 * lp + 2, op.m + 3);
     // behind the ring: HF, the padded hat tables, the mailboxes
     const int tail = r2_align(hf_rows * R2_RB * 8, 128) + 3 * r2_align(8 * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
-    // chunks of 8 degrees if four ring slots of that size fit, else chunks of 4
-    int dc = 0, nch = 0, ns = 0;
-    R2Fixed LF = {};
-    const int want_dc = r2_env("POP_ROW2_DC", 0);
-    for (int cand = 8; cand >= 4 && !dc; cand >>= 1) {
-        if (want_dc && cand != want_dc) continue;
-        const R2Fixed f = r2_fixed(ch, cand, mlc);
-        const int left = ctx->max_smem_optin - f.ring - tail;
-        const int slots = left >= 0 ? std::min(left / f.cb, R2_NS_MAX) : 0;
-        if (slots >= (cand == 8 ? 4 : 3)) { dc = cand; nch = (op.q + cand - 1) / cand; ns = slots; LF = f; }
-    }
-    if (!dc) return unsupported("shared memory too small for the row block and the ring");
-    if (const int w = r2_env("POP_ROW2_NS", 0)) ns = std::max(3, std::min(ns, w));
-    P.ns = ns;
-    int o = LF.ring + ns * LF.cb;
+    // degrees per chunk (TMA box, region of the row block buffer): 4 keeps the hand-over between the blocks fine-grained
+    const int dc = r2_env("POP_ROW2_DC", 4) == 8 ? 8 : 4;
+    const int nch = (op.q + dc - 1) / dc;
+    const R2Fixed LF = r2_fixed(ch, dc, mlc);
+    if (LF.ring + tail > ctx->max_smem_optin) return unsupported("shared memory too small for the row block");
+    if (4 + 4 * ((2 * ch + dc - 1) / dc) > 128) return unsupported("too many barriers");
+    int o = LF.ring;
     P.o_hf = o; o += r2_align(hf_rows * R2_RB * 8, 128);
     P.o_hrd = o; o += r2_align(8 * lp * 8, 128);
     P.o_hcd = o; o += r2_align(8 * lp * 8, 128);
@@ -813,7 +834,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     if (P.pairing) ncl &= ~1;
     cfg.gridDim = dim3((unsigned)(ncl * cs));
     if (r2_env("POP_ROW2_VERBOSE", 0))
-        fprintf(stderr, "pop_row2: chain %d per thread, cluster %d x %d threads, %d B smem, ring %d slots of %d degrees, %d clusters, %d row blocks, F %d\n", ch, cs, nthr, P.total, ns, dc, ncl,
+        fprintf(stderr, "pop_row2: chain %d per thread, cluster %d x %d threads, %d B smem, chunks of %d degrees, %d clusters, %d row blocks, F %d\n", ch, cs, nthr, P.total, dc, ncl,
                 P.nblk, P.useF);
     long long *dbg = nullptr;
     if (r2_env("POP_ROW2_TRACE", 0)) {

@@ -616,8 +616,7 @@ def test_single_pass_tma_row_half_step(basis, m, N, cs, monkeypatch):
     got = {}
     for mode in ("tma", "tma4", "two-pass"):
         monkeypatch.setenv("POP_ROW2", "0" if mode == "two-pass" else "1")
-        monkeypatch.setenv("POP_ROW2_DC", "4" if mode == "tma4" else "8")     # degrees per TMA box / ring slot
-        monkeypatch.setenv("POP_ROW2_NS", "3" if mode == "tma4" else "0")     # the shortest ring
+        monkeypatch.setenv("POP_ROW2_DC", "4" if mode == "tma4" else "8")     # degrees per TMA box / region of the row block buffer
         monkeypatch.setenv("POP_ROW1", "0")
         monkeypatch.setenv("POP_ROW2_CS", str(cs))
         monkeypatch.setenv("POP_ROW2_STRICT", "1")    # the forced plan must apply: no silent fallback
