@@ -91,7 +91,7 @@ __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wai
 // a fixed mlc addresses it with compile-time offsets; the arrays that depend on nh, m, cs and on the number of ring slots
 // follow (their offsets travel in R2Params).
 struct R2Fixed {
-    int in, inh, fh, ct, tab, ttab, ftab, ss, st, ring, cb, hbs;
+    int in, inh, fh, ct, tab, ttab, ftab, gtab, ss, st, ring, cb, hbs;
 };
 __host__ __device__ constexpr int r2_al(int x) { return (x + 127) / 128 * 128; }
 __host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc) {
@@ -107,6 +107,7 @@ __host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc) {
     f.tab = o; o += r2_al((2 * ch + 2) * 16);
     f.ttab = o; o += r2_al((2 * ch + 2) * 16);
     f.ftab = o; o += r2_al((2 * ch + 2) * 16);
+    f.gtab = o; o += r2_al((2 * ch + 2) * 16);
     f.ss = o; o += r2_al(R2_NBMAX * 3 * mlc * 8);
     f.st = o; o += r2_al(R2_NBMAX * 3 * mlc * 8);
     f.ring = o;
@@ -130,9 +131,11 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st
 // DC degrees per TMA box / ring slot (8, or 4 when shared memory is short: more, smaller slots).
 // Threads [0, 16 mlc) compute; one more warp (the last) is the TMA PRODUCER: it alone issues and waits for the tensor
 // copies, and meets the compute threads only through mbarriers (no block-wide barrier on the data path).
+#define R2_FG 4            // chunks per proxy fence in the output phase
 #define R2_BAR_COMPUTE 1   // named barrier of the compute threads
 #define R2_STAMP(slot) do { if (P.dbg && blockIdx.x == 0 && tid == 0 && t < 64) P.dbg[t * 10 + (slot)] = clock64(); } while (0)
-#define R2_BAR_HATS 2      // compute threads + the two hat warps
+#define R2_BAR_HATS 2      // compute threads + the two hat warps: hats solved
+#define R2_BAR_MSG 3       // compute threads (arrive) + the two hat warps (sync): this CTA's message is written
 #define R2_COMPUTE_SLOTS 512   // threads [0, 512): compute (the first 16 mlc of them work), [512, 640): producer warp group
 // MLC > 0: elements per CTA fixed at compile time (every hot shared-memory address is then one register plus an immediate).
 template <int CH, int DC, int MLC>
@@ -163,9 +166,12 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     double2 *tab = reinterpret_cast<double2 *>(r2_raw + LF.tab);   // (rd_j, w2_j)
     double2 *ttab = reinterpret_cast<double2 *>(r2_raw + LF.ttab); // (t0_j, t2_j)
     double2 *ftab = reinterpret_cast<double2 *>(r2_raw + LF.ftab); // (rd_j, w2_{j-2}): the forward sweep's pair
+    double2 *gtab = reinterpret_cast<double2 *>(r2_raw + LF.gtab); // impulse responses of the forward sweep to unit changes of the chain entries 0 and 1
     double *hrd = reinterpret_cast<double *>(r2_raw + P.o_hrd);     // [nh]
     double *hcd = reinterpret_cast<double *>(r2_raw + P.o_hcd);     // off(i,i+1) rd_i
     double *hcu = reinterpret_cast<double *>(r2_raw + P.o_hcu);     // off(i-1,i) rd_i
+    double *hwd = hcu + 8 * P.lp;                                   // weights of the downward segment maps
+    double *hwu = hwd + 8 * P.lp;                                   // weights of the upward segment maps (times rd_i)
     double *sS = reinterpret_cast<double *>(r2_raw + LF.ss);       // [4][3][mlc]
     double *sT = reinterpret_cast<double *>(r2_raw + LF.st);       // [4][3][mlc]
     const int CBD = LF.cb / 8;                // doubles per chunk of DC degrees
@@ -211,6 +217,34 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         }
         for (int x = tid; x < P.hf_rows * R2_RB; x += nthr)   // zero pads around the hats: entry 0 and everything behind hat nh-1
             if (x < R2_RB || x >= (nh + 1) * R2_RB) HF[x] = 0.0;
+    }
+    __syncthreads();
+    if (tid < 8) {
+        // segment maps of the two hat recurrences: h_bottom = sum_i wd_i ytil_i + Ad h_in (downward),
+        // x_top = sum_i wu_i h_i + Au x_in (upward, wu includes rd_i); the products Ad, Au are rebuilt by the hat lanes
+        const int sg = tid, a0 = sg * P.lp;
+        double pd = 1.0;
+        for (int i = 0; i < P.lp; ++i) {
+            hwd[a0 + i] = pd;
+            pd *= -hcd[a0 + i];
+        }
+        double pu = 1.0;
+        for (int i = P.lp - 1; i >= 0; --i) {
+            hwu[a0 + i] = pu * hrd[a0 + i];
+            pu *= -hcu[a0 + i];
+        }
+    }
+    if (tid < 2) {
+        // x = forward sweep of z is linear: a change of z_0 (z_1) of a chain by -d moves x_i by -d * G0_i (G1_i).  The hats enter
+        // the forward sweep only through the first two chain entries (src/arrowhead.jl:475-477), so the sweep can run before the
+        // hats are known and be corrected afterwards.
+        double g0 = 0.0, g1 = 0.0;
+        for (int i = 0; i < CH; ++i) {
+            const double2 cf = ftab[2 * i + tid];
+            g0 = ((i == 0 ? 1.0 : 0.0) - cf.y * g0) * cf.x;
+            g1 = ((i == 1 ? 1.0 : 0.0) - cf.y * g1) * cf.x;
+            gtab[2 * i + tid] = make_double2(g0, g1);
+        }
     }
     __syncthreads();
     if (cs > 1) {   // every CTA's mbarriers are initialised before a peer sends to them
@@ -317,82 +351,69 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             const int lp = P.lp;
             double *col = HF + R2_RB + rr + seg * lp * R2_RB;
             const double *cd = hcd + seg * lp, *cu = hcu + seg * lp, *rdp = hrd + seg * lp;
+            const double *wd = hwd + seg * lp, *wu = hwu + seg * lp;
+            double Ad = 1.0, Au = 1.0;   // the segment's multipliers of the incoming values
+            for (int i = 0; i < lp; ++i) {
+                Ad *= -cd[i];
+                Au *= -cu[i];
+            }
+            const int l4 = lane & 3;
             for (int t = 0; t < nloc; ++t) {
-                named_bar_sync(R2_BAR_HATS, nthr + 64);
-                // pass 1, descending: map of h_i = ytil_i - cd_i h_{i+1}
-                double A = 1.0, Bv = 0.0;
-                for (int i0 = lp - 4; i0 >= 0; i0 -= 4) {
-                    double y[4], c[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        y[u] = col[(i0 + 3 - u) * R2_RB];
-                        c[u] = cd[i0 + 3 - u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        Bv = fma(-c[u], Bv, y[u]);
-                        A *= -c[u];
-                    }
+                named_bar_sync(R2_BAR_HATS, nthr + 64);   // the right-hand sides (times rd) of all hats are in HF
+                // pass 1: what leaves my segment at the bottom with zero coming in: a dot product, no chain
+                double b0 = 0.0, b1 = 0.0;
+                for (int i0 = 0; i0 < lp; i0 += 4) {
+                    b0 = fma(wd[i0], col[i0 * R2_RB], b0);
+                    b1 = fma(wd[i0 + 1], col[(i0 + 1) * R2_RB], b1);
+                    b0 = fma(wd[i0 + 2], col[(i0 + 2) * R2_RB], b0);
+                    b1 = fma(wd[i0 + 3], col[(i0 + 3) * R2_RB], b1);
                 }
+                b0 += b1;
                 double inc = 0.0;
                 {
                     double res = 0.0;   // value leaving the segments above, built from the top
 #pragma unroll
                     for (int s2 = 7; s2 >= 0; --s2) {
-                        const double As = __shfl_sync(POP_FULL_MASK, A, s2 * 4 + (lane & 3)), Bs = __shfl_sync(POP_FULL_MASK, Bv, s2 * 4 + (lane & 3));
+                        const double As = __shfl_sync(POP_FULL_MASK, Ad, s2 * 4 + l4), Bs = __shfl_sync(POP_FULL_MASK, b0, s2 * 4 + l4);
                         if (s2 == seg) inc = res;
                         res = fma(As, res, Bs);
                     }
                 }
-                // pass 2, descending: the final h_i; at the same time the map of the ascending recurrence
-                // x_i = h_i rd_i - cu_i x_{i-1}, composed from the top:  G <- G o f_i,  f_i(x) = h_i rd_i - cu_i x
+                // pass 2, descending: the final h_i = ytil_i - cd_i h_{i+1}; on the way the dot product of the upward map
                 double h = inc;
-                A = 1.0;
-                Bv = 0.0;
+                b0 = 0.0;
                 for (int i0 = lp - 2; i0 >= 0; i0 -= 2) {
-                    double y[2], c[2], c2[2], rd[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        y[u] = col[(i0 + 1 - u) * R2_RB];
-                        c[u] = cd[i0 + 1 - u];
-                        c2[u] = cu[i0 + 1 - u];
-                        rd[u] = rdp[i0 + 1 - u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        h = fma(-c[u], h, y[u]);
-                        col[(i0 + 1 - u) * R2_RB] = h;
-                        Bv = fma(A, h * rd[u], Bv);
-                        A *= -c2[u];
-                    }
+                    const double y1 = col[(i0 + 1) * R2_RB], y0 = col[i0 * R2_RB];
+                    const double c1 = cd[i0 + 1], c0 = cd[i0], w1 = wu[i0 + 1], w0 = wu[i0];
+                    h = fma(-c1, h, y1);
+                    col[(i0 + 1) * R2_RB] = h;
+                    b0 = fma(w1, h, b0);
+                    h = fma(-c0, h, y0);
+                    col[i0 * R2_RB] = h;
+                    b0 = fma(w0, h, b0);
                 }
                 {
                     double res = 0.0;   // value entering from the segments below, built from the bottom
                     inc = 0.0;
 #pragma unroll
                     for (int s2 = 0; s2 < 8; ++s2) {
-                        const double As = __shfl_sync(POP_FULL_MASK, A, s2 * 4 + (lane & 3)), Bs = __shfl_sync(POP_FULL_MASK, Bv, s2 * 4 + (lane & 3));
+                        const double As = __shfl_sync(POP_FULL_MASK, Au, s2 * 4 + l4), Bs = __shfl_sync(POP_FULL_MASK, b0, s2 * 4 + l4);
                         if (s2 == seg) inc = res;
                         res = fma(As, res, Bs);
                     }
                 }
-                // pass 3, ascending: the final x_i
+                // pass 3, ascending: the final x_i = h_i rd_i - cu_i x_{i-1}
                 h = inc;
-                for (int i0 = 0; i0 < lp; i0 += 4) {
-                    double y[4], c2[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        y[u] = col[(i0 + u) * R2_RB] * rdp[i0 + u];
-                        c2[u] = cu[i0 + u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        h = fma(-c2[u], h, y[u]);
-                        col[(i0 + u) * R2_RB] = h;
-                    }
+                for (int i0 = 0; i0 < lp; i0 += 2) {
+                    const double y0 = col[i0 * R2_RB] * rdp[i0], y1 = col[(i0 + 1) * R2_RB] * rdp[i0 + 1];
+                    const double c0 = cu[i0], c1 = cu[i0 + 1];
+                    h = fma(-c0, h, y0);
+                    col[i0 * R2_RB] = h;
+                    h = fma(-c1, h, y1);
+                    col[(i0 + 1) * R2_RB] = h;
                 }
                 __syncwarp();
-                named_bar_sync(R2_BAR_HATS, nthr + 64);
+                named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hats of the 8 rows are solved
             }
         }
     } else {
@@ -500,38 +521,10 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 named_bar_sync(R2_BAR_COMPUTE, nthr);
                 if (tid < cs && tid != rank) dsmem_bulk_copy(mapa_u32(mbme, tid), mbme, (uint32_t)(mbw * 8), mapa_u32(barMB + pb, tid));
                 if (tid == 0) mbar_expect_tx(barMB + pb, (uint32_t)(mbw * 8 * (cs - 1)));
-                mbar_wait_cluster(barMB + pb, phMB);
-            } else {
-                named_bar_sync(R2_BAR_COMPUTE, nthr);
             }
-            // ---- D: the whole hat system of the 8 rows, redundantly in every CTA ---------------------------------
+            // ---- E1: forward sweep (:480-482) WITHOUT the hat corrections, while the hat warps wait for the peers' messages
+            //      and solve the hat systems
             R2_STAMP(4);
-            {
-                const double *mbp = MB + (size_t)pb * cs * mbw;
-                for (int x = tid; x < nh * R2_RB; x += nthr) {
-                    const int i = x / R2_RB, rr = x % R2_RB;
-                    const int c = min(i / mlc, cs - 1), u = i - c * mlc;
-                    double v = mbp[c * mbw + (u + 1) * R2_RB + rr];
-                    if (u == 0 && c > 0) v += mbp[(c - 1) * mbw + (mlc + 1) * R2_RB + rr];
-                    if (u == mlc - 1 && c < cs - 1) v += mbp[(c + 1) * mbw + rr];
-                    HF[(i + 1) * R2_RB + rr] = v * hrd[i];
-                }
-            }
-            R2_STAMP(5);
-            named_bar_sync(R2_BAR_HATS, nthr + 64);   // the right-hand sides are assembled: the hat warps take over
-            named_bar_sync(R2_BAR_HATS, nthr + 64);   // ... and have solved the hat systems of the 8 rows
-            // ---- E: correct the coupled bubbles (:475-477), forward sweep (:480-482), product, output ------------
-            R2_STAMP(6);
-            const double h0 = lds_f64(a_hf), h1 = lds_f64(a_hf + R2_RB * 8), h2 = lds_f64(a_hf + 2 * R2_RB * 8);
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-                const uint32_t sb = a_ss + ii * 6 * mlc * 8;
-                double v = z[ii];
-                v = fma(-lds_f64(sb), h0, v);
-                v = fma(-lds_f64(sb + mlc * 8), h1, v);
-                v = fma(-lds_f64(sb + 2 * mlc * 8), h2, v);
-                z[ii] = v;
-            }
             {
                 double2 ca = lds_v2f64(a_ftab), cb = lds_v2f64(a_ftab + 32);   // (rd_j, w2_{j-2}) two steps ahead
 #pragma unroll
@@ -544,10 +537,50 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     z[i] = v * cf.x;
                 }
             }
+            R2_STAMP(5);
+            // the messages of the peers have landed long ago (plain CTA-scope wait: the bytes were written into this CTA's
+            // shared memory by the async proxy and completed on this CTA's mbarrier, as for a TMA load)
+            if (cs > 1) mbar_wait(barMB + pb, phMB);
+            else named_bar_sync(R2_BAR_COMPUTE, nthr);
+            {
+                // right-hand sides (times rd) of ALL hats of the 8 rows, redundantly in every CTA
+                const double *mbp = MB + (size_t)pb * cs * mbw;
+                for (int x = tid; x < nh * R2_RB; x += nthr) {
+                    const int i = x / R2_RB, rr = x % R2_RB;
+                    const int c = min(i / mlc, cs - 1), u = i - c * mlc;
+                    double v = mbp[c * mbw + (u + 1) * R2_RB + rr];
+                    if (u == 0 && c > 0) v += mbp[(c - 1) * mbw + (mlc + 1) * R2_RB + rr];
+                    if (u == mlc - 1 && c < cs - 1) v += mbp[(c + 1) * mbw + rr];
+                    HF[(i + 1) * R2_RB + rr] = v * hrd[i];
+                }
+            }
+            named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hat warps take over ...
+            named_bar_sync(R2_BAR_HATS, nthr + 64);   // ... and have solved the hat systems of the 8 rows
+            // ---- E2: the corrections of the coupled bubbles (:475-477) carried through the sweep by its impulse responses,
+            //      product, output
+            R2_STAMP(6);
+            const double h0 = lds_f64(a_hf), h1 = lds_f64(a_hf + R2_RB * 8), h2 = lds_f64(a_hf + 2 * R2_RB * 8);
+            double d0, d1;
+            {
+                const uint32_t sb = a_ss;
+                d0 = lds_f64(sb) * h0;
+                d0 = fma(lds_f64(sb + mlc * 8), h1, d0);
+                d0 = fma(lds_f64(sb + 2 * mlc * 8), h2, d0);
+                const uint32_t sc = a_ss + 6 * mlc * 8;
+                d1 = lds_f64(sc) * h0;
+                d1 = fma(lds_f64(sc + mlc * 8), h1, d1);
+                d1 = fma(lds_f64(sc + 2 * mlc * 8), h2, d1);
+            }
+            const uint32_t a_gtab = sbase + LF.gtab + par * 16;
+            auto corrected = [&](int i) -> double {   // x_i = x0_i - d0 G0_i - d1 G1_i
+                const double2 g = lds_v2f64(a_gtab + i * 32);
+                return fma(-d1, g.y, fma(-d0, g.x, z[i]));
+            };
             double *xb = ct;   // [4][mlc][8]: x of the coupled bubbles, for the hat rows of the product
+            double xm = 0.0, x0 = corrected(0), xp = CH > 1 ? corrected(1) : 0.0;   // x_{i-1}, x_i, x_{i+1}
             if (mul) {
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii) xb[((2 * ii + par) * mlc + e) * R2_RB + r] = z[ii];
+                xb[(par * mlc + e) * R2_RB + r] = x0;
+                if (CH > 1) xb[((2 + par) * mlc + e) * R2_RB + r] = xp;
             }
             // chunk cc holds the chain entries i = cc*DC/2 .. (cc+1)*DC/2 - 1 (registers are indexed statically)
             R2_STAMP(7);
@@ -576,9 +609,9 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                             const uint32_t sp = slot + i4 * dstride;
                             double out;
                             if (mul) {
-                                double acc = tc[i4].x * z[i];
-                                if (i + 1 < CH) acc = fma(tc[i4].y, z[i + 1], acc);
-                                if (i >= 1) acc = fma(tm[i4], z[i - 1], acc);
+                                double acc = tc[i4].x * x0;
+                                if (i + 1 < CH) acc = fma(tc[i4].y, xp, acc);
+                                if (i >= 1) acc = fma(tm[i4], xm, acc);
                                 if (i < 2) {
                                     const uint32_t tb = a_st + i * 6 * mlc * 8;
                                     acc = fma(lds_f64(tb), h0, acc);
@@ -587,14 +620,24 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                                 }
                                 out = useF ? fma(P.gamma, lds_f64(sp), acc) : acc;
                             } else {
-                                out = z[i];
+                                out = x0;
                             }
                             sts_f64(sp, out);
+                            xm = x0;
+                            x0 = xp;
+                            if (i + 2 < CH) xp = corrected(i + 2);
                         }
                     }
-                    fence_proxy_async();           // my writes are visible to the TMA store
-                    __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(barR + cc);
+                    // one proxy fence (a CTA-wide memory barrier in SASS) per group of R2_FG chunks, then the group is handed
+                    // to the producer
+                    if ((cc % R2_FG) == R2_FG - 1 || cc == nch - 1) {
+                        fence_proxy_async();           // my writes are visible to the TMA store
+                        __syncwarp();
+                        if ((tid & 31) == 0) {
+#pragma unroll
+                            for (int c2 = cc - (cc % R2_FG); c2 <= cc; ++c2) mbar_arrive(barR + c2);
+                        }
+                    }
                 }
             }
             R2_STAMP(8);
@@ -761,7 +804,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     const int lp = (((op.nh + 7) / 8) + 3) & ~3;            // hats per scan segment (8 segments), a multiple of 4
     const int hf_rows = std::max(8 * lp + 2, op.m + 3);
     // behind the ring: HF, the padded hat tables, the mailboxes
-    const int tail = r2_align(hf_rows * R2_RB * 8, 128) + 3 * r2_align(8 * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
+    const int tail = r2_align(hf_rows * R2_RB * 8, 128) + 2 * r2_align(8 * lp * 8, 128) + r2_align(3 * 8 * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
     // degrees per chunk (TMA box, region of the row block buffer): 4 keeps the hand-over between the blocks fine-grained
     const int dc = r2_env("POP_ROW2_DC", 4) == 8 ? 8 : 4;
     const int nch = (op.q + dc - 1) / dc;
@@ -772,7 +815,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.o_hf = o; o += r2_align(hf_rows * R2_RB * 8, 128);
     P.o_hrd = o; o += r2_align(8 * lp * 8, 128);
     P.o_hcd = o; o += r2_align(8 * lp * 8, 128);
-    P.o_hcu = o; o += r2_align(8 * lp * 8, 128);
+    P.o_hcu = o; o += r2_align(3 * 8 * lp * 8, 128);   // hcu, hwd, hwu
     P.o_mb = o; o += r2_align(2 * cs * P.mbw * 8, 128);
     P.total = o;
     if ((size_t)P.total > (size_t)ctx->max_smem_optin) return unsupported("shared memory too small");
@@ -848,7 +891,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
         long long h[64 * 10];
         POP_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(dbg);
-        static const char *names[8] = {"wait IN", "IN->regs", "backward", "msg+exchange", "assemble", "hat scan", "corr+fwd", "chunks"};
+        static const char *names[8] = {"wait X", "load+backward", "couplings", "message", "forward", "wait hats", "corrections", "chunks"};
         double sum[10] = {0};
         int nb = 0;
         for (int t = 2; t < 64 && h[t * 10 + 9]; ++t, ++nb) {
