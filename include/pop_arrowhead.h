@@ -213,6 +213,10 @@ int pop_adi_shifts(int J, double a, double b, double c, double d, double *p, dou
 int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, const double *dF,
                     int64_t ldf, double *dX, int64_t ldx, double a, double b, double c, double d,
                     double tol, int J);
+/* the same with F and X in HOST memory (one copy in, the whole iteration on the device, one copy out) */
+int pop_adi_poisson_host(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, const double *F,
+                         int64_t ldf, double *X, int64_t ldx, double a, double b, double c, double d,
+                         double tol, int J);
 /* backward Euler with one reused factorisation, examples/heat.jl:58-63:
  * nsteps times  U <- S^{-1} (M U)  with S = M + dt*K; dims = 1: columns of dU (n x nrhs);
  * dims = 2: n x n field, U <- S^{-1} (M U M) S^{-1} (factored 2D extension). */

@@ -110,6 +110,7 @@ _PROTOS = {
     "pop_adi_num_iterations": (C.c_int, [C.c_double] * 5),
     "pop_adi_shifts": (C.c_int, [C.c_int] + [C.c_double] * 4 + [vp, vp]),
     "pop_adi_poisson": (C.c_int, [vp, vp, vp, vp, i64, vp, i64] + [C.c_double] * 5 + [C.c_int]),
+    "pop_adi_poisson_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i64] + [C.c_double] * 5 + [C.c_int]),
     "pop_heat_steps": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.c_int, vp, i64, i64]),
     "pop_eigvals_lanczos": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, vp, vp, C.POINTER(C.c_int)]),
     "pop_heat_steps_theta": (C.c_int, [vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, i64, i64]),

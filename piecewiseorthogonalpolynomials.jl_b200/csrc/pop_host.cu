@@ -426,6 +426,24 @@ extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_a
     POP_REQUIRE(K->d.m == M->d.m && K->d.nh == M->d.nh && K->d.q == M->d.q, POP_ERR_DIM, "pop_adi_poisson: K and M differ in size");
     const int64_t n = K->n();
     POP_REQUIRE(ldf >= n && ldx >= n, POP_ERR_DIM, "pop_adi_poisson: leading dimensions too small");
+    // The transpose-free driver (row sweeps with lanes over the rows, pop_row.cu / pop_row2.cu) on a decomposition of one
+    // rank: 70 ms instead of 88 ms per solve at n = 8191.  Needs the shared D block and aligned panels; the variant with
+    // explicit transposes below serves every other case (POP_ADI_TRANSPOSE=1 forces it).
+    {
+        const char *e = getenv("POP_ADI_TRANSPOSE");
+        const bool aligned = !(ldf & 1) && !((uintptr_t)dF & 15);
+        if (!(e && atoi(e)) && aligned && K->mD == 1 && M->mD == 1 && K->d.q <= 128 && K->d.m >= 1 && K->d.m <= 1024 && abs(K->d.nh - K->d.m) <= 1 && K->d.uD <= 2 && M->d.uD <= 2) {
+            pop_dd *dd = nullptr;
+            int rc = pop_dd_create(ctx, 0, 1, K->d.m, K->d.nh, K->d.q, &dd);
+            if (rc == POP_OK) {
+                rc = pop_adi_poisson_dd(ctx, dd, K, M, dF, ldf, dX, ldx, a, b, c, d, tol, J);
+                pop_dd_destroy(ctx, dd);
+                return rc;
+            }
+            pop_dd_destroy(ctx, dd);   // e.g. out of memory for the work panel: the transposing variant needs less
+            cudaGetLastError();
+        }
+    }
     if (J <= 0) J = pop_adi_num_iterations(a, b, c, d, tol);
     POP_REQUIRE(J >= 1 && J <= 2000, POP_ERR_ARG, "pop_adi_poisson: iteration count %d out of range", J);
     std::vector<double> p(J), q(J);
@@ -484,6 +502,31 @@ extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_a
     free_handles(ctx, top);
     cudaStreamSynchronize(ctx->stream);
     return rc;
+}
+
+// Host-buffer variant: F (n x n, column-major, leading dimension ldf) in host memory in, X out.  One H2D copy, the whole
+// iteration on the device, one D2H copy: 16 B per entry over PCIe for 2J sweeps of 24 B per entry over HBM.
+extern "C" int pop_adi_poisson_host(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, const double *F, int64_t ldf, double *X, int64_t ldx,
+                                    double a, double b, double c, double d, double tol, int J) {
+    POP_REQUIRE(ctx && K && M && F && X, POP_ERR_ARG, "pop_adi_poisson_host: null argument");
+    const int64_t n = K->n();
+    POP_REQUIRE(ldf >= n && ldx >= n, POP_ERR_DIM, "pop_adi_poisson_host: leading dimensions too small");
+    const int64_t ld = (n + 1) & ~(int64_t)1;
+    double *buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)ld * n * 2 * sizeof(double));
+    if (e != cudaSuccess) { pop_set_error("pop_adi_poisson_host: %zu bytes of device memory: %s", (size_t)ld * n * 16, cudaGetErrorString(e)); return POP_ERR_ALLOC; }
+    double *dF = buf, *dX = buf + (size_t)ld * n;
+    int rc = POP_OK;
+    e = cudaMemcpy2DAsync(dF, ld * 8, F, ldf * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rc = pop_adi_poisson(ctx, K, M, dF, ld, dX, ld, a, b, c, d, tol, J);
+        if (rc == POP_OK) e = cudaMemcpy2DAsync(X, ldx * 8, dX, ld * 8, n * 8, n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { pop_set_error("pop_adi_poisson_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return POP_ERR_CUDA; }
+    return POP_OK;
 }
 
 // ------------------------------------------------------------------------------------

@@ -42,19 +42,17 @@ def adi_poisson(M, K, F, a, b, c=None, d=None, tol=1e-15, J=0):
     Mb, Kb = _base(M), _base(K)
     c = -b if c is None else c
     d = -a if d is None else d
-    host = not hasattr(F, "data_ptr")
-    if host:
-        import torch
-        Fd = torch.from_numpy(np.asfortranarray(F).T.copy()).to(f"cuda:{Mb.ctx.device}").t()
-    else:
-        Fd = F
-    pf = _Panel(Fd, False)
-    X = _new_like(Fd, tuple(Fd.shape))
+    if not hasattr(F, "data_ptr"):
+        # host arrays: pop_adi_poisson_host (one copy in, the iteration on the device, one copy out)
+        Fh = np.asfortranarray(F, dtype=np.float64)
+        X = np.empty(Fh.shape, dtype=np.float64, order="F")
+        L.check(L.lib().pop_adi_poisson_host(Mb.ctx.handle, Kb._h, Mb._h, Fh.ctypes.data, Fh.shape[0], X.ctypes.data, X.shape[0], a, b, c, d, tol, int(J)), "ADI")
+        return X
+    pf = _Panel(F, False)
+    X = _new_like(F, tuple(F.shape))
     px = _Panel(X, True)
     _bind_stream(Mb.ctx)
     L.check(L.lib().pop_adi_poisson(Mb.ctx.handle, Kb._h, Mb._h, pf.ptr, pf.ld, px.ptr, px.ld, a, b, c, d, tol, int(J)), "ADI")
-    if host:
-        return np.asfortranarray(X.cpu().numpy())
     return X
 
 
