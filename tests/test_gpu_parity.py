@@ -754,3 +754,64 @@ def test_spectrum_bounds_enclose_dense():
     assert a <= lam[0] and b >= lam[-1]
     assert a > 0.99 * lam[0] and b < 1.01 * lam[-1]
     assert P.adi_num_iterations(a, b, -b, -a) == P.adi_num_iterations(lam[0], lam[-1], -lam[-1], -lam[0])
+
+
+# --------------------------------------------------------------------------------------
+# race evidence without compute-sanitizer (closed on this pool, profiles/r2_sanitizer_closed.log): the kernels that rest on
+# mailbox / mbarrier / flag protocols must return bitwise identical results run after run, for every cluster size
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["fused2-cs1", "fused2-cs4", "fused2-cs8", "fused-smem", "row2-cs1", "row2-cs4", "row2-cs8", "row1-cs4", "two-pass-rows"])
+def test_protocol_kernels_are_bitwise_reproducible(kernel, monkeypatch):
+    from pop_b200 import _lib as L
+    from pop_b200.arrowhead import _bind_stream
+    m, N = 16, 24
+    M, Lp, Mo, Lo = _assemble("dirichlet", m, N)
+    K = -Lp
+    n = Mo.n
+    Fs = P.reversecholesky(K + 3.7 * M)
+    T = 0.5 * M - K
+    rng = np.random.default_rng(21)
+    R0, Fm = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    ctx = M.data.ctx
+    _bind_stream(ctx)
+    Fd = dev(Fm)
+    first = None
+    if kernel.startswith("fused"):
+        if kernel == "fused-smem":
+            monkeypatch.setenv("POP_DISABLE_FUSED2", "1")
+        else:
+            monkeypatch.setenv("POP_F2_CS", kernel[-1])
+
+        def run():
+            R = dev(R0)
+            L.check(L.lib().pop_solve_mul_axpy(ctx.handle, Fs.factor._h, T.data._h, -0.4, Fd.data_ptr(), Fd.stride(1), R.data_ptr(), R.stride(1), n))
+            return R
+    else:
+        dd = P.ElementDecomposition(M)
+        Fp = dd.panel()
+        Fp.copy_(torch.from_numpy(Fm).cuda())
+        monkeypatch.setenv("POP_ROW2", "1" if kernel.startswith("row2") else "0")
+        monkeypatch.setenv("POP_ROW1", "2" if kernel.startswith("row1") else "0")
+        if kernel.startswith("row2"):
+            monkeypatch.setenv("POP_ROW2_CS", kernel[-1])
+            monkeypatch.setenv("POP_ROW2_STRICT", "1")
+        if kernel.startswith("row1"):
+            monkeypatch.setenv("POP_ROW1_CS", kernel[-1])
+            monkeypatch.setenv("POP_ROW1_STRICT", "1")
+
+        def run():
+            R = dd.panel()
+            R.copy_(torch.from_numpy(R0).cuda())
+            L.check(L.lib().pop_dd_row_half_step(ctx.handle, dd._h, Fs.factor._h, T.data._h, -0.4, Fp.data_ptr(), Fp.stride(1), R.data_ptr(), R.stride(1)))
+            return R
+    for it in range(25):
+        got = host(run())
+        torch.cuda.synchronize()
+        if first is None:
+            first = got
+            Xd = np.linalg.solve(O.unpack(O.packed_symmetrize(O.packed_axpby(-1.0, Lo, 3.7, Mo))).to_dense(), R0 if kernel.startswith("fused") else R0.T)
+            Td = O.unpack(O.packed_symmetrize(O.packed_axpby(0.5, Mo, 1.0, Lo))).to_dense()
+            want = Td @ Xd - 0.4 * Fm if kernel.startswith("fused") else Xd.T @ Td - 0.4 * Fm
+            assert relerr(got, want) < TOL
+        else:
+            assert np.array_equal(got, first), (kernel, it)
