@@ -47,6 +47,12 @@ struct pop_dd {
     int hats_ny;        // lanes over the hats in k_row_hats (block = 32 rows x hats_ny)
     size_t hats_smem;
     bool hats_planned;
+    // mailboxes of the single-pass row kernel in remote mode (pop_row2.cu), inside the peer-visible slab
+    bool r2_ok;
+    int r2_csv, r2_mlc, r2_mbw;
+    size_t r2_o_mbox, r2_o_flag;
+    int64_t r2_mbox_doubles;
+    unsigned long long r2_epoch;
 };
 
 struct DDPeers {
@@ -100,6 +106,19 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
     size_t oA, oB, oC, oD, oF;
     dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
     d->slab_bytes = oF + POP_DD_FLAG_BYTES + (size_t)((d->nrows + 31) / 32) * POP_DD_MAXWORLD * 8;
+    {
+        // mailboxes [2][row blocks of 8][world * csv][mbw] and flags of k_row2's remote mode (several GPUs; one GPU: POP_ROW2_REMOTE=1)
+        const char *e = getenv("POP_ROW2_REMOTE");
+        const bool want = world > 1 ? !(e && !atoi(e)) : (e && atoi(e));
+        if (want && pop_row2_remote_plan(m, world, &d->r2_csv, &d->r2_mlc, &d->r2_mbw)) {
+            const int64_t nblk = (d->nrows + 7) / 8, nr = (int64_t)world * d->r2_csv;
+            d->r2_o_mbox = (d->slab_bytes + 255) & ~(size_t)255;
+            d->r2_mbox_doubles = 2 * nblk * d->r2_csv * nr * d->r2_mbw;   // one mailbox per reading CTA
+            d->r2_o_flag = d->r2_o_mbox + (size_t)d->r2_mbox_doubles * 8;
+            d->slab_bytes = d->r2_o_flag;
+            d->r2_ok = true;
+        }
+    }
     cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&d->hx, (size_t)(d->nhl + 3) * d->nrows * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d->gdn, (size_t)d->nrows * 8);
@@ -111,13 +130,15 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
         return POP_ERR_ALLOC;
     }
     POP_CUDA(cudaMemsetAsync(d->slab, 0, d->slab_bytes, ctx->stream));
+    if (d->r2_ok) POP_CUDA(cudaMemsetAsync((char *)d->slab + d->r2_o_mbox, 0xff, (size_t)d->r2_mbox_doubles * 8, ctx->stream));   // all mailbox entries empty
     if (const char *e = getenv("POP_DD_FAKE_PEERS")) {
         if (atoi(e) && world > 1) {
             // one GPU stands in for rank `rank` of `world`: all waits pass at once, all peer stores land locally
             d->fake_peers = true;
             for (int r = 0; r < world; ++r) d->peer_slab[r] = d->slab;
             POP_CUDA(cudaMemsetAsync((char *)d->slab + oF, 0x7f, POP_DD_MAXWORLD * 8, ctx->stream));
-            POP_CUDA(cudaMemsetAsync((char *)d->slab + oF + POP_DD_FLAG_BYTES, 0x7f, d->slab_bytes - oF - POP_DD_FLAG_BYTES, ctx->stream));
+            POP_CUDA(cudaMemsetAsync((char *)d->slab + oF + POP_DD_FLAG_BYTES, 0x7f, (d->r2_ok ? d->r2_o_mbox : d->slab_bytes) - oF - POP_DD_FLAG_BYTES, ctx->stream));
+            if (d->r2_ok) POP_CUDA(cudaMemsetAsync((char *)d->slab + d->r2_o_mbox, 0, (size_t)d->r2_mbox_doubles * 8, ctx->stream));   // stand-in: every entry reads as arrived
         }
     }
     POP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -730,9 +751,28 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
     RowOp op;
     int rc = dd_make_op(d, U, T, gamma, ldf, &op);
     if (rc) return rc;
+    if (d->r2_ok) {
+        // single pass with the hat exchange through mailboxes in peer memory (several GPUs, or forced on one)
+        Row2Remote rem;
+        memset(&rem, 0, sizeof(rem));
+        rem.world = d->world; rem.me = d->rank; rem.csv = d->r2_csv; rem.mlc = d->r2_mlc;
+        rem.standin = d->fake_peers ? 1 : 0;
+        for (int r = 0; r < d->world; ++r) {
+            char *base = (char *)(r == d->rank ? d->slab : d->peer_slab[r]);
+            rem.mbox[r] = (double *)(base + d->r2_o_mbox);
+        }
+        size_t oA, oB, oC, oD, oF;
+        dd_offsets(d, &oA, &oB, &oC, &oD, &oF);
+        rem.merr = (unsigned long long *)((char *)d->slab + oF) + POP_DD_MAXWORLD;
+        rem.epoch = d->r2_epoch + 1;
+        rem.mbox_doubles = d->r2_mbox_doubles;
+        rc = pop_row2_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R, &rem);
+        if (rc == POP_OK) { ++d->r2_epoch; return rc; }
+        if (rc != POP_ROW1_UNSUPPORTED) return rc;
+    }
     if (d->world == 1) {
         // one GPU: the row block stays on chip for the whole half step (pop_row1.cuh), one pass over HBM
-        rc = pop_row2_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R);
+        rc = pop_row2_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R, nullptr);
         if (rc != POP_ROW1_UNSUPPORTED) return rc;
         rc = pop_row1_half_step(ctx, op, (T && gamma != 0.0) ? F : nullptr, R);
         if (rc != POP_ROW1_UNSUPPORTED) return rc;

@@ -153,7 +153,7 @@ int pop_row1_solve_right(pop_ctx *ctx, const pop_arrowhead *U, double *dX, int64
     op.m = u.m; op.nh = u.nh; op.q = u.q; op.k0 = 0; op.ml = u.m; op.hA = 0; op.nhl = u.nh; op.hB = u.nh;
     op.rank = 0; op.world = 1;
     op.nrows = nrhs; op.ld = ldx; op.ldf = 0;
-    const int rc = pop_row2_half_step(ctx, op, nullptr, dX);
+    const int rc = pop_row2_half_step(ctx, op, nullptr, dX, nullptr);
     if (rc != POP_ROW1_UNSUPPORTED) return rc;
     return pop_row1_half_step(ctx, op, nullptr, dX);
 }

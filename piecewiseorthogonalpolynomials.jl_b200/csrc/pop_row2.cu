@@ -58,6 +58,13 @@ struct R2Params {
     int o_in, o_inh, o_fh, o_ring, o_mb, o_hf, o_ct, o_tab, o_ttab, o_ftab, o_hrd, o_hcd, o_hcu, o_ss, o_st, total;
     int mbw;                       // doubles per mailbox message
     long long *dbg;                // POP_ROW2_TRACE: phase time stamps of CTA 0 (clock64), [block][10]
+    // remote mode (several GPUs, or forced): the row direction is split over nr = world * csv CTAs that meet through
+    // mailboxes in (peer) global memory instead of a cluster's shared memory
+    int remote, world, me, csv, nr;
+    int kbase;                     // first element of this GPU's panel (tensor coordinates are panel-local)
+    unsigned long long epoch;      // of this half step; mailbox / flag parity = epoch & 1
+    double *mbox[POP_DD_MAXWORLD];             // mailboxes of all GPUs: [2][nblk][csv readers][nr senders][mbw]
+    unsigned long long *merr;      // error slot (a bounded wait gave up)
 };
 
 // ---- TMA tensor helpers -----------------------------------------------------------------------------------------
@@ -127,6 +134,29 @@ __device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 
+// A mailbox entry.  Cluster mode: shared memory.  Remote mode: an 8-byte word in global memory that another CTA -- of this
+// or of another GPU -- stores exactly once per half step; it holds R2_EMPTY (a NaN no arithmetic produces) until then, the
+// single reader spins on it and puts R2_EMPTY back.  Data and "flag" are the same atomic 8-byte store: no fence, no second
+// round trip over NVLink (the slot is reused two half steps later, ordered by the messages in between).
+#define R2_EMPTY 0xffffffffffffffffull
+__device__ __forceinline__ double r2_mbld(const double *p, int mode, unsigned long long *err) {   // mode 0: shared memory, 1: remote, 2: remote stand-in (profiling: entries are never emptied)
+    if (!mode) return *p;
+    volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(const_cast<double *>(p));
+    unsigned long long v = *q;
+    if (v == R2_EMPTY) {
+        long long spins = 0;
+        while ((v = *q) == R2_EMPTY) {
+            if (++spins > 100000000LL) {   // a peer died: do not hang the device
+                *err = 1;
+                v = 0;
+                break;
+            }
+        }
+    }
+    if (mode == 1) *q = R2_EMPTY;
+    return __longlong_as_double((long long)v);
+}
+
 // CH chain entries per thread: thread (par, e, r) owns the degrees j = 2 i + par, i < CH, of element e in row r.
 // DC degrees per TMA box / ring slot (8, or 4 when shared memory is short: more, smaller slots).
 // Threads [0, 16 mlc) compute; one more warp (the last) is the TMA PRODUCER: it alone issues and waits for the tensor
@@ -153,7 +183,11 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     const int cs = P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch;
     const int nthr = 16 * mlc;         // compute threads
     const R2Fixed LF = r2_fixed(CH, DC, mlc);   // compile-time constants when MLC > 0
-    const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const bool remote = P.remote != 0;
+    const int mbmode = P.remote;                   // 0: cluster (shared-memory mailboxes), 1: remote, 2: remote stand-in
+    const int G = remote ? P.csv : cs;             // CTAs that share a row block on this GPU
+    const int nr = remote ? P.nr : cs;             // ... and over all GPUs
+    const int rank = remote ? P.me * P.csv + (int)(blockIdx.x % (unsigned)P.csv) : (cs > 1 ? (int)cluster_ctarank() : 0);
     const int m = P.m, nh = P.nh, q = P.q;
     const bool mul = P.nbT >= 0;
     const bool useF = P.useF != 0;
@@ -179,7 +213,8 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     const int HBS = LF.hbs / 8;               // distance of the two parity buffers (TMA destinations: 128 B aligned)
     const int mbw = P.mbw;
     const int k0 = rank * mlc;
-    const int hA = k0, hB = rank == cs - 1 ? nh : min(nh, k0 + mlc);
+    const int hA = k0, hB = rank == nr - 1 ? nh : min(nh, k0 + mlc);
+    const int kx0 = k0 - P.kbase;                  // element / hat coordinate inside this GPU's panel
     const int nhl = max(hB - hA, 0);
     const bool producer = tid >= nthr;   // set-up: everybody but the compute threads idles
 
@@ -255,7 +290,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     // row blocks of this cluster: block t is number bbase + t * bstride.  With pairing, two clusters walk through
     // neighbouring row blocks side by side, so that both 64 B halves of every 128 B line are requested within
     // microseconds of each other (the second request hits L2 instead of fetching the line from HBM again).
-    const int ncl = gridDim.x / cs, cl = blockIdx.x / cs;
+    const int ncl = gridDim.x / G, cl = blockIdx.x / G;
     int bbase, bstride, nloc;
     if (P.pairing) {
         const int npt = (P.nblk + 1) / 2, npc = ncl / 2;
@@ -287,12 +322,12 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             const uint32_t cbytes = (uint32_t)(CBD * 8);
             auto load_x = [&](int t, int c) {      // chunk c of block t -> region NCM-1-c
                 mbar_expect_tx(barX + c, cbytes);
-                tma_load_3d(IN + (NCM - 1 - c) * CBD, &P.mapX3, (bbase + t * bstride) * R2_RB, k0, DC * c, barX + c);
+                tma_load_3d(IN + (NCM - 1 - c) * CBD, &P.mapX3, (bbase + t * bstride) * R2_RB, kx0, DC * c, barX + c);
             };
             auto load_h = [&](int t) {             // hats of block t (and of F)
                 mbar_expect_tx(barH + (t & 1), (uint32_t)(HBD * 8 * (useF ? 2 : 1)));
-                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, (bbase + t * bstride) * R2_RB, hA, barH + (t & 1));
-                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, (bbase + t * bstride) * R2_RB, hA, barH + (t & 1));
+                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, (bbase + t * bstride) * R2_RB, kx0, barH + (t & 1));
+                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, (bbase + t * bstride) * R2_RB, kx0, barH + (t & 1));
             };
             load_h(0);
             for (int c = nch - 1; c >= 0; --c) load_x(0, c);
@@ -304,7 +339,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 if (useF)
                     for (int r = 0; r < NCM - nch && r < nch; ++r) {   // regions that never hold X (q below the class maximum)
                         mbar_expect_tx(barF + r, cbytes);
-                        tma_load_3d(IN + r * CBD, &P.mapF3, row0, k0, DC * r, barF + r);
+                        tma_load_3d(IN + r * CBD, &P.mapF3, row0, kx0, DC * r, barF + r);
                     }
                 for (int c = nch - 1; c >= 0; --c) {
                     const int r = NCM - 1 - c;
@@ -312,7 +347,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     if (r < nch) {
                         if (useF) {
                             mbar_expect_tx(barF + r, cbytes);
-                            tma_load_3d(IN + r * CBD, &P.mapF3, row0, k0, DC * r, barF + r);
+                            tma_load_3d(IN + r * CBD, &P.mapF3, row0, kx0, DC * r, barF + r);
                         }
                     } else if (more) {
                         load_x(t + 1, c);
@@ -322,7 +357,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 // phase 2: results out, X(t+1) in behind them
                 for (int r = 0; r < nch; ++r) {
                     mbar_wait(barR + r, ph);
-                    tma_store_3d(&P.mapX3, row0, k0, DC * r, IN + r * CBD);
+                    tma_store_3d(&P.mapX3, row0, kx0, DC * r, IN + r * CBD);
                     tma_commit();
                     if (r >= 1) {
                         tma_wait_read<1>();            // the store of region r-1 has read it
@@ -437,7 +472,9 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             const uint32_t phMB = (uint32_t)(t >> 1) & 1u;
             const int row0 = (bbase + t * bstride) * R2_RB;
             const double *inh = INH + pb * HBS, *fh = FH + pb * HBS;
-            double *mbme = MB + ((size_t)pb * cs + rank) * mbw;
+            double *mbme = remote ? MB : MB + ((size_t)pb * cs + rank) * mbw;   // remote: staging of my message only
+            const size_t mslot = ((size_t)(P.epoch & 1) * P.nblk + (size_t)(bbase + t * bstride)) * G;   // mailboxes of this row block: one per reading CTA
+            const double *mbp = remote ? P.mbox[P.me] + (mslot + (blockIdx.x % (unsigned)G)) * nr * mbw : MB + (size_t)pb * cs * mbw;
             // ---- A+B: the row block, shared memory -> registers, chunk by chunk from the top degrees down, and the
             //      backward sweep  z_j = (b_j - w2_j z_{j+2}) rd_j  on the way
             R2_STAMP(0);
@@ -516,7 +553,15 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 }
                 mbme[tid] = v;
             }
-            if (cs > 1) {
+            if (remote) {
+                // my message into the mailbox of every CTA that shares this row block, on every GPU (mine included)
+                named_bar_sync(R2_BAR_COMPUTE, nthr);
+                for (int g = 0; g < P.world; ++g)
+                    for (int dc = 0; dc < G; ++dc) {
+                        volatile double *dst = P.mbox[g] + ((mslot + dc) * nr + rank) * mbw;
+                        for (int x = tid; x < mbw; x += nthr) dst[x] = mbme[x];
+                    }
+            } else if (cs > 1) {
                 fence_proxy_async();
                 named_bar_sync(R2_BAR_COMPUTE, nthr);
                 if (tid < cs && tid != rank) dsmem_bulk_copy(mapa_u32(mbme, tid), mbme, (uint32_t)(mbw * 8), mapa_u32(barMB + pb, tid));
@@ -540,17 +585,21 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             R2_STAMP(5);
             // the messages of the peers have landed long ago (plain CTA-scope wait: the bytes were written into this CTA's
             // shared memory by the async proxy and completed on this CTA's mbarrier, as for a TMA load)
-            if (cs > 1) mbar_wait(barMB + pb, phMB);
-            else named_bar_sync(R2_BAR_COMPUTE, nthr);
+            if (remote) {
+                // nothing to wait for here: the mailbox loads below spin on the entries themselves
+            } else if (cs > 1) {
+                mbar_wait(barMB + pb, phMB);
+            } else {
+                named_bar_sync(R2_BAR_COMPUTE, nthr);
+            }
             {
                 // right-hand sides (times rd) of ALL hats of the 8 rows, redundantly in every CTA
-                const double *mbp = MB + (size_t)pb * cs * mbw;
                 for (int x = tid; x < nh * R2_RB; x += nthr) {
                     const int i = x / R2_RB, rr = x % R2_RB;
-                    const int c = min(i / mlc, cs - 1), u = i - c * mlc;
-                    double v = mbp[c * mbw + (u + 1) * R2_RB + rr];
-                    if (u == 0 && c > 0) v += mbp[(c - 1) * mbw + (mlc + 1) * R2_RB + rr];
-                    if (u == mlc - 1 && c < cs - 1) v += mbp[(c + 1) * mbw + rr];
+                    const int c = min(i / mlc, nr - 1), u = i - c * mlc;
+                    double v = r2_mbld(mbp + c * mbw + (u + 1) * R2_RB + rr, mbmode, P.merr);
+                    if (u == 0 && c > 0) v += r2_mbld(mbp + (c - 1) * mbw + (mlc + 1) * R2_RB + rr, mbmode, P.merr);
+                    if (u == mlc - 1 && c < nr - 1) v += r2_mbld(mbp + (c + 1) * mbw + rr, mbmode, P.merr);
                     HF[(i + 1) * R2_RB + rr] = v * hrd[i];
                 }
             }
@@ -653,7 +702,6 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     double acc = P.TAd[i] * hc;
                     if (i + 1 < nh) acc = fma(P.TAu[i], hn, acc);
                     if (i > 0) acc = fma(P.TAu[i - 1], hp, acc);
-                    const double *mbp = MB + (size_t)pb * cs * mbw;
 #pragma unroll
                     for (int tt = 0; tt < 3; ++tt) {
                         const int el = u + 1 - tt, kk = k0 + el;   // slot tt of element kk couples to hat i
@@ -669,7 +717,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                             double xs[R2_NBMAX];
 #pragma unroll
                             for (int b = 0; b < R2_NBMAX; ++b) {
-                                double v = zz[b * R2_RB];
+                                double v = r2_mbld(zz + b * R2_RB, mbmode, P.merr);
                                 if (b < P.nb) {
                                     const double *sg = P.S + (size_t)b * 3 * m + kk;
                                     v = fma(-__ldg(sg), g0, v);
@@ -686,7 +734,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     }
                     out = useF ? fma(P.gamma, fh[u * R2_RB + rr], acc) : acc;
                 }
-                if (rw < P.nrows) P.X[rw + (int64_t)i * P.ld] = out;
+                if (rw < P.nrows) P.X[rw + (int64_t)(i - P.kbase) * P.ld] = out;   // hats come first in the panel
             }
             named_bar_sync(R2_BAR_COMPUTE, nthr);   // HF, ct / xb and the mailboxes of this parity are rewritten by later blocks
             R2_STAMP(9);
@@ -763,9 +811,26 @@ static r2_kernel_t r2_kernel(int ch, int dc, int mlc) {
 
 static int r2_align(int x, int a) { return (x + a - 1) / a * a; }
 
+// Remote mode plan for a decomposition of m elements over `world` GPUs: CTAs per row block and GPU (csv), elements per
+// CTA (mlc), doubles per message.  false: the shape is not covered (the two-pass kernels of pop_row.cu serve it).
+bool pop_row2_remote_plan(int m, int world, int *csv, int *mlc, int *mbw) {
+    if (world < 1 || m % world) return false;
+    const int ml = m / world;
+    for (int c = 1; c <= 8; c <<= 1) {
+        if (ml % c) continue;
+        const int e = ml / c;
+        if (e < 2 || (e & 1) || 16 * e > 512) continue;
+        *csv = c;
+        *mlc = e;
+        *mbw = (e + 2) * R2_RB + 2 * R2_NBMAX * R2_RB;
+        return true;
+    }
+    return false;
+}
+
 // POP_OK, an error, or POP_ROW1_UNSUPPORTED (the caller falls back to the older row kernels)
-int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R) {
-    if (op.world != 1 || r2_env("POP_ROW2", 1) == 0) return POP_ROW1_UNSUPPORTED;
+int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R, const Row2Remote *rem) {
+    if ((op.world != 1 && !rem) || r2_env("POP_ROW2", 1) == 0) return POP_ROW1_UNSUPPORTED;
     const bool strict = r2_env("POP_ROW2_STRICT", 0) != 0;
     auto unsupported = [&](const char *why) -> int {
         if (strict) {
@@ -783,18 +848,25 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     if (!enc) return unsupported("cuTensorMapEncodeTiled is not available");
     const int ch = op.q <= 16 ? 8 : op.q <= 32 ? 16 : op.q <= 48 ? 24 : 32;
     const int want_cs = r2_env("POP_ROW2_CS", 0);
-    int cs = 0;
-    for (int c = 1; c <= R2_MAXCS; c <<= 1) {
-        if (want_cs && c != want_cs) continue;
-        if (op.m % c) continue;
-        const int mlc = op.m / c;
-        if (mlc < 1 || 16 * mlc > 512) continue;
-        if (c > 1 && mlc < 2) continue;
-        cs = c;
-        break;
+    int cs = 0, mlc = 0;
+    if (rem) {
+        // several GPUs (or forced): no cluster, the plan was fixed when the mailboxes were allocated
+        if (op.ml * op.world != op.m || op.k0 != op.rank * op.ml || rem->csv * rem->mlc != op.ml) return unsupported("uneven element decomposition");
+        cs = 1;
+        mlc = rem->mlc;
+    } else {
+        for (int c = 1; c <= R2_MAXCS; c <<= 1) {
+            if (want_cs && c != want_cs) continue;
+            if (op.m % c) continue;
+            const int e = op.m / c;
+            if (e < 1 || 16 * e > 512) continue;
+            if (c > 1 && e < 2) continue;
+            cs = c;
+            break;
+        }
+        if (!cs) return unsupported("no cluster size with m % cs == 0 and 16 * m / cs <= 512 threads");
+        mlc = op.m / cs;
     }
-    if (!cs) return unsupported("no cluster size with m % cs == 0 and 16 * m / cs <= 512 threads");
-    const int mlc = op.m / cs;
     if (mlc + 1 > 256) return unsupported("hat box too wide");
     const int nthr = 16 * mlc;
     if (nthr % 32) return unsupported("elements per CTA must be even");   // whole warps: the named barrier and the hat scan need them
@@ -805,6 +877,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     const int hf_rows = std::max(8 * lp + 2, op.m + 3);
     // behind the ring: HF, the padded hat tables, the mailboxes
     const int tail = r2_align(hf_rows * R2_RB * 8, 128) + 2 * r2_align(8 * lp * 8, 128) + r2_align(3 * 8 * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
+    (void)want_cs;
     // degrees per chunk (TMA box, region of the row block buffer): 4 keeps the hand-over between the blocks fine-grained
     const int dc = r2_env("POP_ROW2_DC", 4) == 8 ? 8 : 4;
     const int nch = (op.q + dc - 1) / dc;
@@ -823,9 +896,10 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.hf_rows = hf_rows;
     P.pf_dist = r2_env("POP_ROW2_PF", 0);   // L2 prefetch distance of F in row blocks (0: off)
 
-    if (!r2_make_maps(enc, R, op.ld, op.nrows, op.m, op.nh, op.q, mlc, dc, &P.mapX3, &P.mapXh)) return unsupported("cuTensorMapEncodeTiled rejected the panel");
+    const int pm = rem ? op.ml : op.m, pnh = rem ? op.nhl : op.nh;   // the panel: all elements, or this GPU's
+    if (!r2_make_maps(enc, R, op.ld, op.nrows, pm, pnh, op.q, mlc, dc, &P.mapX3, &P.mapXh)) return unsupported("cuTensorMapEncodeTiled rejected the panel");
     if (useF) {
-        if (!r2_make_maps(enc, F, op.ldf, op.nrows, op.m, op.nh, op.q, mlc, dc, &P.mapF3, &P.mapFh)) return unsupported("cuTensorMapEncodeTiled rejected F");
+        if (!r2_make_maps(enc, F, op.ldf, op.nrows, pm, pnh, op.q, mlc, dc, &P.mapF3, &P.mapFh)) return unsupported("cuTensorMapEncodeTiled rejected F");
     } else {
         P.mapF3 = P.mapX3;
         P.mapFh = P.mapXh;
@@ -838,6 +912,14 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.m = op.m; P.nh = op.nh; P.q = op.q;
     P.cs = cs; P.mlc = mlc; P.nch = nch;
     P.nblk = (int)((op.nrows + R2_RB - 1) / R2_RB);
+    if (rem) {
+        P.remote = rem->standin ? 2 : 1; P.world = rem->world; P.me = rem->me; P.csv = rem->csv; P.nr = rem->world * rem->csv;
+        P.kbase = op.k0;
+        P.epoch = rem->epoch;
+        for (int g = 0; g < rem->world; ++g) P.mbox[g] = rem->mbox[g];
+        P.merr = rem->merr;
+        if ((int64_t)2 * P.nblk * P.csv * P.nr * P.mbw > rem->mbox_doubles) return unsupported("mailbox too small");
+    }
 
     r2_kernel_t kern = r2_kernel(ch, dc, mlc);
     POP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.total));
@@ -854,17 +936,27 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     cfg.numAttrs = 1;
     static std::mutex plan_mu;
     static int cached_key[5] = {0, 0, 0, 0, -1}, cached_ncl = 0;
-    const int key[5] = {ch * 16 + dc + (mlc == 32 ? 1024 : 0), cs, nthr, P.total, ctx->device};
+    const int key[5] = {ch * 16 + dc + (mlc == 32 ? 1024 : 0) + (rem ? 4096 : 0), rem ? rem->csv : cs, nthr, P.total, ctx->device};
     int ncl;
     {
         std::lock_guard<std::mutex> lk(plan_mu);
         ncl = cached_ncl;
         if (!std::equal(key, key + 5, cached_key) || ncl <= 0) {
-            cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count));
             int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, (const void *)kern, &cfg) != cudaSuccess || nc <= 0) {
-                cudaGetLastError();
-                return unsupported("no co-resident cluster");
+            if (rem) {
+                // every CTA of the grid must be resident: the CTAs of a row block wait for each other through the mailboxes
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, 640, (size_t)P.total) != cudaSuccess || per_sm < 1) {
+                    cudaGetLastError();
+                    return unsupported("kernel does not fit an SM");
+                }
+                nc = ctx->sm_count / rem->csv;   // one CTA per SM, the same grid on every GPU
+            } else {
+                cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count));
+                if (cudaOccupancyMaxActiveClusters(&nc, (const void *)kern, &cfg) != cudaSuccess || nc <= 0) {
+                    cudaGetLastError();
+                    return unsupported("no co-resident cluster");
+                }
             }
             ncl = nc;
             std::copy(key, key + 5, cached_key);
@@ -875,7 +967,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     ncl = std::min(ncl, P.nblk);
     P.pairing = (ncl >= 2 && r2_env("POP_ROW2_PAIR", 1)) ? 1 : 0;
     if (P.pairing) ncl &= ~1;
-    cfg.gridDim = dim3((unsigned)(ncl * cs));
+    cfg.gridDim = dim3((unsigned)(ncl * (rem ? rem->csv : cs)));
     if (r2_env("POP_ROW2_VERBOSE", 0))
         fprintf(stderr, "pop_row2: chain %d per thread, cluster %d x %d threads, %d B smem, chunks of %d degrees, %d clusters, %d row blocks, F %d\n", ch, cs, nthr, P.total, dc, ncl,
                 P.nblk, P.useF);

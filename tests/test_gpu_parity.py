@@ -637,6 +637,51 @@ def test_single_pass_tma_row_half_step(basis, m, N, cs, monkeypatch):
     dd.close()
 
 
+@pytest.mark.parametrize("basis,m,N", [("dirichlet", 64, 7), ("c1", 64, 4), ("dirichlet", 128, 5), ("dirichlet", 16, 12)])
+def test_single_pass_row_remote_mailboxes(basis, m, N, monkeypatch):
+    """csrc/pop_row2.cu in REMOTE mode -- the CTAs that share a row block meet through mailboxes and flags in global memory,
+    the way the GPUs of a multi-GPU run do -- forced on one GPU (POP_ROW2_REMOTE=1; m = 64: 2 CTAs per row block, m = 128: 4):
+    against dense algebra and the cluster mode of the same kernel, repeated calls (mailbox parity and epochs)."""
+    from pop_b200 import _lib as L
+    from pop_b200.arrowhead import _bind_stream
+    M, Lp, Mo, Lo = _assemble(basis, m, N)
+    K = -Lp
+    Ko = O.packed_axpby(-1.0, Lo, 0.0, Mo)
+    Md, Kd = O.unpack(O.packed_symmetrize(Mo)).to_dense(), O.unpack(O.packed_symmetrize(Ko)).to_dense()
+    n = Mo.n
+    rng = np.random.default_rng(13)
+    Rm, Fm = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    if basis == "c1":
+        Kd = Kd + 0.3 * Md
+        K = K + 0.3 * M
+    Sd, Td = Kd + 3.7 * Md, 0.5 * Md - Kd
+    Xd = np.linalg.solve(Sd, Rm.T).T
+    Fs = P.reversecholesky(K + 3.7 * M)
+    T = 0.5 * M - K
+    ctx = M.data.ctx
+    _bind_stream(ctx)
+    monkeypatch.setenv("POP_ROW1", "0")
+    monkeypatch.setenv("POP_ROW2", "1")
+    monkeypatch.setenv("POP_ROW2_STRICT", "1")
+    got = {}
+    for mode in ("remote", "cluster"):
+        monkeypatch.setenv("POP_ROW2_REMOTE", "1" if mode == "remote" else "0")
+        dd = P.ElementDecomposition(M)                       # the mailboxes are allocated with the decomposition
+        R, Fd = dd.panel(), dd.panel()
+        Fd.copy_(torch.from_numpy(Fm).cuda())
+        for rep in range(3):                                 # epochs 1, 2, 3: both mailbox parities, reuse of a slot
+            for what, Top, gamma, Fp, want in (("half step", T, -0.4, Fd, Xd @ Td - 0.4 * Fm), ("solve", None, 0.0, None, Xd)):
+                R.copy_(torch.from_numpy(Rm).cuda())
+                L.check(L.lib().pop_dd_row_half_step(ctx.handle, dd._h, Fs.factor._h, Top.data._h if Top is not None else None, gamma,
+                                                     Fp.data_ptr() if Fp is not None else None, Fp.stride(1) if Fp is not None else 0, R.data_ptr(), R.stride(1)))
+                torch.cuda.synchronize()
+                got[mode, what] = host(R)
+                assert relerr(got[mode, what], want) < TOL, (mode, what, rep)
+        dd.close()
+    for what in ("half step", "solve"):
+        assert np.array_equal(got["remote", what], got["cluster", what]), what
+
+
 def test_heat_steps_vs_oracle():
     # examples/heat.jl:58-63 (1D) and its factored 2D extension
     m, N = 6, 10
