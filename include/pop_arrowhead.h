@@ -102,6 +102,10 @@ int pop_arrowhead_desc(const pop_arrowhead *A, pop_desc *desc);
 int pop_arrowhead_download(pop_ctx *ctx, const pop_arrowhead *A, int expand_uniform, double *Ad,
                            double *Au, double *Al, double *B, double *C, double *D);
 int pop_arrowhead_free(pop_ctx *ctx, pop_arrowhead *A);
+/* The upper data of A already hold a reverse-Cholesky factor U (S = U U^T), e.g. `F.U` of a ReverseCholesky the
+ * reference computed on the host (src/arrowhead.jl:276-292): make the handle usable by pop_solve / pop_solve_mul_axpy
+ * without factoring again.  >0: 1-based index of a non-positive pivot. */
+int pop_arrowhead_as_factor(pop_ctx *ctx, pop_arrowhead *A);
 /* copy(A), src/arrowhead.jl:64 ; reversecholcopy, :266-272 */
 int pop_arrowhead_copy(pop_ctx *ctx, const pop_arrowhead *A, pop_arrowhead **out);
 

@@ -68,6 +68,7 @@ _PROTOS = {
     "pop_arrowhead_desc": (C.c_int, [vp, C.POINTER(pop_desc)]),
     "pop_arrowhead_download": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]),
     "pop_arrowhead_free": (C.c_int, [vp, vp]),
+    "pop_arrowhead_as_factor": (C.c_int, [vp, vp]),
     "pop_arrowhead_copy": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "pop_assemble": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(vp), C.POINTER(vp)]),
     "pop_assemble_mesh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp)]),

@@ -532,6 +532,14 @@ def reversecholesky(S) -> ReverseCholesky:
     return ReverseCholesky(BBBArrowheadMatrix(ctx=base.ctx, _handle=h))
 
 
+def as_reversecholesky(U) -> ReverseCholesky:
+    """ReverseCholesky from an arrowhead whose upper data already hold the factor U (S = U U'), e.g. one computed by the
+    reference on the host and uploaded: no second factorisation (pop_arrowhead_as_factor)."""
+    base = U.data if isinstance(U, _Wrapper) else _plain(U)
+    L.check(L.lib().pop_arrowhead_as_factor(base.ctx.handle, base._h), "as_reversecholesky")
+    return ReverseCholesky(base)
+
+
 def reversecholesky_inplace(S) -> ReverseCholesky:
     """reversecholesky!(Symmetric(S)): overwrites the upper data of S (test/test_arrowhead.jl:90)."""
     base = S.data if isinstance(S, Symmetric) else _plain(S)

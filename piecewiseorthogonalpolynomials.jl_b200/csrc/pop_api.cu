@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <limits.h>
+
 #include "pop_internal.h"
 
 // ------------------------------------------------------------------------------------
@@ -434,6 +436,37 @@ __global__ void k_recip(ArrowPtrs p, int nh, int lD, size_t plane) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (size_t)nh) p.rdA[i] = 1.0 / p.Ad[i];
     if (i < plane) p.rdD[i] = 1.0 / p.D[(size_t)lD * plane + i];
+}
+
+// The upper data of A already hold a reverse-Cholesky factor U (S = U U'), e.g. one the reference computed on the host:
+// `F.U` of a ReverseCholesky object.  Marks the handle as a factor for pop_solve / pop_solve_mul_axpy (reciprocal pivots
+// are computed once).  Non-positive or non-finite pivots are rejected like a failed factorisation (1-based index).
+__global__ void k_check_pivots(ArrowPtrs p, int nh, size_t lD_off, size_t plane, int *info) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)nh && !(p.Ad[i] > 0.0) ) atomicMin(info, (int)i + 1);
+    if (i < plane && !(p.D[lD_off + i] > 0.0)) atomicMin(info, nh + (int)i + 1);
+}
+extern "C" int pop_arrowhead_as_factor(pop_ctx *ctx, pop_arrowhead *A) {
+    POP_REQUIRE(ctx && A, POP_ERR_ARG, "pop_arrowhead_as_factor: null argument");
+    const size_t plane = (size_t)A->d.q * A->mD;
+    const size_t n = std::max<size_t>(plane, (size_t)A->d.nh);
+    int big = INT_MAX;
+    POP_CUDA(cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        k_check_pivots<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(A->p, A->d.nh, (size_t)A->d.lD * plane, plane, ctx->d_info);
+        LAUNCH_COUNT(ctx);
+    }
+    POP_CUDA(cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_info[0] != INT_MAX) {
+        pop_set_error("pop_arrowhead_as_factor: pivot %d of the factor is not positive", ctx->h_info[0]);
+        return ctx->h_info[0];
+    }
+    A->has_recip = false;
+    int rc = pop_ensure_recip(ctx, A);
+    if (rc) return rc;
+    A->is_factor = true;
+    return POP_OK;
 }
 
 int pop_ensure_recip(pop_ctx *ctx, pop_arrowhead *A) {

@@ -49,7 +49,7 @@ struct pop_dd {
     bool hats_planned;
     // mailboxes of the single-pass row kernel in remote mode (pop_row2.cu), inside the peer-visible slab
     bool r2_ok;
-    int r2_csv, r2_mlc, r2_mbw;
+    int r2_csv, r2_mlc, r2_rb, r2_mbw;
     size_t r2_o_mbox, r2_o_flag;
     int64_t r2_mbox_doubles;
     unsigned long long r2_epoch;
@@ -110,8 +110,8 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
         // mailboxes [2][row blocks of 8][world * csv][mbw] and flags of k_row2's remote mode (several GPUs; one GPU: POP_ROW2_REMOTE=1)
         const char *e = getenv("POP_ROW2_REMOTE");
         const bool want = world > 1 ? !(e && !atoi(e)) : (e && atoi(e));
-        if (want && pop_row2_remote_plan(m, world, &d->r2_csv, &d->r2_mlc, &d->r2_mbw)) {
-            const int64_t nblk = (d->nrows + 7) / 8, nr = (int64_t)world * d->r2_csv;
+        if (want && pop_row2_remote_plan(m, world, &d->r2_csv, &d->r2_mlc, &d->r2_rb, &d->r2_mbw)) {
+            const int64_t nblk = (d->nrows + d->r2_rb - 1) / d->r2_rb, nr = (int64_t)world * d->r2_csv;
             d->r2_o_mbox = (d->slab_bytes + 255) & ~(size_t)255;
             d->r2_mbox_doubles = 2 * nblk * d->r2_csv * nr * d->r2_mbw;   // one mailbox per reading CTA
             d->r2_o_flag = d->r2_o_mbox + (size_t)d->r2_mbox_doubles * 8;
@@ -755,7 +755,7 @@ static int dd_row_half_step(pop_ctx *ctx, pop_dd *d, const pop_arrowhead *U, con
         // single pass with the hat exchange through mailboxes in peer memory (several GPUs, or forced on one)
         Row2Remote rem;
         memset(&rem, 0, sizeof(rem));
-        rem.world = d->world; rem.me = d->rank; rem.csv = d->r2_csv; rem.mlc = d->r2_mlc;
+        rem.world = d->world; rem.me = d->rank; rem.csv = d->r2_csv; rem.mlc = d->r2_mlc; rem.rb = d->r2_rb;
         rem.standin = d->fake_peers ? 1 : 0;
         for (int r = 0; r < d->world; ++r) {
             char *base = (char *)(r == d->rank ? d->slab : d->peer_slab[r]);

@@ -38,12 +38,12 @@ int pop_row1_solve_right(pop_ctx *ctx, const pop_arrowhead *U, double *dX, int64
 // rem != null: the row direction is split over several GPUs (RowOp describes this GPU's panel); the CTAs that share a
 // row block meet through mailboxes in peer-visible global memory (allocated by pop_dd_create for the plan below).
 struct Row2Remote {
-    int world, me, csv, mlc;
+    int world, me, csv, mlc, rb;
     int standin;                                 // profiling aid (POP_DD_FAKE_PEERS): one GPU stands in for a rank, nobody answers
     double *mbox[POP_DD_MAXWORLD];               // [2][row blocks][csv readers][world * csv senders][mbw] doubles on every GPU, all bits set when empty
     unsigned long long *merr;                    // this GPU's error slot
     unsigned long long epoch;                    // one per half step, the same on every GPU
     int64_t mbox_doubles;                        // capacity of a mailbox
 };
-bool pop_row2_remote_plan(int m, int world, int *csv, int *mlc, int *mbw);
+bool pop_row2_remote_plan(int m, int world, int *csv, int *mlc, int *rb, int *mbw);
 int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R, const Row2Remote *rem);

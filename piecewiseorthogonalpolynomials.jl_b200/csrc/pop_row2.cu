@@ -101,16 +101,16 @@ struct R2Fixed {
     int in, inh, fh, ct, tab, ttab, ftab, gtab, ss, st, ring, cb, hbs;
 };
 __host__ __device__ constexpr int r2_al(int x) { return (x + 127) / 128 * 128; }
-__host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc) {
+__host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc, int rb) {
     R2Fixed f = {};
     const int nchmax = (2 * ch + dc - 1) / dc;
-    f.cb = dc * mlc * R2_RB * 8;
-    f.hbs = r2_al((mlc + 1) * R2_RB * 8);
+    f.cb = dc * mlc * rb * 8;
+    f.hbs = r2_al((mlc + 1) * rb * 8);
     int o = 1024;                                // mbarriers
     f.in = o; o += nchmax * f.cb;
     f.inh = o; o += 2 * f.hbs;
     f.fh = o; o += 2 * f.hbs;
-    f.ct = o; o += r2_al(4 * mlc * R2_RB * 8);
+    f.ct = o; o += r2_al(4 * mlc * rb * 8);
     f.tab = o; o += r2_al((2 * ch + 2) * 16);
     f.ttab = o; o += r2_al((2 * ch + 2) * 16);
     f.ftab = o; o += r2_al((2 * ch + 2) * 16);
@@ -168,7 +168,8 @@ __device__ __forceinline__ double r2_mbld(const double *p, int mode, unsigned lo
 #define R2_BAR_MSG 3       // compute threads (arrive) + the two hat warps (sync): this CTA's message is written
 #define R2_COMPUTE_SLOTS 512   // threads [0, 512): compute (the first 16 mlc of them work), [512, 640): producer warp group
 // MLC > 0: elements per CTA fixed at compile time (every hot shared-memory address is then one register plus an immediate).
-template <int CH, int DC, int MLC>
+// RB rows per block: 8 (64 B runs; clusters / groups walk in pairs) or 16 (128 B runs; for panels of few elements per CTA).
+template <int CH, int DC, int MLC, int RB>
 __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Params P) {
     extern __shared__ __align__(128) unsigned char r2_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(r2_raw);
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     uint64_t *barR = barF + NCM;       // [NCM] every compute warp has written its results of chunk c into region c
     const int tid = threadIdx.x;
     const int cs = P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch;
-    const int nthr = 16 * mlc;         // compute threads
-    const R2Fixed LF = r2_fixed(CH, DC, mlc);   // compile-time constants when MLC > 0
+    const int nthr = 2 * RB * mlc;     // compute threads
+    const R2Fixed LF = r2_fixed(CH, DC, mlc, RB);   // compile-time constants when MLC > 0
     const bool remote = P.remote != 0;
     const int mbmode = P.remote;                   // 0: cluster (shared-memory mailboxes), 1: remote, 2: remote stand-in
     const int G = remote ? P.csv : cs;             // CTAs that share a row block on this GPU
@@ -204,12 +205,12 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     double *hrd = reinterpret_cast<double *>(r2_raw + P.o_hrd);     // [nh]
     double *hcd = reinterpret_cast<double *>(r2_raw + P.o_hcd);     // off(i,i+1) rd_i
     double *hcu = reinterpret_cast<double *>(r2_raw + P.o_hcu);     // off(i-1,i) rd_i
-    double *hwd = hcu + 8 * P.lp;                                   // weights of the downward segment maps
-    double *hwu = hwd + 8 * P.lp;                                   // weights of the upward segment maps (times rd_i)
+    double *hwd = hcu + (64 / RB) * P.lp;                                   // weights of the downward segment maps
+    double *hwu = hwd + (64 / RB) * P.lp;                                   // weights of the upward segment maps (times rd_i)
     double *sS = reinterpret_cast<double *>(r2_raw + LF.ss);       // [4][3][mlc]
     double *sT = reinterpret_cast<double *>(r2_raw + LF.st);       // [4][3][mlc]
     const int CBD = LF.cb / 8;                // doubles per chunk of DC degrees
-    const int HBD = (mlc + 1) * R2_RB;        // doubles per hat box
+    const int HBD = (mlc + 1) * RB;        // doubles per hat box
     const int HBS = LF.hbs / 8;               // distance of the two parity buffers (TMA destinations: 128 B aligned)
     const int mbw = P.mbw;
     const int k0 = rank * mlc;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             ttab[j] = make_double2((in && mul) ? P.t0[j] : 0.0, (in && mul && P.t2 && j + 2 < q) ? P.t2[j] : 0.0);
             ftab[j] = make_double2(in ? P.rd[j] : 0.0, (in && P.w2 && j >= 2) ? P.w2[j - 2] : 0.0);
         }
-        for (int i = tid; i < 8 * P.lp; i += nthr) {   // padded to 8 scan segments of lp hats: zeros behind the last hat
+        for (int i = tid; i < (64 / RB) * P.lp; i += nthr) {   // padded to the 64 / RB scan segments of lp hats: zeros behind the last hat
             const double rdv = i < nh ? P.rdA[i] : 0.0;
             hrd[i] = rdv;
             hcd[i] = (i < nh - 1 ? P.offA[i] : 0.0) * rdv;
@@ -250,11 +251,11 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             sS[x] = b < P.nb ? P.S[((size_t)b * 3 + t) * m + k0 + e] : 0.0;
             sT[x] = (mul && b < P.nbT) ? P.Ts[((size_t)b * 3 + t) * m + k0 + e] : 0.0;
         }
-        for (int x = tid; x < P.hf_rows * R2_RB; x += nthr)   // zero pads around the hats: entry 0 and everything behind hat nh-1
-            if (x < R2_RB || x >= (nh + 1) * R2_RB) HF[x] = 0.0;
+        for (int x = tid; x < P.hf_rows * RB; x += nthr)   // zero pads around the hats: entry 0 and everything behind hat nh-1
+            if (x < RB || x >= (nh + 1) * RB) HF[x] = 0.0;
     }
     __syncthreads();
-    if (tid < 8) {
+    if (tid < 64 / RB) {
         // segment maps of the two hat recurrences: h_bottom = sum_i wd_i ytil_i + Ad h_in (downward),
         // x_top = sum_i wu_i h_i + Au x_in (upward, wu includes rd_i); the products Ad, Au are rebuilt by the hat lanes
         const int sg = tid, a0 = sg * P.lp;
@@ -322,17 +323,17 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             const uint32_t cbytes = (uint32_t)(CBD * 8);
             auto load_x = [&](int t, int c) {      // chunk c of block t -> region NCM-1-c
                 mbar_expect_tx(barX + c, cbytes);
-                tma_load_3d(IN + (NCM - 1 - c) * CBD, &P.mapX3, (bbase + t * bstride) * R2_RB, kx0, DC * c, barX + c);
+                tma_load_3d(IN + (NCM - 1 - c) * CBD, &P.mapX3, (bbase + t * bstride) * RB, kx0, DC * c, barX + c);
             };
             auto load_h = [&](int t) {             // hats of block t (and of F)
                 mbar_expect_tx(barH + (t & 1), (uint32_t)(HBD * 8 * (useF ? 2 : 1)));
-                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, (bbase + t * bstride) * R2_RB, kx0, barH + (t & 1));
-                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, (bbase + t * bstride) * R2_RB, kx0, barH + (t & 1));
+                tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, (bbase + t * bstride) * RB, kx0, barH + (t & 1));
+                if (useF) tma_load_2d(FH + (t & 1) * HBS, &P.mapFh, (bbase + t * bstride) * RB, kx0, barH + (t & 1));
             };
             load_h(0);
             for (int c = nch - 1; c >= 0; --c) load_x(0, c);
             for (int t = 0; t < nloc; ++t) {
-                const int row0 = (bbase + t * bstride) * R2_RB;
+                const int row0 = (bbase + t * bstride) * RB;
                 const uint32_t ph = (uint32_t)t & 1u;
                 const bool more = t + 1 < nloc;
                 // phase 1: regions drain (backward sweep) -> F(t) in, or X(t+1) where the region never holds results
@@ -382,9 +383,10 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             // its map (A, B), the maps are composed across the 8 segments by shuffles, then the segment re-runs with the
             // exact incoming value -- and builds the map of the second recurrence in the same pass.  (These warps run
             // on 32 registers: the compute warps need the rest.)
-            const int lane = tid & 31, rr = (lane & 3) + 4 * ((tid - R2_COMPUTE_SLOTS - 32) >> 5), seg = lane >> 2;
+            constexpr int RW = RB / 2, NSEG = 32 / RW;   // rows per hat warp, scan segments per row
+            const int lane = tid & 31, l4 = lane % RW, rr = l4 + RW * ((tid - R2_COMPUTE_SLOTS - 32) >> 5), seg = lane / RW;
             const int lp = P.lp;
-            double *col = HF + R2_RB + rr + seg * lp * R2_RB;
+            double *col = HF + RB + rr + seg * lp * RB;
             const double *cd = hcd + seg * lp, *cu = hcu + seg * lp, *rdp = hrd + seg * lp;
             const double *wd = hwd + seg * lp, *wu = hwu + seg * lp;
             double Ad = 1.0, Au = 1.0;   // the segment's multipliers of the incoming values
@@ -392,24 +394,23 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 Ad *= -cd[i];
                 Au *= -cu[i];
             }
-            const int l4 = lane & 3;
             for (int t = 0; t < nloc; ++t) {
                 named_bar_sync(R2_BAR_HATS, nthr + 64);   // the right-hand sides (times rd) of all hats are in HF
                 // pass 1: what leaves my segment at the bottom with zero coming in: a dot product, no chain
                 double b0 = 0.0, b1 = 0.0;
                 for (int i0 = 0; i0 < lp; i0 += 4) {
-                    b0 = fma(wd[i0], col[i0 * R2_RB], b0);
-                    b1 = fma(wd[i0 + 1], col[(i0 + 1) * R2_RB], b1);
-                    b0 = fma(wd[i0 + 2], col[(i0 + 2) * R2_RB], b0);
-                    b1 = fma(wd[i0 + 3], col[(i0 + 3) * R2_RB], b1);
+                    b0 = fma(wd[i0], col[i0 * RB], b0);
+                    b1 = fma(wd[i0 + 1], col[(i0 + 1) * RB], b1);
+                    b0 = fma(wd[i0 + 2], col[(i0 + 2) * RB], b0);
+                    b1 = fma(wd[i0 + 3], col[(i0 + 3) * RB], b1);
                 }
                 b0 += b1;
                 double inc = 0.0;
                 {
                     double res = 0.0;   // value leaving the segments above, built from the top
 #pragma unroll
-                    for (int s2 = 7; s2 >= 0; --s2) {
-                        const double As = __shfl_sync(POP_FULL_MASK, Ad, s2 * 4 + l4), Bs = __shfl_sync(POP_FULL_MASK, b0, s2 * 4 + l4);
+                    for (int s2 = NSEG - 1; s2 >= 0; --s2) {
+                        const double As = __shfl_sync(POP_FULL_MASK, Ad, s2 * RW + l4), Bs = __shfl_sync(POP_FULL_MASK, b0, s2 * RW + l4);
                         if (s2 == seg) inc = res;
                         res = fma(As, res, Bs);
                     }
@@ -418,21 +419,21 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 double h = inc;
                 b0 = 0.0;
                 for (int i0 = lp - 2; i0 >= 0; i0 -= 2) {
-                    const double y1 = col[(i0 + 1) * R2_RB], y0 = col[i0 * R2_RB];
+                    const double y1 = col[(i0 + 1) * RB], y0 = col[i0 * RB];
                     const double c1 = cd[i0 + 1], c0 = cd[i0], w1 = wu[i0 + 1], w0 = wu[i0];
                     h = fma(-c1, h, y1);
-                    col[(i0 + 1) * R2_RB] = h;
+                    col[(i0 + 1) * RB] = h;
                     b0 = fma(w1, h, b0);
                     h = fma(-c0, h, y0);
-                    col[i0 * R2_RB] = h;
+                    col[i0 * RB] = h;
                     b0 = fma(w0, h, b0);
                 }
                 {
                     double res = 0.0;   // value entering from the segments below, built from the bottom
                     inc = 0.0;
 #pragma unroll
-                    for (int s2 = 0; s2 < 8; ++s2) {
-                        const double As = __shfl_sync(POP_FULL_MASK, Au, s2 * 4 + l4), Bs = __shfl_sync(POP_FULL_MASK, b0, s2 * 4 + l4);
+                    for (int s2 = 0; s2 < NSEG; ++s2) {
+                        const double As = __shfl_sync(POP_FULL_MASK, Au, s2 * RW + l4), Bs = __shfl_sync(POP_FULL_MASK, b0, s2 * RW + l4);
                         if (s2 == seg) inc = res;
                         res = fma(As, res, Bs);
                     }
@@ -440,12 +441,12 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 // pass 3, ascending: the final x_i = h_i rd_i - cu_i x_{i-1}
                 h = inc;
                 for (int i0 = 0; i0 < lp; i0 += 2) {
-                    const double y0 = col[i0 * R2_RB] * rdp[i0], y1 = col[(i0 + 1) * R2_RB] * rdp[i0 + 1];
+                    const double y0 = col[i0 * RB] * rdp[i0], y1 = col[(i0 + 1) * RB] * rdp[i0 + 1];
                     const double c0 = cu[i0], c1 = cu[i0 + 1];
                     h = fma(-c0, h, y0);
-                    col[i0 * R2_RB] = h;
+                    col[i0 * RB] = h;
                     h = fma(-c1, h, y1);
-                    col[(i0 + 1) * R2_RB] = h;
+                    col[(i0 + 1) * RB] = h;
                 }
                 __syncwarp();
                 named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hats of the 8 rows are solved
@@ -455,22 +456,22 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
       asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
       if (tid < nthr) {
         // =========================== compute threads ============================================================
-        const int par = tid / (mlc * R2_RB);          // 0 / 1
-        const int tp = tid - par * mlc * R2_RB;
-        const int e = tp / R2_RB, r = tp % R2_RB;
+        const int par = tid / (mlc * RB);          // 0 / 1
+        const int tp = tid - par * mlc * RB;
+        const int e = tp / RB, r = tp % RB;
         const int k = k0 + e;
         // 32-bit shared addresses of this thread's entries: one base register, the rest are immediates when MLC > 0
         const uint32_t sbase = smem_u32(r2_raw);
-        const uint32_t off_er = sbase + (uint32_t)(((par * mlc + e) * R2_RB + r) * 8);   // (parity, element, row) inside a [degree][element][row] box
-        const uint32_t dstride = (uint32_t)(2 * mlc * R2_RB * 8);                       // two degrees further
+        const uint32_t off_er = sbase + (uint32_t)(((par * mlc + e) * RB + r) * 8);   // (parity, element, row) inside a [degree][element][row] box
+        const uint32_t dstride = (uint32_t)(2 * mlc * RB * 8);                       // two degrees further
         const uint32_t a_tab = sbase + LF.tab + par * 16, a_ttab = sbase + LF.ttab + par * 16, a_ftab = sbase + LF.ftab + par * 16;
         const uint32_t a_in = off_er + LF.in;
         const uint32_t a_ss = sbase + LF.ss + (par * 3 * mlc + e) * 8, a_st = sbase + LF.st + (par * 3 * mlc + e) * 8;
-        const uint32_t a_hf = sbase + P.o_hf + (k * R2_RB + r) * 8;
+        const uint32_t a_hf = sbase + P.o_hf + (k * RB + r) * 8;
         for (int t = 0; t < nloc; ++t) {
             const int pb = t & 1;
             const uint32_t phMB = (uint32_t)(t >> 1) & 1u;
-            const int row0 = (bbase + t * bstride) * R2_RB;
+            const int row0 = (bbase + t * bstride) * RB;
             const double *inh = INH + pb * HBS, *fh = FH + pb * HBS;
             double *mbme = remote ? MB : MB + ((size_t)pb * cs + rank) * mbw;   // remote: staging of my message only
             const size_t mslot = ((size_t)(P.epoch & 1) * P.nblk + (size_t)(bbase + t * bstride)) * G;   // mailboxes of this row block: one per reading CTA
@@ -523,33 +524,33 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     c1 = fma(lds_f64(sb + mlc * 8), z[ii], c1);
                     c2 = fma(lds_f64(sb + 2 * mlc * 8), z[ii], c2);
                     // the backward-swept coupled bubbles of my two edge elements travel with the message
-                    if (e == 0) mbme[(mlc + 2) * R2_RB + (0 * R2_NBMAX + b) * R2_RB + r] = z[ii];
-                    if (e == mlc - 1) mbme[(mlc + 2) * R2_RB + (1 * R2_NBMAX + b) * R2_RB + r] = z[ii];
+                    if (e == 0) mbme[(mlc + 2) * RB + (0 * R2_NBMAX + b) * RB + r] = z[ii];
+                    if (e == mlc - 1) mbme[(mlc + 2) * RB + (1 * R2_NBMAX + b) * RB + r] = z[ii];
                 }
                 // the couplings of both parities of an (element, row) are summed in shared memory: odd degrees first
                 if (par == 1) {
-                    ct[(0 * mlc + e) * R2_RB + r] = c0;
-                    ct[(1 * mlc + e) * R2_RB + r] = c1;
-                    ct[(2 * mlc + e) * R2_RB + r] = c2;
+                    ct[(0 * mlc + e) * RB + r] = c0;
+                    ct[(1 * mlc + e) * RB + r] = c1;
+                    ct[(2 * mlc + e) * RB + r] = c2;
                 }
                 named_bar_sync(R2_BAR_COMPUTE, nthr);
                 if (par == 0) {
-                    ct[(0 * mlc + e) * R2_RB + r] += c0;
-                    ct[(1 * mlc + e) * R2_RB + r] += c1;
-                    ct[(2 * mlc + e) * R2_RB + r] += c2;
+                    ct[(0 * mlc + e) * RB + r] += c0;
+                    ct[(1 * mlc + e) * RB + r] += c1;
+                    ct[(2 * mlc + e) * RB + r] += c2;
                 }
             }
             named_bar_sync(R2_BAR_COMPUTE, nthr);
             // ---- C: my message: hat right-hand sides minus the couplings of MY elements, for hats k0-1 .. k0+mlc --
             R2_STAMP(3);
             mbar_wait(barH + pb, phMB);   // the hats of this block (loaded a block ahead)
-            if (tid < (mlc + 2) * R2_RB) {
-                const int u = tid / R2_RB - 1, rr = tid % R2_RB;
-                double v = (u >= 0 && u < nhl) ? inh[u * R2_RB + rr] : 0.0;
+            if (tid < (mlc + 2) * RB) {
+                const int u = tid / RB - 1, rr = tid % RB;
+                double v = (u >= 0 && u < nhl) ? inh[u * RB + rr] : 0.0;
 #pragma unroll
                 for (int tt = 0; tt < 3; ++tt) {
                     const int el = u + 1 - tt;   // slot tt of element el couples to hat el + tt - 1
-                    if (el >= 0 && el < mlc) v -= ct[(tt * mlc + el) * R2_RB + rr];
+                    if (el >= 0 && el < mlc) v -= ct[(tt * mlc + el) * RB + rr];
                 }
                 mbme[tid] = v;
             }
@@ -594,13 +595,13 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             }
             {
                 // right-hand sides (times rd) of ALL hats of the 8 rows, redundantly in every CTA
-                for (int x = tid; x < nh * R2_RB; x += nthr) {
-                    const int i = x / R2_RB, rr = x % R2_RB;
+                for (int x = tid; x < nh * RB; x += nthr) {
+                    const int i = x / RB, rr = x % RB;
                     const int c = min(i / mlc, nr - 1), u = i - c * mlc;
-                    double v = r2_mbld(mbp + c * mbw + (u + 1) * R2_RB + rr, mbmode, P.merr);
-                    if (u == 0 && c > 0) v += r2_mbld(mbp + (c - 1) * mbw + (mlc + 1) * R2_RB + rr, mbmode, P.merr);
+                    double v = r2_mbld(mbp + c * mbw + (u + 1) * RB + rr, mbmode, P.merr);
+                    if (u == 0 && c > 0) v += r2_mbld(mbp + (c - 1) * mbw + (mlc + 1) * RB + rr, mbmode, P.merr);
                     if (u == mlc - 1 && c < nr - 1) v += r2_mbld(mbp + (c + 1) * mbw + rr, mbmode, P.merr);
-                    HF[(i + 1) * R2_RB + rr] = v * hrd[i];
+                    HF[(i + 1) * RB + rr] = v * hrd[i];
                 }
             }
             named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hat warps take over ...
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             // ---- E2: the corrections of the coupled bubbles (:475-477) carried through the sweep by its impulse responses,
             //      product, output
             R2_STAMP(6);
-            const double h0 = lds_f64(a_hf), h1 = lds_f64(a_hf + R2_RB * 8), h2 = lds_f64(a_hf + 2 * R2_RB * 8);
+            const double h0 = lds_f64(a_hf), h1 = lds_f64(a_hf + RB * 8), h2 = lds_f64(a_hf + 2 * RB * 8);
             double d0, d1;
             {
                 const uint32_t sb = a_ss;
@@ -628,8 +629,8 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             double *xb = ct;   // [4][mlc][8]: x of the coupled bubbles, for the hat rows of the product
             double xm = 0.0, x0 = corrected(0), xp = CH > 1 ? corrected(1) : 0.0;   // x_{i-1}, x_i, x_{i+1}
             if (mul) {
-                xb[(par * mlc + e) * R2_RB + r] = x0;
-                if (CH > 1) xb[((2 + par) * mlc + e) * R2_RB + r] = xp;
+                xb[(par * mlc + e) * RB + r] = x0;
+                if (CH > 1) xb[((2 + par) * mlc + e) * RB + r] = xp;
             }
             // chunk cc holds the chain entries i = cc*DC/2 .. (cc+1)*DC/2 - 1 (registers are indexed statically)
             R2_STAMP(7);
@@ -692,13 +693,13 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             R2_STAMP(8);
             named_bar_sync(R2_BAR_COMPUTE, nthr);   // xb complete
             // hat rows: x = h (plain solve) or T_A h + sum_b T_b x_b + gamma f, for my hats
-            if (tid < nhl * R2_RB) {
-                const int u = tid / R2_RB, rr = tid % R2_RB, i = hA + u;
+            if (tid < nhl * RB) {
+                const int u = tid / RB, rr = tid % RB, i = hA + u;
                 const int64_t rw = (int64_t)row0 + rr;
-                const double hc = HF[(i + 1) * R2_RB + rr];
+                const double hc = HF[(i + 1) * RB + rr];
                 double out = hc;
                 if (mul) {
-                    const double hp = HF[i * R2_RB + rr], hn = HF[(i + 2) * R2_RB + rr];
+                    const double hp = HF[i * RB + rr], hn = HF[(i + 2) * RB + rr];
                     double acc = P.TAd[i] * hc;
                     if (i + 1 < nh) acc = fma(P.TAu[i], hn, acc);
                     if (i > 0) acc = fma(P.TAu[i - 1], hp, acc);
@@ -707,17 +708,17 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                         const int el = u + 1 - tt, kk = k0 + el;   // slot tt of element kk couples to hat i
                         if (kk < 0 || kk >= m) continue;
                         if (el >= 0 && el < mlc) {
-                            for (int b = 0; b < P.nbT; ++b) acc = fma(sT[(b * 3 + tt) * mlc + el], xb[(b * mlc + el) * R2_RB + rr], acc);
+                            for (int b = 0; b < P.nbT; ++b) acc = fma(sT[(b * 3 + tt) * mlc + el], xb[(b * mlc + el) * RB + rr], acc);
                         } else {
                             // an edge element of a neighbour CTA: its x_b follow from its backward-swept z_b (in the
                             // neighbour's message) and the hats, exactly as its owner computes them
                             const int nbr = el < 0 ? rank - 1 : rank + 1, side = el < 0 ? 1 : 0;
-                            const double *zz = mbp + nbr * mbw + (mlc + 2) * R2_RB + side * R2_NBMAX * R2_RB + rr;
-                            const double g0 = HF[kk * R2_RB + rr], g1 = HF[(kk + 1) * R2_RB + rr], g2 = HF[(kk + 2) * R2_RB + rr];
+                            const double *zz = mbp + nbr * mbw + (mlc + 2) * RB + side * R2_NBMAX * RB + rr;
+                            const double g0 = HF[kk * RB + rr], g1 = HF[(kk + 1) * RB + rr], g2 = HF[(kk + 2) * RB + rr];
                             double xs[R2_NBMAX];
 #pragma unroll
                             for (int b = 0; b < R2_NBMAX; ++b) {
-                                double v = r2_mbld(zz + b * R2_RB, mbmode, P.merr);
+                                double v = r2_mbld(zz + b * RB, mbmode, P.merr);
                                 if (b < P.nb) {
                                     const double *sg = P.S + (size_t)b * 3 * m + kk;
                                     v = fma(-__ldg(sg), g0, v);
@@ -732,7 +733,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                                 if (b < P.nbT) acc = fma(__ldg(P.Ts + ((size_t)b * 3 + tt) * m + kk), xs[b], acc);
                         }
                     }
-                    out = useF ? fma(P.gamma, fh[u * R2_RB + rr], acc) : acc;
+                    out = useF ? fma(P.gamma, fh[u * RB + rr], acc) : acc;
                 }
                 if (rw < P.nrows) P.X[rw + (int64_t)(i - P.kbase) * P.ld] = out;   // hats come first in the panel
             }
@@ -774,12 +775,12 @@ static int r2_env(const char *name, int dflt) {
 }
 
 // bubbles of a panel as (row, element, degree), hats as (row, hat); boxes (8, mlc, 8) and (8, mlc + 1)
-static bool r2_make_maps(encode_tiled_t enc, const double *base, int64_t ld, int64_t nrows, int m, int nh, int q, int mlc, int dc, CUtensorMap *m3, CUtensorMap *mh) {
+static bool r2_make_maps(encode_tiled_t enc, const double *base, int64_t ld, int64_t nrows, int m, int nh, int q, int mlc, int dc, int rb, CUtensorMap *m3, CUtensorMap *mh) {
     const CUtensorMapL2promotion promo = r2_env("POP_ROW2_L2PROMO", 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     {
         cuuint64_t dims[3] = {(cuuint64_t)nrows, (cuuint64_t)m, (cuuint64_t)q};
         cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)ld * 8 * (cuuint64_t)m};
-        cuuint32_t box[3] = {R2_RB, (cuuint32_t)mlc, (cuuint32_t)dc};
+        cuuint32_t box[3] = {(cuuint32_t)rb, (cuuint32_t)mlc, (cuuint32_t)dc};
         cuuint32_t es[3] = {1, 1, 1};
         if (enc(m3, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)(base + (int64_t)nh * ld), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -788,7 +789,7 @@ static bool r2_make_maps(encode_tiled_t enc, const double *base, int64_t ld, int
     {
         cuuint64_t dims[2] = {(cuuint64_t)nrows, (cuuint64_t)std::max(nh, 1)};
         cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-        cuuint32_t box[2] = {R2_RB, (cuuint32_t)(mlc + 1)};
+        cuuint32_t box[2] = {(cuuint32_t)rb, (cuuint32_t)(mlc + 1)};
         cuuint32_t es[2] = {1, 1};
         if (enc(mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -798,13 +799,23 @@ static bool r2_make_maps(encode_tiled_t enc, const double *base, int64_t ld, int
 }
 
 typedef void (*r2_kernel_t)(const R2Params);
-static r2_kernel_t r2_kernel(int ch, int dc, int mlc) {
-    if (mlc == 32 && ch == 32) return dc == 8 ? k_row2<32, 8, 32> : k_row2<32, 4, 32>;   // the ADI shapes (m = 128: cluster of 4, m = 256: of 8)
+static r2_kernel_t r2_kernel(int ch, int dc, int mlc, int rb) {
+    if (rb == 16) {   // panels of few elements per CTA (8 GPUs: 16 elements each): 16 rows per block
+        if (mlc == 16 && ch == 32) return dc == 8 ? k_row2<32, 8, 16, 16> : k_row2<32, 4, 16, 16>;
+        switch (ch) {
+            case 8: return dc == 8 ? k_row2<8, 8, 0, 16> : k_row2<8, 4, 0, 16>;
+            case 16: return dc == 8 ? k_row2<16, 8, 0, 16> : k_row2<16, 4, 0, 16>;
+            case 24: return dc == 8 ? k_row2<24, 8, 0, 16> : k_row2<24, 4, 0, 16>;
+            case 32: return dc == 8 ? k_row2<32, 8, 0, 16> : k_row2<32, 4, 0, 16>;
+        }
+        return nullptr;
+    }
+    if (mlc == 32 && ch == 32) return dc == 8 ? k_row2<32, 8, 32, 8> : k_row2<32, 4, 32, 8>;   // the ADI shapes (m = 128: cluster of 4, m = 256: of 8)
     switch (ch) {
-        case 8: return dc == 8 ? k_row2<8, 8, 0> : k_row2<8, 4, 0>;
-        case 16: return dc == 8 ? k_row2<16, 8, 0> : k_row2<16, 4, 0>;
-        case 24: return dc == 8 ? k_row2<24, 8, 0> : k_row2<24, 4, 0>;
-        case 32: return dc == 8 ? k_row2<32, 8, 0> : k_row2<32, 4, 0>;
+        case 8: return dc == 8 ? k_row2<8, 8, 0, 8> : k_row2<8, 4, 0, 8>;
+        case 16: return dc == 8 ? k_row2<16, 8, 0, 8> : k_row2<16, 4, 0, 8>;
+        case 24: return dc == 8 ? k_row2<24, 8, 0, 8> : k_row2<24, 4, 0, 8>;
+        case 32: return dc == 8 ? k_row2<32, 8, 0, 8> : k_row2<32, 4, 0, 8>;
     }
     return nullptr;
 }
@@ -813,7 +824,7 @@ static int r2_align(int x, int a) { return (x + a - 1) / a * a; }
 
 // Remote mode plan for a decomposition of m elements over `world` GPUs: CTAs per row block and GPU (csv), elements per
 // CTA (mlc), doubles per message.  false: the shape is not covered (the two-pass kernels of pop_row.cu serve it).
-bool pop_row2_remote_plan(int m, int world, int *csv, int *mlc, int *mbw) {
+bool pop_row2_remote_plan(int m, int world, int *csv, int *mlc, int *rb, int *mbw) {
     if (world < 1 || m % world) return false;
     const int ml = m / world;
     for (int c = 1; c <= 8; c <<= 1) {
@@ -822,7 +833,8 @@ bool pop_row2_remote_plan(int m, int world, int *csv, int *mlc, int *mbw) {
         if (e < 2 || (e & 1) || 16 * e > 512) continue;
         *csv = c;
         *mlc = e;
-        *mbw = (e + 2) * R2_RB + 2 * R2_NBMAX * R2_RB;
+        *rb = (e <= 16 && r2_env("POP_ROW2_RB", 16) == 16) ? 16 : 8;   // 2 * rb * e <= 512 compute threads
+        *mbw = (e + 2) * *rb + 2 * R2_NBMAX * *rb;
         return true;
     }
     return false;
@@ -849,11 +861,13 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     const int ch = op.q <= 16 ? 8 : op.q <= 32 ? 16 : op.q <= 48 ? 24 : 32;
     const int want_cs = r2_env("POP_ROW2_CS", 0);
     int cs = 0, mlc = 0;
+    int rb = R2_RB;
     if (rem) {
         // several GPUs (or forced): no cluster, the plan was fixed when the mailboxes were allocated
         if (op.ml * op.world != op.m || op.k0 != op.rank * op.ml || rem->csv * rem->mlc != op.ml) return unsupported("uneven element decomposition");
         cs = 1;
         mlc = rem->mlc;
+        rb = rem->rb;
     } else {
         for (int c = 1; c <= R2_MAXCS; c <<= 1) {
             if (want_cs && c != want_cs) continue;
@@ -868,27 +882,28 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
         mlc = op.m / cs;
     }
     if (mlc + 1 > 256) return unsupported("hat box too wide");
-    const int nthr = 16 * mlc;
+    const int nthr = 2 * rb * mlc;
     if (nthr % 32) return unsupported("elements per CTA must be even");   // whole warps: the named barrier and the hat scan need them
     R2Params P;
     memset(&P, 0, sizeof(P));
-    P.mbw = (mlc + 2) * R2_RB + 2 * R2_NBMAX * R2_RB;
-    const int lp = (((op.nh + 7) / 8) + 3) & ~3;            // hats per scan segment (8 segments), a multiple of 4
-    const int hf_rows = std::max(8 * lp + 2, op.m + 3);
+    P.mbw = (mlc + 2) * rb + 2 * R2_NBMAX * rb;
+    const int nseg = 64 / rb;                                // scan segments per row (two hat warps share the rows)
+    const int lp = (((op.nh + nseg - 1) / nseg) + 3) & ~3;  // hats per scan segment, a multiple of 4
+    const int hf_rows = std::max(nseg * lp + 2, op.m + 3);
     // behind the ring: HF, the padded hat tables, the mailboxes
-    const int tail = r2_align(hf_rows * R2_RB * 8, 128) + 2 * r2_align(8 * lp * 8, 128) + r2_align(3 * 8 * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
+    const int tail = r2_align(hf_rows * rb * 8, 128) + 2 * r2_align(nseg * lp * 8, 128) + r2_align(3 * nseg * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
     (void)want_cs;
     // degrees per chunk (TMA box, region of the row block buffer): 4 keeps the hand-over between the blocks fine-grained
     const int dc = r2_env("POP_ROW2_DC", 4) == 8 ? 8 : 4;
     const int nch = (op.q + dc - 1) / dc;
-    const R2Fixed LF = r2_fixed(ch, dc, mlc);
+    const R2Fixed LF = r2_fixed(ch, dc, mlc, rb);
     if (LF.ring + tail > ctx->max_smem_optin) return unsupported("shared memory too small for the row block");
     if (4 + 4 * ((2 * ch + dc - 1) / dc) > 128) return unsupported("too many barriers");
     int o = LF.ring;
-    P.o_hf = o; o += r2_align(hf_rows * R2_RB * 8, 128);
-    P.o_hrd = o; o += r2_align(8 * lp * 8, 128);
-    P.o_hcd = o; o += r2_align(8 * lp * 8, 128);
-    P.o_hcu = o; o += r2_align(3 * 8 * lp * 8, 128);   // hcu, hwd, hwu
+    P.o_hf = o; o += r2_align(hf_rows * rb * 8, 128);
+    P.o_hrd = o; o += r2_align(nseg * lp * 8, 128);
+    P.o_hcd = o; o += r2_align(nseg * lp * 8, 128);
+    P.o_hcu = o; o += r2_align(3 * nseg * lp * 8, 128);   // hcu, hwd, hwu
     P.o_mb = o; o += r2_align(2 * cs * P.mbw * 8, 128);
     P.total = o;
     if ((size_t)P.total > (size_t)ctx->max_smem_optin) return unsupported("shared memory too small");
@@ -897,9 +912,9 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.pf_dist = r2_env("POP_ROW2_PF", 0);   // L2 prefetch distance of F in row blocks (0: off)
 
     const int pm = rem ? op.ml : op.m, pnh = rem ? op.nhl : op.nh;   // the panel: all elements, or this GPU's
-    if (!r2_make_maps(enc, R, op.ld, op.nrows, pm, pnh, op.q, mlc, dc, &P.mapX3, &P.mapXh)) return unsupported("cuTensorMapEncodeTiled rejected the panel");
+    if (!r2_make_maps(enc, R, op.ld, op.nrows, pm, pnh, op.q, mlc, dc, rb, &P.mapX3, &P.mapXh)) return unsupported("cuTensorMapEncodeTiled rejected the panel");
     if (useF) {
-        if (!r2_make_maps(enc, F, op.ldf, op.nrows, pm, pnh, op.q, mlc, dc, &P.mapF3, &P.mapFh)) return unsupported("cuTensorMapEncodeTiled rejected F");
+        if (!r2_make_maps(enc, F, op.ldf, op.nrows, pm, pnh, op.q, mlc, dc, rb, &P.mapF3, &P.mapFh)) return unsupported("cuTensorMapEncodeTiled rejected F");
     } else {
         P.mapF3 = P.mapX3;
         P.mapFh = P.mapXh;
@@ -911,7 +926,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.X = R; P.F = F; P.ld = op.ld; P.ldf = op.ldf; P.nrows = op.nrows;
     P.m = op.m; P.nh = op.nh; P.q = op.q;
     P.cs = cs; P.mlc = mlc; P.nch = nch;
-    P.nblk = (int)((op.nrows + R2_RB - 1) / R2_RB);
+    P.nblk = (int)((op.nrows + rb - 1) / rb);
     if (rem) {
         P.remote = rem->standin ? 2 : 1; P.world = rem->world; P.me = rem->me; P.csv = rem->csv; P.nr = rem->world * rem->csv;
         P.kbase = op.k0;
@@ -921,7 +936,8 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
         if ((int64_t)2 * P.nblk * P.csv * P.nr * P.mbw > rem->mbox_doubles) return unsupported("mailbox too small");
     }
 
-    r2_kernel_t kern = r2_kernel(ch, dc, mlc);
+    r2_kernel_t kern = r2_kernel(ch, dc, mlc, rb);
+    if (!kern) return unsupported("no kernel for this chain class");
     POP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.total));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -936,7 +952,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     cfg.numAttrs = 1;
     static std::mutex plan_mu;
     static int cached_key[5] = {0, 0, 0, 0, -1}, cached_ncl = 0;
-    const int key[5] = {ch * 16 + dc + (mlc == 32 ? 1024 : 0) + (rem ? 4096 : 0), rem ? rem->csv : cs, nthr, P.total, ctx->device};
+    const int key[5] = {ch * 16 + dc + (mlc == 32 ? 1024 : 0) + (rem ? 4096 : 0) + (rb == 16 ? 8192 : 0), rem ? rem->csv : cs, nthr, P.total, ctx->device};
     int ncl;
     {
         std::lock_guard<std::mutex> lk(plan_mu);
@@ -965,7 +981,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     }
     if (const int cap = r2_env("POP_ROW2_NCL", 0)) ncl = std::min(ncl, cap);
     ncl = std::min(ncl, P.nblk);
-    P.pairing = (ncl >= 2 && r2_env("POP_ROW2_PAIR", 1)) ? 1 : 0;
+    P.pairing = (rb == 8 && ncl >= 2 && r2_env("POP_ROW2_PAIR", 1)) ? 1 : 0;   // 16 rows are whole 128 B lines already
     if (P.pairing) ncl &= ~1;
     cfg.gridDim = dim3((unsigned)(ncl * (rem ? rem->csv : cs)));
     if (r2_env("POP_ROW2_VERBOSE", 0))

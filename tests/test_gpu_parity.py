@@ -637,10 +637,12 @@ def test_single_pass_tma_row_half_step(basis, m, N, cs, monkeypatch):
     dd.close()
 
 
-@pytest.mark.parametrize("basis,m,N", [("dirichlet", 64, 7), ("c1", 64, 4), ("dirichlet", 128, 5), ("dirichlet", 16, 12)])
+@pytest.mark.parametrize("basis,m,N", [("dirichlet", 64, 7), ("c1", 64, 4), ("dirichlet", 128, 5), ("dirichlet", 16, 12), ("c1", 8, 9), ("dirichlet", 16, 64),
+                                       ("c1", 16, 33)])
 def test_single_pass_row_remote_mailboxes(basis, m, N, monkeypatch):
     """csrc/pop_row2.cu in REMOTE mode -- the CTAs that share a row block meet through mailboxes and flags in global memory,
-    the way the GPUs of a multi-GPU run do -- forced on one GPU (POP_ROW2_REMOTE=1; m = 64: 2 CTAs per row block, m = 128: 4):
+    the way the GPUs of a multi-GPU run do -- forced on one GPU (POP_ROW2_REMOTE=1; m = 64: 2 CTAs per row block, m = 128: 4;
+    m <= 16: blocks of 16 rows, the shape of an 8-GPU run):
     against dense algebra and the cluster mode of the same kernel, repeated calls (mailbox parity and epochs)."""
     from pop_b200 import _lib as L
     from pop_b200.arrowhead import _bind_stream
@@ -679,7 +681,8 @@ def test_single_pass_row_remote_mailboxes(basis, m, N, monkeypatch):
                 assert relerr(got[mode, what], want) < TOL, (mode, what, rep)
         dd.close()
     for what in ("half step", "solve"):
-        assert np.array_equal(got["remote", what], got["cluster", what]), what
+        # same arithmetic; the hat scan splits a row into 4 (16-row blocks) or 8 (8-row blocks) segments: last-bit differences
+        assert relerr(got["remote", what], got["cluster", what]) < 1e-14, what
 
 
 def test_heat_steps_vs_oracle():
