@@ -312,6 +312,32 @@ def adi_case(P, torch, dist, rank, world, dev):
     else:
         Xfull[:, cols] = X
     res, err = adi_check(P, torch, M, K, Y, Ffull, Xfull)
+    e2e_adi = None
+    if world == 1:
+        # end to end through the host-buffer entry point pop_adi_poisson_host (what `ADI(...)` of examples/adi_poisson.jl:42-59 is for a
+        # Julia caller): F in host memory in, X in host memory out, both copies inside the timed region
+        try:
+            e2e_adi = {}
+            for kind in ("pinned", "pageable"):
+                hF = torch.empty((n, n), dtype=torch.float64)
+                hX = torch.empty((n, n), dtype=torch.float64)
+                if kind == "pinned":
+                    hF, hX = hF.pin_memory(), hX.pin_memory()
+                hF.copy_(Ffull.t())                              # hF.numpy().T is F, Fortran-ordered with leading dimension n
+                ts = []
+                for it in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    P.adi_poisson(M, K, hF.numpy().T, a, b, J=J, out=hX.numpy().T)
+                    ts.append(time.perf_counter() - t0)
+                rel = float(torch.linalg.norm(hX.to(Xfull.device).t() - Xfull) / torch.linalg.norm(Xfull))
+                e2e_adi[kind] = {"s_per_solve": ts[-1], "unknown_rhs_per_s": 2.0 * J * n * n / ts[-1], "rel_diff_vs_device_resident": rel}
+                del hF, hX
+            e2e_adi["h2d_bytes_per_solve"] = e2e_adi["d2h_bytes_per_solve"] = n * n * 8
+            e2e_adi["api"] = "pop_adi_poisson_host (adi_poisson(M, K, numpy F)): one copy in, 2J sweeps on the device, one copy out"
+        except Exception as ex:
+            e2e_adi = {"error": f"{type(ex).__name__}: {ex}"}
+    out["e2e"] = e2e_adi
     del Xfull, Y, Ffull
     out["residual_rel"] = res
     out["solution_rel_err_vs_manufactured"] = err
@@ -597,7 +623,7 @@ def main():
         # the same call on PAGEABLE host memory (what a Julia Array or a plain NumPy array is)
         try:
             hXp = torch.empty((nrhs, n), dtype=torch.float64)
-            e2e["pageable"] = {"value": host_loop(hB, hXp, min(ksteps, 3)), "unit": UNIT, "note": "same call, host panel in ordinary (pageable) memory"}
+            e2e["pageable"] = {"value": host_loop(hB, hXp, min(ksteps, 3)), "unit": UNIT, "note": "same call, host panel in ordinary (pageable) memory: worker threads stage it through pinned pieces (csrc/pop_host.cu StagedXfer)"}
             del hXp
         except Exception as ex:
             e2e["pageable"] = {"error": f"{type(ex).__name__}: {ex}"}
@@ -646,7 +672,8 @@ def main():
                      "adi_error": None if ok or adi is None else adi.get("error"),
                      "adi_s_per_solve": adi["s_per_solve"] if ok else None, "adi_J": adi["J"] if ok else None,
                      "adi_residual": adi["residual_rel"] if ok else None, "adi_solution_err": adi["solution_rel_err_vs_manufactured"] if ok else None,
-                     "adi_frac_per_gpu": adi["frac_of_measured_hbm_peak_per_gpu"] if ok else None})
+                     "adi_frac_per_gpu": adi["frac_of_measured_hbm_peak_per_gpu"] if ok else None,
+                     "adi_e2e_s_per_solve": (adi.get("e2e") or {}).get("pinned", {}).get("s_per_solve") if ok else None})
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

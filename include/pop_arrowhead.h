@@ -90,6 +90,19 @@ int pop_sync(pop_ctx *ctx);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */
 int64_t pop_launch_count(const pop_ctx *ctx);
 
+/* ---- device-resident panels --------------------------------------------------------
+ * For hosts without a CUDA binding of their own (julia/PopArrowheadGPU.jl `DevicePanel`): a rows x cols Float64
+ * matrix in device memory, column-major with the (even) leading dimension returned in *ld, zero-initialised.
+ * Chains of calls on device pointers (pop_mul, pop_solve, pop_adi_poisson, pop_heat_steps ...) then move no data over
+ * PCIe; the reference keeps its matrices in host memory, so this is the one place the drop-in adds a type.
+ * upload / download copy a host matrix (leading dimension ldh) in / out and synchronise. */
+int pop_panel_alloc(pop_ctx *ctx, int64_t rows, int64_t cols, double **dptr, int64_t *ld);
+int pop_panel_free(pop_ctx *ctx, double *dptr);
+int pop_panel_upload(pop_ctx *ctx, const double *host, int64_t ldh, double *dptr, int64_t ldd, int64_t rows,
+                     int64_t cols);
+int pop_panel_download(pop_ctx *ctx, const double *dptr, int64_t ldd, double *host, int64_t ldh, int64_t rows,
+                       int64_t cols);
+
 /* ---- container (src/arrowhead.jl:31-41,89-120) --------------------------------- */
 /* BBBArrowheadMatrix(A,B,C,D): validates what the constructor asserts.  Any of
  * Au/Al/B/C may be NULL (= zero / empty). */
@@ -122,6 +135,12 @@ int pop_assemble(pop_ctx *ctx, int basis, int m, int N, double h, pop_arrowhead 
  * defines weaklaplacian itself for ranges only).  Synchronises the context's stream. */
 int pop_assemble_mesh(pop_ctx *ctx, int basis, int m, int N, const double *h_elems, pop_arrowhead **mass,
                       pop_arrowhead **lap);
+
+/* The same with a piecewise-constant diffusion coefficient a_elems[k] > 0 on element k (NULL = 1): lap becomes
+ * -(D*C)' * (a .* (D*C)) of examples/heat.jl:77-79 for a in span of the piecewise constants (every element integral of
+ * the weak Laplacian scaled by a_k); the mass matrix is unchanged. */
+int pop_assemble_mesh_coef(pop_ctx *ctx, int basis, int m, int N, const double *h_elems, const double *a_elems,
+                           pop_arrowhead **mass, pop_arrowhead **lap);
 
 /* ---- algebra: alpha*X + beta*Y with ragged B/C and D bands (src/arrowhead.jl:392-417) */
 int pop_axpby(pop_ctx *ctx, double alpha, const pop_arrowhead *X, double beta,
@@ -202,6 +221,20 @@ int pop_weakform_apply(pop_ctx *ctx, int basis, int m, int N, double h, const do
  * max_jump synchronises the stream. */
 int pop_legendre_to_c1(pop_ctx *ctx, int basis, int m, int N, int side, const double *dX, int64_t ldx, double *dY,
                        int64_t ldy, int64_t cnt, double *max_jump);
+
+/* INVERSE transforms (`Pl \ cfs`, src/continuouspolynomial.jl:129-146,171-184; src/dirichlet.jl:97-110,143-163;
+ * test/test_continuouspolynomial.jl:19,26,33: `F \ (F * vals) ≈ vals`).
+ * pop_c1_to_legendre: coefficients in ContinuousPolynomial{1} / DirichletPolynomial blocks 1..N-1 (n = nh + m (N-2)) ->
+ * Legendre coefficients, N degrees per element in P ordering: the `Pl.R \ dat` step, i.e. the truncated conversion
+ * (P \ C)[Block.(1:N), Block.(1:N-1)] of src/continuouspolynomial.jl:226-235.  side as in pop_legendre_to_c1 (its inverse).
+ * pop_legendre_synthesis_2d: `legendretransform \ dat` for a 2D field: dF holds the tensor Legendre coefficients interlaced
+ * as pop_legendre_analysis_2d writes them, S_host (p x p, column-major, host) is the synthesis matrix of the cell grid
+ * (values = S * coefficients, S[s,a] = P_a(z_s), the inverse of the analysis matrix T); dV receives the values
+ * (entry (i p + s, j p + t) = node s of cell i, node t of cell j).  p <= 64.  Synchronises the stream. */
+int pop_c1_to_legendre(pop_ctx *ctx, int basis, int m, int N, int side, const double *dX, int64_t ldx, double *dY,
+                       int64_t ldy, int64_t cnt);
+int pop_legendre_synthesis_2d(pop_ctx *ctx, int n, int p, const double *S_host, const double *dF, int64_t ldf,
+                              double *dV, int64_t ldv);
 
 /* out-of-place transpose dst (cols x rows, ldd) <- src^T, src rows x cols (lds) */
 int pop_transpose(pop_ctx *ctx, const double *dsrc, int64_t lds, int64_t rows, int64_t cols,

@@ -774,17 +774,18 @@ def assemble_mass(basis: int, m: int, N: int, h) -> Packed:
     return Packed(m, nh, q, 0, 2, Ad, Au, np.zeros_like(Au), B, np.zeros((0, 3, m)), D)
 
 
-def assemble_weaklaplacian(basis: int, m: int, N: int, h) -> Packed:
+def assemble_weaklaplacian(basis: int, m: int, N: int, h, a=None) -> Packed:
     """weaklaplacian(C)[KR,KR] upper data (negative semi-definite).
     C1: src/continuouspolynomial.jl:348-357 ; Dirichlet: src/dirichlet.jl:169-178 (uniform meshes; the reference
     defines it for ranges only).  With an array of element lengths: -(diff C)' G (diff C) with the per-element
     scalings of `diff` on a non-uniform mesh (src/continuouspolynomial.jl:318-325)."""
     q = N - 1
     nh = m + 1 if basis == C1 else m - 1
-    if np.ndim(h) == 0:
+    if np.ndim(h) == 0 and a is None:
         return _assemble_weaklaplacian_uniform(basis, m, N, float(h))
     hk = _element_steps(h, m)
-    si = 1.0 / hk
+    # a: piecewise-constant diffusion coefficient, one value per element: -(D*C)' * (a .* (D*C)) of examples/heat.jl:77-79
+    si = (1.0 if a is None else np.asarray(a, dtype=np.float64)) / hk
     node = np.zeros(m + 1)
     node[:-1] -= si
     node[1:] -= si
@@ -796,7 +797,7 @@ def assemble_weaklaplacian(basis: int, m: int, N: int, h) -> Packed:
         Au = si[1:-1].copy()
     D = np.zeros((1, q, m))
     i1 = np.arange(1, q + 1, dtype=float)
-    D[0] = -4.0 / (hk[None, :] * (2 * i1 + 1)[:, None])
+    D[0] = -4.0 * si[None, :] / (2 * i1 + 1)[:, None]
     return Packed(m, nh, q, 0, 0, Ad, Au, np.zeros_like(Au), np.zeros((0, 3, m)), np.zeros((0, 3, m)), D)
 
 
@@ -825,7 +826,7 @@ def bubble_values(xi, nmax):
     return W, dW
 
 
-def quadrature_matrices(basis: int, m: int, N: int, h):
+def quadrature_matrices(basis: int, m: int, N: int, h, a=None):
     """Dense mass and weak-Laplacian (= -stiffness) of the C1 / Dirichlet basis on a mesh of m elements
     (scalar h: uniform; array: element lengths) with blocks 1..N, computed by Gauss-Legendre quadrature."""
     q = N - 1
@@ -844,7 +845,7 @@ def quadrature_matrices(basis: int, m: int, N: int, h):
         F = np.vstack([hat, W[2:N + 1]])
         dF = np.vstack([dhat, dW[2:N + 1]])
         Ml = (F * wg) @ F.T * (hk[k] / 2)
-        Kl = (dF * wg) @ dF.T * (2 / hk[k])
+        Kl = (dF * wg) @ dF.T * (2 / hk[k]) * (1.0 if a is None else a[k])   # a: diffusion coefficient of the element
         Mm[np.ix_(idx, idx)] += Ml
         Km[np.ix_(idx, idx)] += Kl
     if basis == DIRICHLET:
@@ -1001,6 +1002,22 @@ def c1_from_legendre(basis: int, m: int, N: int, Y: np.ndarray) -> np.ndarray:
     nh = m + 1 if basis == C1 else m - 1
     R = R[:, :nh + m * (N - 2)]                 # W_N needs Legendre degree N: not representable with N degrees
     return np.linalg.lstsq(R, np.asarray(Y, dtype=np.float64), rcond=None)[0]
+
+
+def legendre_from_c1(basis: int, m: int, N: int, X: np.ndarray) -> np.ndarray:
+    """The `Pl.R \\ dat` step of the INVERSE transform `Pl \\ cfs` (src/continuouspolynomial.jl:129-146,171-184;
+    src/dirichlet.jl:97-110): coefficients in C1 / Dirichlet blocks 1..N-1 (columns of X) -> Legendre coefficients, N
+    degrees per element in P ordering = the truncated conversion (P \\ C)[Block.(1:N), Block.(1:N-1)]."""
+    nh = m + 1 if basis == C1 else m - 1
+    return lowering_dense(basis, m, N)[:, :nh + m * (N - 2)] @ np.asarray(X, dtype=np.float64)
+
+
+def synthesis_2d(F: np.ndarray, n: int, p: int, S: np.ndarray) -> np.ndarray:
+    """`legendretransform \\ dat` for a 2D field (the inverse of analysis_2d): F[i + n a, j + n b] = tensor Legendre
+    coefficient (a, b) of cell (i, j), S[s, a] = P_a(z_s); returns vals[i p + s, j p + t]."""
+    C4 = np.asarray(F, dtype=np.float64).reshape(p, n, p, n)              # [a, i, b, j]
+    V = np.einsum("sa,aibj,tb->isjt", S, C4, S, optimize=True)
+    return V.reshape(n * p, n * p)
 
 
 def heat_theta_dense(Md, Kd, u0, dt, theta, nsteps):

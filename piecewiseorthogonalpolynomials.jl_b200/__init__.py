@@ -11,5 +11,5 @@ from .bases import Block, BlockRange, ContinuousPolynomial, DirichletPolynomial,
 from .drivers import (DistMatrix, ElementDecomposition, adi_poisson_dd, dd_columns, DistTranspose, adi_poisson_p2p, heat_steps_p2p, adi_num_iterations, adi_poisson, adi_poisson_distributed, adi_shifts, heat_steps,
                       shard_bounds, spectrum_bounds, eigvals)
 from .rhs import (DiscontinuityError, analysis_2d, cell_grid, legendre_grid_transform, legendre_to_c1, transform, transform_2d,
-                  weakform_apply, weakform_rhs)
+                  weakform_apply, weakform_rhs, c1_to_legendre, synthesis_2d, itransform, itransform_2d, legendre_synthesis_matrix)
 from ._lib import LEFT, RIGHT

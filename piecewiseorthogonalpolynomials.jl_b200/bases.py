@@ -94,13 +94,17 @@ class LazyArrowhead:
     """Linear combination of the infinite mass and weak-Laplacian matrices of one basis;
     `A[KR, KR]` materialises the truncation on the device as Symmetric(BBBArrowheadMatrix)."""
 
-    def __init__(self, basis: _Basis, cm: float, cl: float, ctx=None):
+    def __init__(self, basis: _Basis, cm: float, cl: float, ctx=None, coef=None):
         self.basis, self.cm, self.cl, self.ctx = basis, float(cm), float(cl), ctx
+        self.coef = coef          # per-element diffusion coefficients of the weak-Laplacian part (None: 1)
 
     def _comb(self, o, s):
         if not isinstance(o, LazyArrowhead) or o.basis != self.basis:
             raise TypeError("lazy arrowheads combine only within one basis")
-        return LazyArrowhead(self.basis, self.cm + s * o.cm, self.cl + s * o.cl, self.ctx or o.ctx)
+        ca, cb = (self.coef if self.cl != 0 else None), (o.coef if o.cl != 0 else None)
+        if self.cl != 0 and o.cl != 0 and not ((ca is None and cb is None) or (ca is not None and cb is not None and np.array_equal(ca, cb))):
+            raise TypeError("weak Laplacians with different diffusion coefficients do not combine lazily")
+        return LazyArrowhead(self.basis, self.cm + s * o.cm, self.cl + s * o.cl, self.ctx or o.ctx, ca if ca is not None else cb)
 
     def __add__(self, o):
         return self._comb(o, 1.0)
@@ -109,15 +113,15 @@ class LazyArrowhead:
         return self._comb(o, -1.0)
 
     def __neg__(self):
-        return LazyArrowhead(self.basis, -self.cm, -self.cl, self.ctx)
+        return LazyArrowhead(self.basis, -self.cm, -self.cl, self.ctx, self.coef)
 
     def __mul__(self, c):
-        return LazyArrowhead(self.basis, self.cm * c, self.cl * c, self.ctx)
+        return LazyArrowhead(self.basis, self.cm * c, self.cl * c, self.ctx, self.coef)
 
     __rmul__ = __mul__
 
     def __truediv__(self, c):
-        return LazyArrowhead(self.basis, self.cm / c, self.cl / c, self.ctx)
+        return LazyArrowhead(self.basis, self.cm / c, self.cl / c, self.ctx, self.coef)
 
     def __getitem__(self, idx) -> Symmetric:
         KR, JR = idx
@@ -126,7 +130,12 @@ class LazyArrowhead:
         ctx = self.ctx or L.default_context()
         hm, hl = C.c_void_p(), C.c_void_p()
         pm, pl = (C.byref(hm) if self.cm != 0 else None), (C.byref(hl) if self.cl != 0 else None)
-        if self.basis.uniform:
+        coef = self.coef if self.cl != 0 else None
+        if coef is not None:
+            hk = self.basis.hk if not self.basis.uniform else np.full(self.basis.m, float(self.basis.h))
+            L.check(L.lib().pop_assemble_mesh_coef(ctx.handle, self.basis.basis_id, self.basis.m, KR.N, hk.ctypes.data_as(C.c_void_p),
+                                                   coef.ctypes.data_as(C.c_void_p), pm, pl), "assemble")
+        elif self.basis.uniform:
             L.check(L.lib().pop_assemble(ctx.handle, self.basis.basis_id, self.basis.m, KR.N, self.basis.h, pm, pl), "assemble")
         else:
             hk = self.basis.hk
@@ -147,7 +156,12 @@ def grammatrix(basis: _Basis, ctx=None) -> LazyArrowhead:
     return LazyArrowhead(basis, 1.0, 0.0, ctx)
 
 
-def weaklaplacian(basis: _Basis, ctx=None) -> LazyArrowhead:
+def weaklaplacian(basis: _Basis, ctx=None, a=None) -> LazyArrowhead:
     """Delta = weaklaplacian(C), negative semi-definite (src/continuouspolynomial.jl:348-357,
-    src/dirichlet.jl:169-178)."""
-    return LazyArrowhead(basis, 0.0, 1.0, ctx)
+    src/dirichlet.jl:169-178).  a: one positive diffusion coefficient per element, the piecewise-constant case of
+    `-(D*C)' * (a .* (D*C))` (examples/heat.jl:77-79)."""
+    if a is not None:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != (basis.m,):
+            raise L.DimensionMismatch(-2, f"DimensionMismatch: {basis.m} elements, {a.shape} coefficients")
+    return LazyArrowhead(basis, 0.0, 1.0, ctx, a)

@@ -28,6 +28,7 @@ extern "C" int pop_abi_version(void) { return POP_ABI_VERSION; }
 // ------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------
+static int ctx_init(pop_ctx *ctx, int device, void *stream);
 extern "C" int pop_create(pop_ctx **out, int device, void *stream) {
     POP_REQUIRE(out != nullptr, POP_ERR_ARG, "pop_create: null output pointer");
     *out = nullptr;
@@ -43,6 +44,16 @@ extern "C" int pop_create(pop_ctx **out, int device, void *stream) {
     pop_ctx *ctx = new pop_ctx();
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
+    const int rc = ctx_init(ctx, device, stream);
+    if (rc != POP_OK) {   // nothing half-built survives a failed set-up
+        pop_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return POP_OK;
+}
+
+static int ctx_init(pop_ctx *ctx, int device, void *stream) {
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
         ctx->own_stream = false;
@@ -74,21 +85,65 @@ extern "C" int pop_create(pop_ctx **out, int device, void *stream) {
         }
         cudaGetLastError();
     }
-    *out = ctx;
     return POP_OK;
 }
 
 extern "C" int pop_destroy(pop_ctx *ctx) {
     if (!ctx) return POP_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream || !ctx->own_stream) cudaStreamSynchronize(ctx->stream);
+    pop_host_stage_free(ctx);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
-    for (int i = 0; i < 2; ++i) cudaStreamDestroy(ctx->s_copy[i]);
-    for (int i = 0; i < 32; ++i) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->s_copy[i]) cudaStreamDestroy(ctx->s_copy[i]);
+    for (int i = 0; i < 32; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
+    return POP_OK;
+}
+
+// ---- device-resident panels for hosts without a CUDA binding of their own (the Julia shim's DevicePanel) -----------
+extern "C" int pop_panel_alloc(pop_ctx *ctx, int64_t rows, int64_t cols, double **dptr, int64_t *ld) {
+    POP_REQUIRE(ctx && dptr && ld, POP_ERR_ARG, "pop_panel_alloc: null argument");
+    POP_REQUIRE(rows >= 0 && cols >= 0, POP_ERR_DIM, "pop_panel_alloc: negative size");
+    *ld = std::max<int64_t>((rows + 1) & ~(int64_t)1, 2);   // even pitch: every column is 16-byte aligned (the fused kernels' TMA path)
+    *dptr = nullptr;
+    cudaError_t e = cudaMalloc((void **)dptr, (size_t)*ld * (size_t)std::max<int64_t>(cols, 1) * sizeof(double));
+    if (e != cudaSuccess) {
+        pop_set_error("pop_panel_alloc: %lld x %lld doubles: %s", (long long)rows, (long long)cols, cudaGetErrorString(e));
+        return POP_ERR_ALLOC;
+    }
+    POP_CUDA(cudaMemsetAsync(*dptr, 0, (size_t)*ld * (size_t)std::max<int64_t>(cols, 1) * sizeof(double), ctx->stream));
+    return POP_OK;
+}
+
+extern "C" int pop_panel_free(pop_ctx *ctx, double *dptr) {
+    POP_REQUIRE(ctx, POP_ERR_ARG, "pop_panel_free: null ctx");
+    if (!dptr) return POP_OK;
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));
+    POP_CUDA(cudaFree(dptr));
+    return POP_OK;
+}
+
+extern "C" int pop_panel_upload(pop_ctx *ctx, const double *host, int64_t ldh, double *dptr, int64_t ldd, int64_t rows, int64_t cols) {
+    POP_REQUIRE(ctx && (host || rows * cols == 0) && (dptr || rows * cols == 0), POP_ERR_ARG, "pop_panel_upload: null argument");
+    POP_REQUIRE(rows >= 0 && cols >= 0 && ldh >= std::max<int64_t>(rows, 1) && ldd >= std::max<int64_t>(rows, 1), POP_ERR_DIM, "pop_panel_upload: DimensionMismatch");
+    if (rows == 0 || cols == 0) return POP_OK;
+    POP_CUDA(cudaMemcpy2DAsync(dptr, ldd * 8, host, ldh * 8, rows * 8, cols, cudaMemcpyHostToDevice, ctx->stream));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));   // the host array may be freed by its owner as soon as the call returns
+    return POP_OK;
+}
+
+extern "C" int pop_panel_download(pop_ctx *ctx, const double *dptr, int64_t ldd, double *host, int64_t ldh, int64_t rows, int64_t cols) {
+    POP_REQUIRE(ctx && (host || rows * cols == 0) && (dptr || rows * cols == 0), POP_ERR_ARG, "pop_panel_download: null argument");
+    POP_REQUIRE(rows >= 0 && cols >= 0 && ldh >= std::max<int64_t>(rows, 1) && ldd >= std::max<int64_t>(rows, 1), POP_ERR_DIM, "pop_panel_download: DimensionMismatch");
+    if (rows == 0 || cols == 0) return POP_OK;
+    POP_CUDA(cudaMemcpy2DAsync(host, ldh * 8, dptr, ldd * 8, rows * 8, cols, cudaMemcpyDeviceToHost, ctx->stream));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));
     return POP_OK;
 }
 
@@ -553,17 +608,20 @@ extern "C" int pop_assemble(pop_ctx *ctx, int basis, int m, int N, double h, pop
 // The element integrals are those of the uniform closed forms with h -> h_k, i.e. what the reference's generic
 // L' * grammatrix(P) * L (src/continuouspolynomial.jl:259-265,293-297) and -(diff C)' G (diff C)
 // (src/continuouspolynomial.jl:318-325) evaluate to.
-__global__ void k_assemble_mesh(ArrowPtrs M, ArrowPtrs L, int basis, int m, int nh, int q, const double *__restrict__ hk) {
+// ak (may be null = 1): diffusion coefficient of element k, the piecewise-constant case of `-(D*C)' * (a .* (D*C))`
+// (examples/heat.jl:77-79): every element integral of the weak Laplacian is scaled by a_k.
+__global__ void k_assemble_mesh(ArrowPtrs M, ArrowPtrs L, int basis, int m, int nh, int q, const double *__restrict__ hk, const double *__restrict__ ak) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nh) {
         // hat i sits on node i (C1) or node i+1 (Dirichlet): elements node-1 and node
         const int node = basis == POP_BASIS_C1 ? i : i + 1;
         const double hl = node >= 1 ? hk[node - 1] : 0.0, hr = node < m ? hk[node] : 0.0;
         if (M.Ad) M.Ad[i] = (hl + hr) / 3;
-        if (L.Ad) L.Ad[i] = -((node >= 1 ? 1.0 / hl : 0.0) + (node < m ? 1.0 / hr : 0.0));
+        const double al = (ak && node >= 1) ? ak[node - 1] : 1.0, ar = (ak && node < m) ? ak[node] : 1.0;
+        if (L.Ad) L.Ad[i] = -((node >= 1 ? al / hl : 0.0) + (node < m ? ar / hr : 0.0));
         if (i < nh - 1) {   // hats i and i+1 share element `node`
             if (M.Au) M.Au[i] = hr / 6;
-            if (L.Au) L.Au[i] = 1.0 / hr;
+            if (L.Au) L.Au[i] = ar / hr;
         }
     }
     if (i < m && M.B) {
@@ -589,11 +647,16 @@ __global__ void k_assemble_mesh(ArrowPtrs M, ArrowPtrs L, int basis, int m, int 
             M.D[plane + e] = 0.0;
             M.D[2 * plane + e] = (j + 2 < q) ? (h / 2) * (-2.0) / ((2 * j1 + 1) * (2 * j1 + 3) * (2 * j1 + 5)) : 0.0;
         }
-        if (L.D) L.D[e] = -4.0 / (h * (2 * j1 + 1));
+        if (L.D) L.D[e] = -4.0 * (ak ? ak[k] : 1.0) / (h * (2 * j1 + 1));
     }
 }
 
 extern "C" int pop_assemble_mesh(pop_ctx *ctx, int basis, int m, int N, const double *h_elems, pop_arrowhead **mass, pop_arrowhead **lap) {
+    return pop_assemble_mesh_coef(ctx, basis, m, N, h_elems, nullptr, mass, lap);
+}
+
+extern "C" int pop_assemble_mesh_coef(pop_ctx *ctx, int basis, int m, int N, const double *h_elems, const double *a_elems, pop_arrowhead **mass,
+                                      pop_arrowhead **lap) {
     POP_REQUIRE(ctx && h_elems, POP_ERR_ARG, "pop_assemble_mesh: null argument");
     POP_REQUIRE(basis == POP_BASIS_C1 || basis == POP_BASIS_DIRICHLET, POP_ERR_ARG, "pop_assemble_mesh: unknown basis %d", basis);
     POP_REQUIRE(N >= 1, POP_ERR_ARG, "pop_assemble_mesh: need N>=1");
@@ -601,10 +664,15 @@ extern "C" int pop_assemble_mesh(pop_ctx *ctx, int basis, int m, int N, const do
     POP_REQUIRE(m >= 1 && nh >= 1, POP_ERR_DIM, "pop_assemble_mesh: mesh of %d elements has no hat functions for this basis", m);
     for (int k = 0; k < m; ++k) POP_REQUIRE(h_elems[k] > 0, POP_ERR_ARG, "pop_assemble_mesh: element %d has non-positive length (points must be increasing)", k);
     const int q = N - 1;
-    double *dh = nullptr;
-    int rc = pop_ctx_scratch(ctx, (size_t)m * sizeof(double), (void **)&dh);
+    double *dh = nullptr, *da = nullptr;
+    int rc = pop_ctx_scratch(ctx, (size_t)2 * m * sizeof(double), (void **)&dh);
     if (rc) return rc;
     POP_CUDA(cudaMemcpyAsync(dh, h_elems, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (a_elems) {
+        for (int k = 0; k < m; ++k) POP_REQUIRE(a_elems[k] > 0, POP_ERR_ARG, "pop_assemble_mesh: element %d has a non-positive diffusion coefficient", k);
+        da = dh + m;
+        POP_CUDA(cudaMemcpyAsync(da, a_elems, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     pop_arrowhead *hm = nullptr, *hl = nullptr;
     ArrowPtrs pm = {}, pl = {};
     if (mass) {
@@ -621,7 +689,7 @@ extern "C" int pop_assemble_mesh(pop_ctx *ctx, int basis, int m, int N, const do
     }
     const size_t work = std::max<size_t>((size_t)q * m, (size_t)std::max(nh, m));
     const int blocks = (int)std::min<size_t>((work + 255) / 256, 4096);
-    k_assemble_mesh<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(pm, pl, basis, m, nh, q, dh);
+    k_assemble_mesh<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(pm, pl, basis, m, nh, q, dh, da);
     LAUNCH_COUNT(ctx);
     POP_CUDA(cudaGetLastError());
     POP_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's h_elems and the scratch copy may be reused at once

@@ -226,6 +226,8 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
     POP_REQUIRE(!(T && gamma != 0.0) || (F && !(ldf & 1) && !((uintptr_t)F & 15)), POP_ERR_DIM,
                 "fused solve+product needs an even leading dimension and a 16-byte aligned F panel");
     p.stagger_ns = 0;
+    p.f_evict_first = 1;   // measured: 160.8 -> 155.4 us per ADI iteration at 1024 columns per GPU, neutral for large panels
+    if (const char *e = getenv("POP_F_EVICT_FIRST")) p.f_evict_first = atoi(e);
     if (const char *e = getenv("POP_F2_STAGGER_NS")) p.stagger_ns = atoi(e);
     p.gamma = gamma;
     p.F = F ? F : X;

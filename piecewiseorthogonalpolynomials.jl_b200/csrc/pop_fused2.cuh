@@ -32,6 +32,7 @@ struct F2Params {
     double *X;
     int64_t ldx, nrhs;
     // plan
+    int f_evict_first;     // F is a stream without reuse: its loads carry the L2 evict_first policy (the panel then survives in L2 between half steps when it fits)
     int stagger_ns;        // start-up offset between clusters (de-phases the clusters' memory bursts)
     int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap, nf;   // nf: slots of the F ring (fused product)
     int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_hw, o_ring, o_fring;   // offsets in doubles
@@ -221,7 +222,10 @@ __device__ __forceinline__ void f2_issue_fchunk(const F2Params &P, uint64_t *ffu
     const int64_t a0 = gs & ~(int64_t)1, a1 = (gs + (int64_t)nr * P.m + 1) & ~(int64_t)1;
     const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
     mbar_expect_tx(ffull + slot, bytes);
-    tma_load_1d(fring + (size_t)slot * P.slot_stride, fcol + a0, bytes, ffull + slot);
+    if (P.f_evict_first)
+        tma_load_1d_hint(fring + (size_t)slot * P.slot_stride, fcol + a0, bytes, ffull + slot, l2_policy_evict_first());
+    else
+        tma_load_1d(fring + (size_t)slot * P.slot_stride, fcol + a0, bytes, ffull + slot);
 }
 
 template <int ROWS, int NPAR, int ND, bool SKIP1, bool MUL>

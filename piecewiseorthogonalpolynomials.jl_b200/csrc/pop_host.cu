@@ -2,8 +2,14 @@
 // examples/adi_poisson.jl and examples/heat.jl on top of the device kernels.
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "pop_internal.h"
@@ -26,6 +32,158 @@ __global__ void k_repitch(const double *__restrict__ src, int64_t lds, double *_
     }
 }
 
+// ------------------------------------------------------------------------------------
+// PAGEABLE host panels (a Julia Array, a plain NumPy array).  cudaMemcpyAsync on pageable memory is staged by the driver
+// through one small bounce buffer, synchronously: 13 GB/s and no overlap of the two directions on this platform, a sixth
+// of what pinned memory gets.  Here worker threads move the panel through pinned pieces instead: each in-worker copies a
+// piece of the panel into one of its two private pinned slots and queues the H2D copy of the slot, each out-worker
+// queues the D2H copy of a finished piece into a private slot and copies it home.  Pieces are taken in order from
+// shared counters; the device streams order everything else.  The slots live with the context (allocated on first use).
+// ------------------------------------------------------------------------------------
+struct HostStage {
+    char *base = nullptr;          // [2 directions][nthr][2 slots][piece]
+    size_t piece = 0;
+    int nthr = 0;
+    std::vector<cudaEvent_t> ev;   // same indexing as the slots
+};
+
+static int host_stage_threads() {
+    if (const char *e = getenv("POP_HOST_THREADS")) return std::min(std::max(atoi(e), 1), 16);
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min(8u, std::max(2u, hw / 3));   // per direction; measured (16 cores): 3 -> 68 ms, 4 -> 58.5, 6 -> 59, 8 -> 55.5 per 1.34 GB panel
+}
+
+void pop_host_stage_free(pop_ctx *ctx) {
+    HostStage *hs = (HostStage *)ctx->host_stage;
+    if (!hs) return;
+    for (auto e : hs->ev) cudaEventDestroy(e);
+    if (hs->base) cudaFreeHost(hs->base);
+    delete hs;
+    ctx->host_stage = nullptr;
+}
+
+static HostStage *host_stage_get(pop_ctx *ctx, size_t piece) {
+    HostStage *hs = (HostStage *)ctx->host_stage;
+    const int nthr = host_stage_threads();
+    if (hs && hs->piece >= piece && hs->nthr == nthr) return hs;
+    pop_host_stage_free(ctx);
+    hs = new HostStage();
+    hs->piece = piece;
+    hs->nthr = nthr;
+    if (cudaHostAlloc((void **)&hs->base, (size_t)4 * nthr * piece, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        delete hs;
+        return nullptr;
+    }
+    hs->ev.resize((size_t)4 * nthr);
+    for (auto &e : hs->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    ctx->host_stage = hs;
+    return hs;
+}
+
+static bool host_is_pageable(const void *p) {
+    if (const char *e = getenv("POP_HOST_STAGE")) {
+        if (atoi(e) == 0) return false;   // 0: never stage (the driver's own pageable path), 2: always
+        if (atoi(e) == 2) return true;
+    }
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// One transfer of a contiguous host range [host, host + pb.back()) to / from the device range starting at dev, in the
+// pieces [pb[i], pb[i+1]).  in: start_in() launches the workers; wait_in(bytes) returns once every piece below `bytes` has
+// its H2D copy queued on s_copy[0] (the caller then records an event there).  out: start_out(); release_out(bytes) lets
+// the pieces below `bytes` go home -- the caller has made s_copy[1] wait for the kernels that produce them before.
+struct StagedXfer {
+    pop_ctx *ctx;
+    HostStage *hs;
+    char *host, *dev;
+    std::vector<int64_t> pb;
+    std::atomic<int> next_in{0}, next_out{0}, failed{0}, stop{0};
+    std::unique_ptr<std::atomic<int>[]> issued;
+    std::atomic<int64_t> out_ready{0};
+    std::vector<std::thread> thr;
+
+    StagedXfer(pop_ctx *c, HostStage *h, void *hostp, void *devp, std::vector<int64_t> bounds)
+        : ctx(c), hs(h), host((char *)hostp), dev((char *)devp), pb(std::move(bounds)), issued(new std::atomic<int>[pb.size()]) {
+        for (size_t i = 0; i < pb.size(); ++i) issued[i].store(0);
+    }
+    int npieces() const { return (int)pb.size() - 1; }
+    char *slot(int dir, int w, int s) const { return hs->base + (((size_t)dir * hs->nthr + w) * 2 + s) * hs->piece; }
+    cudaEvent_t event(int dir, int w, int s) const { return hs->ev[((size_t)dir * hs->nthr + w) * 2 + s]; }
+
+    void in_worker(int w) {
+        cudaSetDevice(ctx->device);
+        for (int i = 0;; ++i) {
+            const int p = next_in.fetch_add(1);
+            if (p >= npieces() || stop.load()) break;
+            const int s = i & 1;
+            const size_t len = (size_t)(pb[p + 1] - pb[p]);
+            if (i >= 2 && cudaEventSynchronize(event(0, w, s)) != cudaSuccess) failed.store(1);   // the slot's previous copy has left
+            memcpy(slot(0, w, s), host + pb[p], len);
+            if (cudaMemcpyAsync(dev + pb[p], slot(0, w, s), len, cudaMemcpyHostToDevice, ctx->s_copy[0]) != cudaSuccess) failed.store(1);
+            cudaEventRecord(event(0, w, s), ctx->s_copy[0]);
+            issued[p].store(1, std::memory_order_release);
+        }
+    }
+    void out_worker(int w) {
+        cudaSetDevice(ctx->device);
+        int pend = -1, pend_slot = 0;
+        auto finish = [&]() {
+            if (pend < 0) return;
+            if (cudaEventSynchronize(event(1, w, pend_slot)) != cudaSuccess) failed.store(1);
+            memcpy(host + pb[pend], slot(1, w, pend_slot), (size_t)(pb[pend + 1] - pb[pend]));
+            pend = -1;
+        };
+        for (int i = 0;; ++i) {
+            const int p = next_out.fetch_add(1);
+            if (p >= npieces()) break;
+            bool go = true;
+            if (out_ready.load(std::memory_order_acquire) < pb[p + 1]) {
+                finish();                                     // nothing to overlap with: bring the pending piece home first
+                while (out_ready.load(std::memory_order_acquire) < pb[p + 1]) {
+                    if (stop.load()) { go = false; break; }
+                    std::this_thread::sleep_for(std::chrono::microseconds(20));
+                }
+            }
+            if (!go) break;
+            const int s = i & 1;
+            if (pend >= 0 && pend_slot == s) finish();
+            if (cudaMemcpyAsync(slot(1, w, s), dev + pb[p], (size_t)(pb[p + 1] - pb[p]), cudaMemcpyDeviceToHost, ctx->s_copy[1]) != cudaSuccess) failed.store(1);
+            cudaEventRecord(event(1, w, s), ctx->s_copy[1]);
+            if (pend >= 0) finish();                          // the previous piece comes home while this one crosses PCIe
+            pend = p;
+            pend_slot = s;
+        }
+        finish();
+    }
+    void start_in() {
+        for (int w = 0; w < hs->nthr; ++w) thr.emplace_back([this, w] { in_worker(w); });
+    }
+    void start_out() {
+        for (int w = 0; w < hs->nthr; ++w) thr.emplace_back([this, w] { out_worker(w); });
+    }
+    void wait_in(int64_t bytes) {
+        for (int p = 0; p < npieces() && pb[p] < bytes; ++p)
+            while (!issued[p].load(std::memory_order_acquire)) {
+                if (failed.load()) return;
+                std::this_thread::yield();
+            }
+    }
+    void release_out(int64_t bytes) { out_ready.store(bytes, std::memory_order_release); }
+    // joins the workers; abort = true: give up on what has not been released
+    int finish(bool abort) {
+        if (abort) stop.store(1);
+        for (auto &t : thr) t.join();
+        thr.clear();
+        return failed.load() ? POP_ERR_CUDA : POP_OK;
+    }
+};
+
 #define POP_HOST_FLAT_NOFIT (1 << 20)
 // Contiguous host panel (n x nrhs, ldx == n): the panel crosses PCIe as FLAT blocks whose host addresses are 4 KiB
 // aligned, independent of the column boundaries (measured on this platform, tools/pcie: 48.5 GB/s each way for aligned
@@ -42,8 +200,8 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
     // ends so that the first columns are solved and the last block is on its way home after an eighth of a block time
     std::vector<int64_t> bnd;
     bnd.push_back(0);
+    const int64_t U = std::max<int64_t>(A, (blk_bytes / 8) & ~(A - 1));            // ramp unit, a multiple of 4 KiB
     {
-        const int64_t U = std::max<int64_t>(A, (blk_bytes / 8) & ~(A - 1));        // ramp unit, a multiple of 4 KiB
         const int64_t nu = (total - off0 + U - 1) / U;                             // units to cover
         std::vector<int64_t> sizes;                                                // in units
         if (nu >= 1 + 2 + 4 + 8 + 4 + 2 + 1) {
@@ -91,12 +249,30 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
     };
     mark(ctx->stream, -1);
     int rc = POP_OK;
+    // pageable host memory: worker threads carry the panel through pinned pieces of one ramp unit (see StagedXfer)
+    std::unique_ptr<StagedXfer> sx;
+    if (host_is_pageable(X)) {
+        if (HostStage *hs = host_stage_get(ctx, (size_t)U)) {
+            std::vector<int64_t> pb;
+            pb.push_back(0);
+            for (int64_t b = off0 > 0 ? off0 : U; b < total; b += U) pb.push_back(b);
+            pb.push_back(total);
+            sx.reset(new StagedXfer(ctx, hs, X, dflat, std::move(pb)));
+            sx->start_in();
+            sx->start_out();
+        }
+    }
     int64_t col_done = 0;      // columns [0, col_done) are solved
     int blk_home = 0;          // flat blocks [0, blk_home) have been sent back
     for (int k = 0; k < nblk && rc == POP_OK; ++k) {
         mark(ctx->s_copy[0], 0);
-        e = cudaMemcpyAsync(dflat + bnd[k], (const char *)X + bnd[k], (size_t)(bnd[k + 1] - bnd[k]), cudaMemcpyHostToDevice, ctx->s_copy[0]);
-        if (e != cudaSuccess) { pop_set_error("host panel H2D: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
+        if (sx) {
+            sx->wait_in(bnd[k + 1]);
+            if (sx->failed.load()) { pop_set_error("host panel H2D (staged): copy failed"); rc = POP_ERR_CUDA; break; }
+        } else {
+            e = cudaMemcpyAsync(dflat + bnd[k], (const char *)X + bnd[k], (size_t)(bnd[k + 1] - bnd[k]), cudaMemcpyHostToDevice, ctx->s_copy[0]);
+            if (e != cudaSuccess) { pop_set_error("host panel H2D: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
+        }
         cudaEventRecord(h2d[k & 7], ctx->s_copy[0]);
         mark(ctx->s_copy[0], 1);
         const int64_t c_hi = k == nblk - 1 ? nrhs : bnd[k + 1] / colb;   // columns complete on the device
@@ -122,7 +298,8 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
             while (last < nblk && bnd[last + 1] <= col_done * colb) ++last;
             if (last > blk_home) {
                 cudaStreamWaitEvent(ctx->s_copy[1], cmp[k & 7], 0);
-                for (int j = blk_home; j < last; ++j) {
+                if (sx) sx->release_out(bnd[last]);
+                for (int j = blk_home; j < last && !sx; ++j) {
                     mark(ctx->s_copy[1], 4);
                     e = cudaMemcpyAsync((char *)X + bnd[j], dflat + bnd[j], (size_t)(bnd[j + 1] - bnd[j]), cudaMemcpyDeviceToHost, ctx->s_copy[1]);
                     if (e != cudaSuccess) { pop_set_error("host panel D2H: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
@@ -131,6 +308,10 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
                 blk_home = last;
             }
         }
+    }
+    if (sx) {
+        const int rs = sx->finish(rc != POP_OK);
+        if (rc == POP_OK && rs != POP_OK) { pop_set_error("host panel (staged): a copy failed"); rc = rs; }
     }
     cudaStreamSynchronize(ctx->s_copy[0]);
     cudaStreamSynchronize(ctx->stream);
@@ -504,6 +685,39 @@ extern "C" int pop_adi_poisson(pop_ctx *ctx, const pop_arrowhead *K, const pop_a
     return rc;
 }
 
+// Contiguous pageable host range <-> device range through the pinned pieces (StagedXfer), synchronous for the caller:
+// to the device: returns with the copies queued and ctx->stream waiting for them; from the device: returns with the data home.
+static int staged_copy(pop_ctx *ctx, bool to_device, void *host, void *dev, int64_t bytes) {
+    const int64_t U = (int64_t)4 << 20;
+    HostStage *hs = host_stage_get(ctx, (size_t)U);
+    POP_REQUIRE(hs, POP_ERR_ALLOC, "staged copy: no pinned staging memory");
+    std::vector<int64_t> pb;
+    const int64_t off0 = (4096 - (int64_t)((uintptr_t)host % 4096)) % 4096;
+    pb.push_back(0);
+    for (int64_t b = off0 > 0 ? off0 : U; b < bytes; b += U) pb.push_back(b);
+    pb.push_back(bytes);
+    StagedXfer sx(ctx, hs, host, dev, std::move(pb));
+    if (to_device) {
+        POP_CUDA(cudaEventRecord(ctx->ev[24], ctx->stream));
+        POP_CUDA(cudaStreamWaitEvent(ctx->s_copy[0], ctx->ev[24], 0));      // the destination is free
+        sx.start_in();
+        sx.wait_in(bytes);
+        const int rc = sx.finish(false);
+        POP_REQUIRE(rc == POP_OK, POP_ERR_CUDA, "staged copy to the device failed");
+        POP_CUDA(cudaEventRecord(ctx->ev[25], ctx->s_copy[0]));
+        POP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[25], 0));
+    } else {
+        POP_CUDA(cudaEventRecord(ctx->ev[24], ctx->stream));
+        POP_CUDA(cudaStreamWaitEvent(ctx->s_copy[1], ctx->ev[24], 0));      // the source is complete
+        sx.start_out();
+        sx.release_out(bytes);
+        const int rc = sx.finish(false);
+        POP_REQUIRE(rc == POP_OK, POP_ERR_CUDA, "staged copy from the device failed");
+        POP_CUDA(cudaStreamSynchronize(ctx->s_copy[1]));
+    }
+    return POP_OK;
+}
+
 // Host-buffer variant: F (n x n, column-major, leading dimension ldf) in host memory in, X out.  One H2D copy, the whole
 // iteration on the device, one D2H copy: 16 B per entry over PCIe for 2J sweeps of 24 B per entry over HBM.
 extern "C" int pop_adi_poisson_host(pop_ctx *ctx, const pop_arrowhead *K, const pop_arrowhead *M, const double *F, int64_t ldf, double *X, int64_t ldx,
@@ -512,15 +726,38 @@ extern "C" int pop_adi_poisson_host(pop_ctx *ctx, const pop_arrowhead *K, const 
     const int64_t n = K->n();
     POP_REQUIRE(ldf >= n && ldx >= n, POP_ERR_DIM, "pop_adi_poisson_host: leading dimensions too small");
     const int64_t ld = (n + 1) & ~(int64_t)1;
+    // Contiguous host matrices (leading dimension n) cross PCIe as ONE linear copy each way and are re-pitched on the device
+    // (pitched 2-D DMA with an odd row length runs far below the link rate on this platform); pageable ones (a Julia
+    // Array) go through the pinned staging pieces on the way.
+    const bool flatF = ldf == n && n > 1, flatX = ldx == n && n > 1;
+    const bool stageF = flatF && host_is_pageable(F), stageX = flatX && host_is_pageable(X);
     double *buf = nullptr;
-    cudaError_t e = cudaMalloc(&buf, (size_t)ld * n * 2 * sizeof(double));
+    cudaError_t e = cudaMalloc(&buf, (size_t)ld * n * ((flatF || flatX) ? 3 : 2) * sizeof(double));
     if (e != cudaSuccess) { pop_set_error("pop_adi_poisson_host: %zu bytes of device memory: %s", (size_t)ld * n * 16, cudaGetErrorString(e)); return POP_ERR_ALLOC; }
-    double *dF = buf, *dX = buf + (size_t)ld * n;
+    double *dF = buf, *dX = buf + (size_t)ld * n, *flat = buf + (size_t)2 * ld * n;
     int rc = POP_OK;
-    e = cudaMemcpy2DAsync(dF, ld * 8, F, ldf * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
+    if (flatF) {
+        if (stageF) rc = staged_copy(ctx, true, const_cast<double *>(F), flat, n * n * 8);
+        else e = cudaMemcpyAsync(flat, F, (size_t)n * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == POP_OK && e == cudaSuccess) {
+            k_repitch<<<592, 256, 0, ctx->stream>>>(flat, n, dF, ld, n, n);
+            ctx->launches++;
+        }
+    } else {
+        e = cudaMemcpy2DAsync(dF, ld * 8, F, ldf * 8, n * 8, n, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess && rc == POP_OK) {
         rc = pop_adi_poisson(ctx, K, M, dF, ld, dX, ld, a, b, c, d, tol, J);
-        if (rc == POP_OK) e = cudaMemcpy2DAsync(X, ldx * 8, dX, ld * 8, n * 8, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (rc == POP_OK) {
+            if (flatX) {
+                k_repitch<<<592, 256, 0, ctx->stream>>>(dX, ld, flat, n, n, n);
+                ctx->launches++;
+                if (stageX) rc = staged_copy(ctx, false, X, flat, n * n * 8);
+                else e = cudaMemcpyAsync(X, flat, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            } else {
+                e = cudaMemcpy2DAsync(X, ldx * 8, dX, ld * 8, n * 8, n, cudaMemcpyDeviceToHost, ctx->stream);
+            }
+        }
     }
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(buf);

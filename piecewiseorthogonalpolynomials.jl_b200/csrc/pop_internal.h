@@ -70,8 +70,10 @@ struct pop_ctx {
     int *h_info;      // pinned mirror
     // streams/events for the chunked host variants
     cudaStream_t s_copy[2];
-    cudaEvent_t ev[32];   // [0,8) H2D done, [8,16) compute done, [16,24) D2H done, 24: misc
+    cudaEvent_t ev[32];   // [0,8) H2D done, [8,16) compute done, [16,24) D2H done, 24, 25: misc
+    void *host_stage;     // pinned staging pieces for pageable host panels (pop_host.cu), allocated on first use
 };
+void pop_host_stage_free(pop_ctx *ctx);
 
 int pop_ctx_scratch(pop_ctx *ctx, size_t bytes, void **out);
 

@@ -52,6 +52,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 eviction policies for streams with no reuse (evict_first) and for data the next kernel reads back (evict_last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
 // L2 prefetch of a contiguous global range (size a multiple of 16 B)
 __device__ __forceinline__ void l2_prefetch_bulk(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");

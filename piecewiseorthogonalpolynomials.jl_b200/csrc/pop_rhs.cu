@@ -256,6 +256,69 @@ extern "C" int pop_legendre_to_c1(pop_ctx *ctx, int basis, int m, int N, int sid
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Coefficients in ContinuousPolynomial{1} / DirichletPolynomial (blocks 1..N-1) -> Legendre coefficients per element
+// (N degrees, P ordering): the `Pl.R \ dat` of the INVERSE transform `Pl \ cfs` (src/continuouspolynomial.jl:129-146,
+// :171-184; src/dirichlet.jl:97-110,143-163), i.e. the truncated conversion (P \ C)[Block.(1:N), Block.(1:N-1)] of
+// src/continuouspolynomial.jl:226-235:  hat on the left node = (P_0 - P_1)/2, on the right node = (P_0 + P_1)/2,
+// bubble j = W_{j+1} = (P_{j-1} - P_{j+1}) / (2j+1).  One thread per (element, vector), every entry read / written once.
+// ---------------------------------------------------------------------------------------------------
+template <bool LEFT>
+__global__ void __launch_bounds__(256) k_c1_to_legendre(WeakOp w, const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int64_t cnt) {
+    const int m = w.m, N = w.N, q = w.q;   // q = N - 2 bubbles per element
+    const int64_t ix = (int64_t)blockIdx.x * 32 + threadIdx.x, iy = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    const int64_t kk = LEFT ? ix : iy, c = LEFT ? iy : ix;
+    if (kk >= m || c >= cnt) return;
+    const int k = (int)kk;
+    const double *x = LEFT ? X + c * ldx : X + c;
+    double *y = LEFT ? Y + c * ldy : Y + c;
+    const int64_t xs = LEFT ? 1 : ldx, ys = LEFT ? 1 : ldy;
+    const int64_t xstep = (int64_t)m * xs, ystep = (int64_t)m * ys;
+    const int hoff = w.basis == POP_BASIS_C1 ? 0 : -1;
+    const int il = k + hoff, ir = il + 1;                       // hats on the left / right node of element k
+    const double hl = (il >= 0 && il < w.nh) ? x[(int64_t)il * xs] : 0.0, hr = (ir >= 0 && ir < w.nh) ? x[(int64_t)ir * xs] : 0.0;
+    const double *xp = x + ((int64_t)w.nh + k) * xs;            // bubble 1 of element k
+    double *yp = y + (int64_t)k * ys;                           // degree 0 of element k
+    // degree a receives + b_{a+1} / (2a+3) - b_{a-1} / (2a-1); b_j = 0 outside 1..q
+    double bm = 0.0, b0 = 0.0, bp = q >= 1 ? xp[0] : 0.0;       // b_{a-1}, b_a, b_{a+1} at a = 0
+    for (int a = 0; a < N; ++a) {
+        double v = bp / (2 * a + 3);
+        if (a >= 2) v -= bm / (2 * a - 1);
+        if (a == 0) v += 0.5 * (hl + hr);
+        if (a == 1) v += 0.5 * (hr - hl);
+        *yp = v;
+        yp += ystep;
+        bm = b0;
+        b0 = bp;
+        bp = (a + 2 <= q) ? xp[(int64_t)(a + 1) * xstep] : 0.0;   // b_{a+2}
+    }
+}
+
+extern "C" int pop_c1_to_legendre(pop_ctx *ctx, int basis, int m, int N, int side, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t cnt) {
+    POP_REQUIRE(ctx && dX && dY, POP_ERR_ARG, "pop_c1_to_legendre: null argument");
+    POP_REQUIRE(basis == POP_BASIS_C1 || basis == POP_BASIS_DIRICHLET, POP_ERR_ARG, "pop_c1_to_legendre: unknown basis %d", basis);
+    POP_REQUIRE(side == POP_LEFT || side == POP_RIGHT, POP_ERR_ARG, "pop_c1_to_legendre: bad side");
+    const int nh = basis == POP_BASIS_C1 ? m + 1 : m - 1;
+    POP_REQUIRE(m >= 1 && nh >= 1 && N >= 2, POP_ERR_DIM, "pop_c1_to_legendre: need m >= 1 elements with hats and N >= 2 Legendre degrees per element");
+    const int64_t n = (int64_t)nh + (int64_t)m * (N - 2), np = (int64_t)m * N;
+    POP_REQUIRE(cnt >= 0, POP_ERR_DIM, "pop_c1_to_legendre: negative count");
+    if (side == POP_LEFT) POP_REQUIRE(ldx >= n && ldy >= np, POP_ERR_DIM, "pop_c1_to_legendre: DimensionMismatch: X needs %lld rows, Y %lld", (long long)n, (long long)np);
+    else POP_REQUIRE(ldx >= std::max<int64_t>(cnt, 1) && ldy >= std::max<int64_t>(cnt, 1), POP_ERR_DIM, "pop_c1_to_legendre: leading dimensions smaller than the row count");
+    if (cnt == 0) return POP_OK;
+    WeakOp w = {basis, m, N, nh, N - 2, 0.0, nullptr};
+    const dim3 blk(32, 8);
+    if (side == POP_LEFT) {
+        POP_REQUIRE((cnt + 7) / 8 <= 65535, POP_ERR_DIM, "pop_c1_to_legendre: at most 524280 columns per call");
+        k_c1_to_legendre<true><<<dim3((unsigned)((m + 31) / 32), (unsigned)((cnt + 7) / 8)), blk, 0, ctx->stream>>>(w, dX, ldx, dY, ldy, cnt);
+    } else {
+        POP_REQUIRE((m + 7) / 8 <= 65535, POP_ERR_DIM, "pop_c1_to_legendre: at most 524280 elements");
+        k_c1_to_legendre<false><<<dim3((unsigned)((cnt + 31) / 32), (unsigned)((m + 7) / 8)), blk, 0, ctx->stream>>>(w, dX, ldx, dY, ldy, cnt);
+    }
+    ctx->launches++;
+    POP_CUDA(cudaGetLastError());
+    return POP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // per-cell tensor Legendre analysis  C = T V T^T
 // ---------------------------------------------------------------------------------------------------
 #define AN_TILE 4
@@ -265,7 +328,10 @@ extern "C" int pop_legendre_to_c1(pop_ctx *ctx, int basis, int m, int N, int sid
 // differ in ta read 16 consecutive 16-byte words: conflict-free 128-bit loads), columns 4 tb .. 4 tb + 3 (two values
 // per warp: broadcast).  Two passes of p rank-1 updates.  Persistent CTAs loop over the cells (x fastest, so the CTAs
 // that complete one 32 B sector of the interlaced output run at the same time); T is staged once per CTA.
-__global__ void __launch_bounds__(256, 2) k_analysis_2d(int n, int p, const double *__restrict__ T, const double *__restrict__ V, int64_t ldv,
+// SYNTH: the inverse direction (`legendretransform \ dat`): the cell's coefficients are gathered from the interlaced
+// layout, T is the synthesis matrix (values = T * coefficients), the values go to the cell's block of V.
+template <bool SYNTH>
+__global__ void __launch_bounds__(256, 2) k_analysis_2d(int n, int p, const double *__restrict__ T, double *__restrict__ V, int64_t ldv,
                                                         double *__restrict__ F, int64_t ldf) {
     extern __shared__ __align__(16) double an_sm[];
     const int pp = (p + 3) & ~3, ldp = 68;   // p <= 64
@@ -283,11 +349,14 @@ __global__ void __launch_bounds__(256, 2) k_analysis_2d(int n, int p, const doub
     for (int64_t cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
         const int ci = (int)(cell % n), cj = (int)(cell / n);
         // values of the cell: column t of the cell is p consecutive doubles (node s fastest)
-        const double *Vc = V + (int64_t)ci * p + (int64_t)cj * p * ldv;
+        double *Vc = V + (int64_t)ci * p + (int64_t)cj * p * ldv;
+        double *Fc = F + (int64_t)ci + (int64_t)cj * ldf;   // interlaced: degree a of cell ci at row ci + n a
         __syncthreads();   // the previous cell's second pass has read Vt/Wt
         for (int e = tid; e < 64 * pp; e += 256) {
             const int sI = e & 63, t = e >> 6;
-            Vt[sI * ldp + t] = (sI < p && t < p) ? Vc[sI + (int64_t)t * ldv] : 0.0;
+            double v = 0.0;
+            if (sI < p && t < p) v = SYNTH ? Fc[(int64_t)n * sI + (int64_t)n * t * ldf] : Vc[sI + (int64_t)t * ldv];
+            Vt[sI * ldp + t] = v;
         }
         __syncthreads();
         double acc[AN_TILE][AN_TILE];
@@ -329,36 +398,52 @@ __global__ void __launch_bounds__(256, 2) k_analysis_2d(int n, int p, const doub
 #pragma unroll
                     for (int y = 0; y < AN_TILE; ++y) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
             }
-            // interlaced store: degree a of cell ci at row ci + n a
-            double *Fc = F + (int64_t)ci + (int64_t)cj * ldf;
+            // interlaced store: degree a of cell ci at row ci + n a (analysis); node a of the cell (synthesis)
 #pragma unroll
             for (int y = 0; y < AN_TILE; ++y)
 #pragma unroll
                 for (int x = 0; x < AN_TILE; ++x) {
                     const int a = (x < 2 ? a0 : a1 - 2) + x, b = b0 + y;
-                    if (a < p && b < p) Fc[(int64_t)n * a + (int64_t)n * b * ldf] = acc[x][y];
+                    if (a < p && b < p) {
+                        if (SYNTH) Vc[a + (int64_t)b * ldv] = acc[x][y];
+                        else Fc[(int64_t)n * a + (int64_t)n * b * ldf] = acc[x][y];
+                    }
                 }
         }
     }
 }
 
-extern "C" int pop_legendre_analysis_2d(pop_ctx *ctx, int n, int p, const double *T_host, const double *dV, int64_t ldv, double *dF, int64_t ldf) {
-    POP_REQUIRE(ctx && T_host && dV && dF, POP_ERR_ARG, "pop_legendre_analysis_2d: null argument");
-    POP_REQUIRE(n >= 1 && p >= 1, POP_ERR_ARG, "pop_legendre_analysis_2d: need n >= 1 cells per dimension and p >= 1 nodes per cell");
-    POP_REQUIRE(p <= 64, POP_ERR_DIM, "pop_legendre_analysis_2d: p = %d nodes per cell: the per-cell kernel holds p <= 64", p);
+static int cell_transform_2d(pop_ctx *ctx, bool synth, int n, int p, const double *T_host, double *dV, int64_t ldv, double *dF, int64_t ldf) {
+    const char *who = synth ? "pop_legendre_synthesis_2d" : "pop_legendre_analysis_2d";
+    POP_REQUIRE(ctx && T_host && dV && dF, POP_ERR_ARG, "%s: null argument", who);
+    POP_REQUIRE(n >= 1 && p >= 1, POP_ERR_ARG, "%s: need n >= 1 cells per dimension and p >= 1 nodes per cell", who);
+    POP_REQUIRE(p <= 64, POP_ERR_DIM, "%s: p = %d nodes per cell: the per-cell kernel holds p <= 64", who, p);
     const int64_t np = (int64_t)n * p;
-    POP_REQUIRE(ldv >= np && ldf >= np, POP_ERR_DIM, "pop_legendre_analysis_2d: DimensionMismatch: panels need %lld rows", (long long)np);
+    POP_REQUIRE(ldv >= np && ldf >= np, POP_ERR_DIM, "%s: DimensionMismatch: panels need %lld rows", who, (long long)np);
     double *dT = nullptr;
     int rc = pop_ctx_scratch(ctx, (size_t)p * p * sizeof(double), (void **)&dT);
     if (rc) return rc;
     POP_CUDA(cudaMemcpyAsync(dT, T_host, (size_t)p * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const size_t smem = (size_t)3 * 64 * 68 * sizeof(double);
-    POP_CUDA(cudaFuncSetAttribute(k_analysis_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ncell = (int64_t)n * n;
     const unsigned grid = (unsigned)std::min<int64_t>(ncell, (int64_t)2 * ctx->sm_count);
-    k_analysis_2d<<<grid, 256, smem, ctx->stream>>>(n, p, dT, dV, ldv, dF, ldf);
+    if (synth) {
+        POP_CUDA(cudaFuncSetAttribute(k_analysis_2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_analysis_2d<true><<<grid, 256, smem, ctx->stream>>>(n, p, dT, dV, ldv, dF, ldf);
+    } else {
+        POP_CUDA(cudaFuncSetAttribute(k_analysis_2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_analysis_2d<false><<<grid, 256, smem, ctx->stream>>>(n, p, dT, dV, ldv, dF, ldf);
+    }
     ctx->launches++;
     POP_CUDA(cudaGetLastError());
     POP_CUDA(cudaStreamSynchronize(ctx->stream));   // T_host and the scratch copy may be reused at once
     return POP_OK;
+}
+
+extern "C" int pop_legendre_analysis_2d(pop_ctx *ctx, int n, int p, const double *T_host, const double *dV, int64_t ldv, double *dF, int64_t ldf) {
+    return cell_transform_2d(ctx, false, n, p, T_host, const_cast<double *>(dV), ldv, dF, ldf);
+}
+
+extern "C" int pop_legendre_synthesis_2d(pop_ctx *ctx, int n, int p, const double *S_host, const double *dF, int64_t ldf, double *dV, int64_t ldv) {
+    return cell_transform_2d(ctx, true, n, p, S_host, dV, ldv, const_cast<double *>(dF), ldf);
 }

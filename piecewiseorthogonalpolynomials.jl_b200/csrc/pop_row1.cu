@@ -107,11 +107,11 @@ static int row1_launch(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     cfg.numAttrs = 1;
     // persistent clusters: as many as are co-resident (queried once per shape)
     static std::mutex plan_mu;
-    static int cached_key[6] = {0, 0, 0, 0, 0, 0}, cached_ncl = 0;
-    const int key[6] = {rows, rb, npar * 2 + (op.has1 != 0), cs, nthr, (int)smem};
+    static int cached_key[7] = {0, 0, 0, 0, 0, 0, -1}, cached_ncl = 0;
+    const int key[7] = {rows, rb, npar * 2 + (op.has1 != 0), cs, nthr, (int)smem, ctx->device};
     std::lock_guard<std::mutex> lk(plan_mu);
     int ncl = cached_ncl;
-    if (!std::equal(key, key + 6, cached_key) || ncl <= 0) {
+    if (!std::equal(key, key + 7, cached_key) || ncl <= 0) {
         cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count));
         int nc = 0;
         if (cudaOccupancyMaxActiveClusters(&nc, (const void *)kern, &cfg) != cudaSuccess || nc <= 0) {
@@ -119,7 +119,7 @@ static int row1_launch(pop_ctx *ctx, const RowOp &op, const double *F, double *R
             return POP_ROW1_UNSUPPORTED;
         }
         ncl = nc;
-        std::copy(key, key + 6, cached_key);
+        std::copy(key, key + 7, cached_key);
         cached_ncl = ncl;
     }
     const int cap = env_int("POP_ROW1_NCL", 0);

@@ -52,12 +52,18 @@ struct R2Params {
     int m, nh, q;
     int cs, mlc, nch, nblk, pf_dist;
     int pairing;                   // clusters 2p and 2p+1 work on the row blocks 2b and 2b+1 at the same time (the two halves of every 128 B line)
-    int hf_rows;                   // rows of HF: entry 0, the hats, zero pads up to 4*lp+1 and m+2
+    int hfs;                       // doubles per row of HF: HF[row][2 + hat], zeros in front of hat 0 and behind hat nh-1 (even, hfs/2 odd: rows land in different banks)
+    int hat_mode;                  // 1: the compute warps solve the hat systems themselves, one warp per row, hat_L hats per lane (Kogge-Stone over the lanes)
+    int hat_L;
+    int o_ks;                      // tables of the warp-per-row hat scan (hat_mode 1): [2][5][32] step multipliers, then cd, cu, rd as [hat_L][32] (entry (i, lane) = hat lane*L + i - 1)
+    int o_pos;                     // int [hfs]: position of hat h inside a row of HF at index h + 1 (hat -1 and the hats behind the last are zero pads)
     int lp;                        // hats per scan segment (8 segments; tables and HF are padded to 8*lp)
     // shared-memory offsets (bytes)
     int o_in, o_inh, o_fh, o_ring, o_mb, o_hf, o_ct, o_tab, o_ttab, o_ftab, o_hrd, o_hcd, o_hcu, o_ss, o_st, total;
     int mbw;                       // doubles per mailbox message
-    long long *dbg;                // POP_ROW2_TRACE: phase time stamps of CTA 0 (clock64), [block][10]
+    int f_evict_first;             // F loads carry the L2 evict_first policy
+    int no_send;                   // stand-in profiling only (POP_ROW2_NOSEND): skip the sends, to time them by difference
+    long long *dbg;                // POP_ROW2_TRACE: phase time stamps of CTA 0 (clock64), [block][16]
     // remote mode (several GPUs, or forced): the row direction is split over nr = world * csv CTAs that meet through
     // mailboxes in (peer) global memory instead of a cluster's shared memory
     int remote, world, me, csv, nr;
@@ -71,6 +77,11 @@ struct R2Params {
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -98,7 +109,7 @@ __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wai
 // a fixed mlc addresses it with compile-time offsets; the arrays that depend on nh, m, cs and on the number of ring slots
 // follow (their offsets travel in R2Params).
 struct R2Fixed {
-    int in, inh, fh, ct, tab, ttab, ftab, gtab, ss, st, ring, cb, hbs;
+    int in, inh, fh, ct, tab, ttab, ftab, gtab, ss, st, se, ring, cb, hbs;
 };
 __host__ __device__ constexpr int r2_al(int x) { return (x + 127) / 128 * 128; }
 __host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc, int rb) {
@@ -117,6 +128,7 @@ __host__ __device__ constexpr R2Fixed r2_fixed(int ch, int dc, int mlc, int rb) 
     f.gtab = o; o += r2_al((2 * ch + 2) * 16);
     f.ss = o; o += r2_al(R2_NBMAX * 3 * mlc * 8);
     f.st = o; o += r2_al(R2_NBMAX * 3 * mlc * 8);
+    f.se = o; o += r2_al(4 * R2_NBMAX * 3 * 8 + (2 * mlc + 8) * 8);
     f.ring = o;
     return f;
 }
@@ -139,20 +151,37 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st
 // single reader spins on it and puts R2_EMPTY back.  Data and "flag" are the same atomic 8-byte store: no fence, no second
 // round trip over NVLink (the slot is reused two half steps later, ordered by the messages in between).
 #define R2_EMPTY 0xffffffffffffffffull
+// the wait itself (rare: a message usually arrived long before it is read) stays out of line, the kernel inlines only the test
+__device__ __noinline__ unsigned long long r2_mbspin(volatile unsigned long long *q, unsigned long long *err) {
+    unsigned long long v;
+    long long spins = 0;
+    while ((v = *q) == R2_EMPTY) {
+        if (++spins > 100000000LL) {   // a peer died: do not hang the device
+            *err = 1;
+            v = 0;
+            break;
+        }
+    }
+    return v;
+}
 __device__ __forceinline__ double r2_mbld(const double *p, int mode, unsigned long long *err) {   // mode 0: shared memory, 1: remote, 2: remote stand-in (profiling: entries are never emptied)
     if (!mode) return *p;
     volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(const_cast<double *>(p));
     unsigned long long v = *q;
-    if (v == R2_EMPTY) {
-        long long spins = 0;
-        while ((v = *q) == R2_EMPTY) {
-            if (++spins > 100000000LL) {   // a peer died: do not hang the device
-                *err = 1;
-                v = 0;
-                break;
-            }
-        }
-    }
+    if (v == R2_EMPTY) v = r2_mbspin(q, err);
+    if (mode == 1) *q = R2_EMPTY;
+    return __longlong_as_double((long long)v);
+}
+
+// The same in two steps, so that several entries are requested before the first one is waited for (a mailbox read is an
+// L2 or NVLink round trip: issued one after the other they add up on the critical path of the row block).
+// (measured on 8 GPUs: ld.relaxed.gpu / ld.global.cg loads and plain or 16-byte stores change nothing, profiles/r2_dd8_variants.txt)
+__device__ __forceinline__ unsigned long long r2_mbpeek(const double *p) {
+    return *reinterpret_cast<volatile const unsigned long long *>(p);
+}
+__device__ __forceinline__ double r2_mbtake(const double *p, unsigned long long v, int mode, unsigned long long *err) {
+    volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(const_cast<double *>(p));
+    if (v == R2_EMPTY) v = r2_mbspin(q, err);
     if (mode == 1) *q = R2_EMPTY;
     return __longlong_as_double((long long)v);
 }
@@ -163,13 +192,15 @@ __device__ __forceinline__ double r2_mbld(const double *p, int mode, unsigned lo
 // copies, and meets the compute threads only through mbarriers (no block-wide barrier on the data path).
 #define R2_FG 4            // chunks per proxy fence in the output phase
 #define R2_BAR_COMPUTE 1   // named barrier of the compute threads
-#define R2_STAMP(slot) do { if (P.dbg && blockIdx.x == 0 && tid == 0 && t < 64) P.dbg[t * 10 + (slot)] = clock64(); } while (0)
+#define R2_STAMP(slot) do { if (P.dbg && blockIdx.x == 0 && tid == 0 && t < 64) P.dbg[t * 16 + (slot)] = clock64(); } while (0)
 #define R2_BAR_HATS 2      // compute threads + the two hat warps: hats solved
 #define R2_BAR_MSG 3       // compute threads (arrive) + the two hat warps (sync): this CTA's message is written
 #define R2_COMPUTE_SLOTS 512   // threads [0, 512): compute (the first 16 mlc of them work), [512, 640): producer warp group
 // MLC > 0: elements per CTA fixed at compile time (every hot shared-memory address is then one register plus an immediate).
 // RB rows per block: 8 (64 B runs; clusters / groups walk in pairs) or 16 (128 B runs; for panels of few elements per CTA).
-template <int CH, int DC, int MLC, int RB>
+// REM: remote mode (mailboxes in peer-visible global memory, hat systems solved by the compute warps) compiled as a kernel of
+// its own: the cluster-mode kernel carries none of its code (measured: the shared source cost the one-GPU ADI 5 %).
+template <int CH, int DC, int MLC, int RB, bool REM>
 __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Params P) {
     extern __shared__ __align__(128) unsigned char r2_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(r2_raw);
@@ -181,11 +212,12 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     uint64_t *barF = barXfree + NCM;   // [NCM] F of chunk c has landed in region c (bytes)
     uint64_t *barR = barF + NCM;       // [NCM] every compute warp has written its results of chunk c into region c
     const int tid = threadIdx.x;
-    const int cs = P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch;
+    const int cs = REM ? 1 : P.cs, mlc = MLC ? MLC : P.mlc, nch = P.nch;   // remote mode: no cluster
     const int nthr = 2 * RB * mlc;     // compute threads
     const R2Fixed LF = r2_fixed(CH, DC, mlc, RB);   // compile-time constants when MLC > 0
-    const bool remote = P.remote != 0;
-    const int mbmode = P.remote;                   // 0: cluster (shared-memory mailboxes), 1: remote, 2: remote stand-in
+    constexpr bool remote = REM;
+    const int mbmode = REM ? P.remote : 0;         // 0: cluster (shared-memory mailboxes), 1: remote, 2: remote stand-in
+    const bool hatm = REM && P.hat_mode != 0;      // the compute warps solve the hat systems (one warp per row)
     const int G = remote ? P.csv : cs;             // CTAs that share a row block on this GPU
     const int nr = remote ? P.nr : cs;             // ... and over all GPUs
     const int rank = remote ? P.me * P.csv + (int)(blockIdx.x % (unsigned)P.csv) : (cs > 1 ? (int)cluster_ctarank() : 0);
@@ -196,7 +228,16 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     double *INH = reinterpret_cast<double *>(r2_raw + LF.inh);     // [2][(mlc+1)*8]
     double *FH = reinterpret_cast<double *>(r2_raw + LF.fh);       // [2][(mlc+1)*8]
     double *MB = reinterpret_cast<double *>(r2_raw + P.o_mb);       // [2][cs][mbw]
-    double *HF = reinterpret_cast<double *>(r2_raw + P.o_hf);       // [m+3][8], entry i+1 = hat i, zeros around
+    double *HF = reinterpret_cast<double *>(r2_raw + P.o_hf);       // [RB][hfs], entry 2 + i of a row = hat i, zeros around
+    const int HFS = P.hfs;
+    // row stride of HF: hat_mode 1 keeps a row together ([row][position]), hat_mode 0 keeps the rows of a hat together
+    // ([position][row], the layout the two hat warps walk without bank conflicts); posT holds position * (stride of a position)
+    const int HSR = hatm ? HFS : 1;
+    double *ksT = reinterpret_cast<double *>(r2_raw + P.o_ks);
+    // hat h of a row sits at HF[row * HFS + posT(h + 1)]: hat_mode 1 interleaves the hats over the lanes of the scan ((g % L) * 32 + g / L
+    // with g = h + 1: the warp's accesses are conflict-free), hat_mode 0 keeps them in order (2 + h)
+    const int *posTab = reinterpret_cast<const int *>(r2_raw + P.o_pos);
+    auto posT = [&](int g) -> int { return REM ? posTab[g] : (g + 1) * RB; };   // cluster mode: [position][row] with one more pad in front
     double *ct = reinterpret_cast<double *>(r2_raw + LF.ct);       // [3][mlc][8] (both parities summed); later xb [4][mlc][8]
     double2 *tab = reinterpret_cast<double2 *>(r2_raw + LF.tab);   // (rd_j, w2_j)
     double2 *ttab = reinterpret_cast<double2 *>(r2_raw + LF.ttab); // (t0_j, t2_j)
@@ -209,6 +250,10 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     double *hwu = hwd + (64 / RB) * P.lp;                                   // weights of the upward segment maps (times rd_i)
     double *sS = reinterpret_cast<double *>(r2_raw + LF.ss);       // [4][3][mlc]
     double *sT = reinterpret_cast<double *>(r2_raw + LF.st);       // [4][3][mlc]
+    double *sEdge = reinterpret_cast<double *>(r2_raw + LF.se);    // [2][4][3] couplings of the elements k0+mlc (side 0) and k0-1 (side 1): the neighbours' edge elements
+    double *tEdge = sEdge + 2 * R2_NBMAX * 3;                      // the same of the product operator
+    double *tAd = tEdge + 2 * R2_NBMAX * 3;                        // [mlc+1] diagonal of the product's hat block at my hats
+    double *tAu = tAd + mlc + 1;                                   // [mlc+2] its off-diagonal: entry u = coupling of the hats hA+u-1 and hA+u
     const int CBD = LF.cb / 8;                // doubles per chunk of DC degrees
     const int HBD = (mlc + 1) * RB;        // doubles per hat box
     const int HBS = LF.hbs / 8;               // distance of the two parity buffers (TMA destinations: 128 B aligned)
@@ -251,8 +296,23 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             sS[x] = b < P.nb ? P.S[((size_t)b * 3 + t) * m + k0 + e] : 0.0;
             sT[x] = (mul && b < P.nbT) ? P.Ts[((size_t)b * 3 + t) * m + k0 + e] : 0.0;
         }
-        for (int x = tid; x < P.hf_rows * RB; x += nthr)   // zero pads around the hats: entry 0 and everything behind hat nh-1
-            if (x < RB || x >= (nh + 1) * RB) HF[x] = 0.0;
+        for (int x = tid; x < 2 * R2_NBMAX * 3; x += nthr) {
+            const int side = x / (R2_NBMAX * 3), b = (x / 3) % R2_NBMAX, t = x % 3;
+            const int kk = side == 0 ? k0 + mlc : k0 - 1;   // side 0: the right neighbour's first element, side 1: the left neighbour's last
+            const bool in = kk >= 0 && kk < m;
+            sEdge[x] = (in && b < P.nb) ? P.S[((size_t)b * 3 + t) * m + kk] : 0.0;
+            tEdge[x] = (in && mul && b < P.nbT) ? P.Ts[((size_t)b * 3 + t) * m + kk] : 0.0;
+        }
+        for (int x = tid; x < mlc + 2; x += nthr) {
+            const int i = hA + x;
+            if (x <= mlc) tAd[x] = (mul && i < nh) ? P.TAd[i] : 0.0;
+            tAu[x] = (mul && i >= 1 && i < nh) ? P.TAu[i - 1] : 0.0;
+        }
+        for (int x = tid; x < HFS * RB; x += nthr) HF[x] = 0.0;   // the pads around the hats stay zero for the whole kernel
+        for (int g = tid; g < HFS; g += nthr) {
+            int *pw = reinterpret_cast<int *>(r2_raw + P.o_pos);
+            pw[g] = hatm ? ((g < 32 * P.hat_L) ? (g % P.hat_L) * 32 + g / P.hat_L : 32 * P.hat_L) : min(g + 1, HFS - 1) * RB;
+        }
     }
     __syncthreads();
     if (tid < 64 / RB) {
@@ -268,6 +328,33 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         for (int i = P.lp - 1; i >= 0; --i) {
             hwu[a0 + i] = pu * hrd[a0 + i];
             pu *= -hcu[a0 + i];
+        }
+    }
+    if (hatm && tid >= 32 && tid < 64) {
+        // warp-per-row hat scan: lane l owns the hats [l L, (l+1) L); its multipliers and the Kogge-Stone step multipliers
+        const int lane = tid - 32, L = P.hat_L;
+        double ad = 1.0, au = 1.0;
+        for (int i = 0; i < L; ++i) {
+            const int hi = lane * L + i - 1;   // entry 0 of lane 0 is the zero pad in front of hat 0
+            const bool in = hi >= 0 && hi < nh;
+            const double rdv = in ? P.rdA[hi] : 0.0;
+            const double cdv = (in && hi < nh - 1 ? P.offA[hi] : 0.0) * rdv, cuv = (in && hi > 0 ? P.offA[hi - 1] : 0.0) * rdv;
+            ksT[(10 + i) * 32 + lane] = cdv;
+            ksT[(10 + L + i) * 32 + lane] = cuv;
+            ksT[(10 + 2 * L + i) * 32 + lane] = rdv;
+            ad *= -cdv;
+            au *= -cuv;
+        }
+        // step st of the suffix scan multiplies what comes from lane l + 2^st by the product of the multipliers of the lanes
+        // [l, l + 2^st); the prefix scan (upward recurrence) mirrors it
+        for (int st = 0; st < 5; ++st) {
+            double pd = 1.0, pu = 1.0;
+            for (int j = 0; j < (1 << st); ++j) {
+                pd *= __shfl_sync(POP_FULL_MASK, ad, (lane + j) & 31);
+                pu *= __shfl_sync(POP_FULL_MASK, au, (lane - j) & 31);
+            }
+            ksT[st * 32 + lane] = (lane + (1 << st) < 32) ? pd : 0.0;   // zero where the step has no partner: the scan needs no branch
+            ksT[(5 + st) * 32 + lane] = (lane >= (1 << st)) ? pu : 0.0;
         }
     }
     if (tid < 2) {
@@ -325,6 +412,13 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 mbar_expect_tx(barX + c, cbytes);
                 tma_load_3d(IN + (NCM - 1 - c) * CBD, &P.mapX3, (bbase + t * bstride) * RB, kx0, DC * c, barX + c);
             };
+            const uint64_t polF = l2_policy_evict_first();
+            auto load_f = [&](int r, int row0) {   // F of chunk r -> region r (a stream without reuse: evict_first when asked)
+                if (P.f_evict_first)
+                    tma_load_3d_hint(IN + r * CBD, &P.mapF3, row0, kx0, DC * r, barF + r, polF);
+                else
+                    tma_load_3d(IN + r * CBD, &P.mapF3, row0, kx0, DC * r, barF + r);
+            };
             auto load_h = [&](int t) {             // hats of block t (and of F)
                 mbar_expect_tx(barH + (t & 1), (uint32_t)(HBD * 8 * (useF ? 2 : 1)));
                 tma_load_2d(INH + (t & 1) * HBS, &P.mapXh, (bbase + t * bstride) * RB, kx0, barH + (t & 1));
@@ -340,7 +434,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 if (useF)
                     for (int r = 0; r < NCM - nch && r < nch; ++r) {   // regions that never hold X (q below the class maximum)
                         mbar_expect_tx(barF + r, cbytes);
-                        tma_load_3d(IN + r * CBD, &P.mapF3, row0, kx0, DC * r, barF + r);
+                        load_f(r, row0);
                     }
                 for (int c = nch - 1; c >= 0; --c) {
                     const int r = NCM - 1 - c;
@@ -348,7 +442,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                     if (r < nch) {
                         if (useF) {
                             mbar_expect_tx(barF + r, cbytes);
-                            tma_load_3d(IN + r * CBD, &P.mapF3, row0, kx0, DC * r, barF + r);
+                            load_f(r, row0);
                         }
                     } else if (more) {
                         load_x(t + 1, c);
@@ -386,7 +480,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             constexpr int RW = RB / 2, NSEG = 32 / RW;   // rows per hat warp, scan segments per row
             const int lane = tid & 31, l4 = lane % RW, rr = l4 + RW * ((tid - R2_COMPUTE_SLOTS - 32) >> 5), seg = lane / RW;
             const int lp = P.lp;
-            double *col = HF + RB + rr + seg * lp * RB;
+            double *col = HF + rr + (2 + seg * lp) * RB;   // hat_mode 0 layout: [position][row]
             const double *cd = hcd + seg * lp, *cu = hcu + seg * lp, *rdp = hrd + seg * lp;
             const double *wd = hwd + seg * lp, *wu = hwu + seg * lp;
             double Ad = 1.0, Au = 1.0;   // the segment's multipliers of the incoming values
@@ -394,7 +488,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 Ad *= -cd[i];
                 Au *= -cu[i];
             }
-            for (int t = 0; t < nloc; ++t) {
+            for (int t = 0; t < (hatm ? 0 : nloc); ++t) {   // hat_mode 1: the compute warps solve the hats, these two warps idle
                 named_bar_sync(R2_BAR_HATS, nthr + 64);   // the right-hand sides (times rd) of all hats are in HF
                 // pass 1: what leaves my segment at the bottom with zero coming in: a dot product, no chain
                 double b0 = 0.0, b1 = 0.0;
@@ -467,7 +561,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         const uint32_t a_tab = sbase + LF.tab + par * 16, a_ttab = sbase + LF.ttab + par * 16, a_ftab = sbase + LF.ftab + par * 16;
         const uint32_t a_in = off_er + LF.in;
         const uint32_t a_ss = sbase + LF.ss + (par * 3 * mlc + e) * 8, a_st = sbase + LF.st + (par * 3 * mlc + e) * 8;
-        const uint32_t a_hf = sbase + P.o_hf + (k * RB + r) * 8;
+        const uint32_t a_hfr = sbase + P.o_hf + r * HSR * 8;              // row r of HF; hats k-1, k, k+1 through posT
         for (int t = 0; t < nloc; ++t) {
             const int pb = t & 1;
             const uint32_t phMB = (uint32_t)(t >> 1) & 1u;
@@ -557,6 +651,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             if (remote) {
                 // my message into the mailbox of every CTA that shares this row block, on every GPU (mine included)
                 named_bar_sync(R2_BAR_COMPUTE, nthr);
+                if (!P.no_send)
                 for (int g = 0; g < P.world; ++g)
                     for (int dc = 0; dc < G; ++dc) {
                         volatile double *dst = P.mbox[g] + ((mslot + dc) * nr + rank) * mbw;
@@ -593,23 +688,109 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             } else {
                 named_bar_sync(R2_BAR_COMPUTE, nthr);
             }
+            R2_STAMP(10);
             {
                 // right-hand sides (times rd) of ALL hats of the 8 rows, redundantly in every CTA
+                if (REM) {
+                    // remote mailboxes: every thread takes the main entries (hat right-hand sides) of all messages in ONE linear,
+                    // coalesced sweep, four requests in flight before the first is waited for.  Slot u + 1 of message c is hat
+                    // c mlc + u; the slots 0 and mlc + 1 belong to the neighbours' edge hats: they are parked in HE (the idle
+                    // coupling buffer) and added behind a barrier, so no entry is read twice and no address depends on a branch.
+                    const int per = (mlc + 2) * RB, tot = nr * per;
+                    double *HE = ct;   // [2][nr][RB]
+                    for (int y0 = tid; y0 < tot; y0 += 4 * nthr) {
+                        unsigned long long va[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int y = y0 + kk * nthr;
+                            const int c = y / per;
+                            va[kk] = y < tot ? r2_mbpeek(mbp + c * mbw + (y - c * per)) : 0ull;
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int y = y0 + kk * nthr;
+                            if (y < tot) {
+                                const int c = y / per, w = y - c * per, slot = w / RB, rr = w % RB;
+                                const double val = r2_mbtake(mbp + c * mbw + w, va[kk], mbmode, P.merr);
+                                const int i = c * mlc + slot - 1;
+                                if (slot == 0) HE[c * RB + rr] = val;
+                                else if (slot == mlc + 1) HE[(nr + c) * RB + rr] = val;
+                                else if (i < nh) HF[rr * HSR + posT(i + 1)] = val * hrd[i];
+                            }
+                        }
+                    }
+                    named_bar_sync(R2_BAR_COMPUTE, nthr);
+                    for (int x = tid; x < 2 * nr * RB; x += nthr) {
+                        const int side = x / (nr * RB), c = (x / RB) % nr, rr = x % RB;
+                        const int i = side == 0 ? c * mlc - 1 : (c + 1) * mlc;   // the hat next to message c's range
+                        if (i >= 0 && i < nh) {
+                            double *dst = HF + rr * HSR + posT(i + 1);
+                            const double val = HE[x] * hrd[i];
+                            if (side == 1 && c == nr - 1) *dst = val;   // the last hat of a ContinuousPolynomial{1} basis has no other entry
+                            else *dst += val;
+                        }
+                    }
+                } else
                 for (int x = tid; x < nh * RB; x += nthr) {
                     const int i = x / RB, rr = x % RB;
                     const int c = min(i / mlc, nr - 1), u = i - c * mlc;
                     double v = r2_mbld(mbp + c * mbw + (u + 1) * RB + rr, mbmode, P.merr);
                     if (u == 0 && c > 0) v += r2_mbld(mbp + (c - 1) * mbw + (mlc + 1) * RB + rr, mbmode, P.merr);
                     if (u == mlc - 1 && c < nr - 1) v += r2_mbld(mbp + (c + 1) * mbw + rr, mbmode, P.merr);
-                    HF[(i + 1) * RB + rr] = v * hrd[i];
+                    HF[rr * HSR + posT(i + 1)] = v * hrd[i];
                 }
             }
-            named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hat warps take over ...
-            named_bar_sync(R2_BAR_HATS, nthr + 64);   // ... and have solved the hat systems of the 8 rows
+            R2_STAMP(11);
+            if (hatm) {
+                // The two bidiagonal recurrences of the hat block (src/arrowhead.jl:453, :472), one warp per row, lane l owns the
+                // hats [l L, (l+1) L): local recurrence with zero coming in, Kogge-Stone over the lanes with the multipliers of
+                // the factor (tables, the same for every row), local recurrence again with the exact incoming value.
+                named_bar_sync(R2_BAR_COMPUTE, nthr);   // the right-hand sides (times rd) of all hats are in HF
+                R2_STAMP(12);
+                const int w = tid >> 5, lane = tid & 31;
+                if (w < RB) {
+                    const int L = P.hat_L;
+                    double *rowp = HF + w * HFS + lane;   // entry (i, lane) at rowp[i * 32]
+                    const double *cdT = ksT + 10 * 32 + lane, *cuT = cdT + L * 32, *rdT = cuT + L * 32;
+                    // (every pass re-reads the row from shared memory instead of keeping it in registers: the chain of the
+                    // thread's element occupies them)
+                    double tdn = 0.0;
+                    for (int i = L - 1; i >= 0; --i) tdn = fma(-cdT[i * 32], tdn, rowp[i * 32]);
+#pragma unroll
+                    for (int st = 0; st < 5; ++st) {
+                        const double o = __shfl_down_sync(POP_FULL_MASK, tdn, 1 << st);
+                        tdn = fma(ksT[st * 32 + lane], o, tdn);
+                    }
+                    double hin = __shfl_down_sync(POP_FULL_MASK, tdn, 1);
+                    if (lane == 31) hin = 0.0;
+                    for (int i = L - 1; i >= 0; --i) {
+                        hin = fma(-cdT[i * 32], hin, rowp[i * 32]);   // h_i = ytil_i - cd_i h_{i+1}
+                        rowp[i * 32] = hin * rdT[i * 32];
+                    }
+                    double tup = 0.0;
+                    for (int i = 0; i < L; ++i) tup = fma(-cuT[i * 32], tup, rowp[i * 32]);
+#pragma unroll
+                    for (int st = 0; st < 5; ++st) {
+                        const double o = __shfl_up_sync(POP_FULL_MASK, tup, 1 << st);
+                        tup = fma(ksT[(5 + st) * 32 + lane], o, tup);
+                    }
+                    double xin = __shfl_up_sync(POP_FULL_MASK, tup, 1);
+                    if (lane == 0) xin = 0.0;
+                    for (int i = 0; i < L; ++i) {
+                        xin = fma(-cuT[i * 32], xin, rowp[i * 32]);   // x_i = h_i rd_i - cu_i x_{i-1}
+                        rowp[i * 32] = xin;
+                    }
+                }
+                R2_STAMP(13);
+                named_bar_sync(R2_BAR_COMPUTE, nthr);   // the hats of all rows are solved
+            } else {
+                named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hat warps take over ...
+                named_bar_sync(R2_BAR_HATS, nthr + 64);   // ... and have solved the hat systems of the rows
+            }
             // ---- E2: the corrections of the coupled bubbles (:475-477) carried through the sweep by its impulse responses,
             //      product, output
             R2_STAMP(6);
-            const double h0 = lds_f64(a_hf), h1 = lds_f64(a_hf + RB * 8), h2 = lds_f64(a_hf + 2 * RB * 8);
+            const double h0 = lds_f64(a_hfr + posT(k) * 8), h1 = lds_f64(a_hfr + posT(k + 1) * 8), h2 = lds_f64(a_hfr + posT(k + 2) * 8);
             double d0, d1;
             {
                 const uint32_t sb = a_ss;
@@ -696,13 +877,14 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             if (tid < nhl * RB) {
                 const int u = tid / RB, rr = tid % RB, i = hA + u;
                 const int64_t rw = (int64_t)row0 + rr;
-                const double hc = HF[(i + 1) * RB + rr];
+                const double *hrow = HF + rr * HSR;       // hat h of this row: hrow[posT(h + 1)]
+                const double hc = hrow[posT(i + 1)];
                 double out = hc;
                 if (mul) {
-                    const double hp = HF[i * RB + rr], hn = HF[(i + 2) * RB + rr];
-                    double acc = P.TAd[i] * hc;
-                    if (i + 1 < nh) acc = fma(P.TAu[i], hn, acc);
-                    if (i > 0) acc = fma(P.TAu[i - 1], hp, acc);
+                    const double hp = hrow[posT(i)], hn = hrow[posT(i + 2)];
+                    double acc = tAd[u] * hc;
+                    acc = fma(tAu[u + 1], hn, acc);   // zero beyond the last hat
+                    acc = fma(tAu[u], hp, acc);       // zero in front of the first
 #pragma unroll
                     for (int tt = 0; tt < 3; ++tt) {
                         const int el = u + 1 - tt, kk = k0 + el;   // slot tt of element kk couples to hat i
@@ -714,23 +896,26 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                             // neighbour's message) and the hats, exactly as its owner computes them
                             const int nbr = el < 0 ? rank - 1 : rank + 1, side = el < 0 ? 1 : 0;
                             const double *zz = mbp + nbr * mbw + (mlc + 2) * RB + side * R2_NBMAX * RB + rr;
-                            const double g0 = HF[kk * RB + rr], g1 = HF[(kk + 1) * RB + rr], g2 = HF[(kk + 2) * RB + rr];
+                            const double g0 = hrow[posT(kk)], g1 = hrow[posT(kk + 1)], g2 = hrow[posT(kk + 2)];
                             double xs[R2_NBMAX];
+                            unsigned long long zv[R2_NBMAX];
+#pragma unroll
+                            for (int b = 0; b < R2_NBMAX; ++b) zv[b] = mbmode ? r2_mbpeek(zz + b * RB) : 0ull;   // all four requested at once
 #pragma unroll
                             for (int b = 0; b < R2_NBMAX; ++b) {
-                                double v = r2_mbld(zz + b * RB, mbmode, P.merr);
-                                if (b < P.nb) {
-                                    const double *sg = P.S + (size_t)b * 3 * m + kk;
-                                    v = fma(-__ldg(sg), g0, v);
-                                    v = fma(-__ldg(sg + m), g1, v);
-                                    v = fma(-__ldg(sg + 2 * m), g2, v);
+                                double v = mbmode ? r2_mbtake(zz + b * RB, zv[b], mbmode, P.merr) : zz[b * RB];
+                                {   // couplings of the neighbour's edge element (zero beyond P.nb), cached at set-up
+                                    const double *sg = sEdge + (side * R2_NBMAX + b) * 3;
+                                    v = fma(-sg[0], g0, v);
+                                    v = fma(-sg[1], g1, v);
+                                    v = fma(-sg[2], g2, v);
                                 }
                                 if (b >= 2) v = fma(-tab[b - 2].y, xs[b - 2], v);
                                 xs[b] = v * tab[b].x;
                             }
 #pragma unroll
                             for (int b = 0; b < R2_NBMAX; ++b)
-                                if (b < P.nbT) acc = fma(__ldg(P.Ts + ((size_t)b * 3 + tt) * m + kk), xs[b], acc);
+                                acc = fma(tEdge[(side * R2_NBMAX + b) * 3 + tt], xs[b], acc);
                         }
                     }
                     out = useF ? fma(P.gamma, fh[u * RB + rr], acc) : acc;
@@ -799,25 +984,30 @@ static bool r2_make_maps(encode_tiled_t enc, const double *base, int64_t ld, int
 }
 
 typedef void (*r2_kernel_t)(const R2Params);
-static r2_kernel_t r2_kernel(int ch, int dc, int mlc, int rb) {
+template <bool REM>
+static r2_kernel_t r2_kernel_t8(int ch, int dc, int mlc) {   // 8 rows per block
+    if (mlc == 32 && ch == 32) return dc == 8 ? k_row2<32, 8, 32, 8, REM> : k_row2<32, 4, 32, 8, REM>;   // the ADI shapes (m = 128: cluster of 4, m = 256: of 8)
+    switch (ch) {
+        case 8: return dc == 8 ? k_row2<8, 8, 0, 8, REM> : k_row2<8, 4, 0, 8, REM>;
+        case 16: return dc == 8 ? k_row2<16, 8, 0, 8, REM> : k_row2<16, 4, 0, 8, REM>;
+        case 24: return dc == 8 ? k_row2<24, 8, 0, 8, REM> : k_row2<24, 4, 0, 8, REM>;
+        case 32: return dc == 8 ? k_row2<32, 8, 0, 8, REM> : k_row2<32, 4, 0, 8, REM>;
+    }
+    return nullptr;
+}
+static r2_kernel_t r2_kernel(int ch, int dc, int mlc, int rb, bool rem) {
+    if (!rem) return rb == 8 ? r2_kernel_t8<false>(ch, dc, mlc) : nullptr;   // cluster mode walks 8-row blocks only
     if (rb == 16) {   // panels of few elements per CTA (8 GPUs: 16 elements each): 16 rows per block
-        if (mlc == 16 && ch == 32) return dc == 8 ? k_row2<32, 8, 16, 16> : k_row2<32, 4, 16, 16>;
+        if (mlc == 16 && ch == 32) return dc == 8 ? k_row2<32, 8, 16, 16, true> : k_row2<32, 4, 16, 16, true>;
         switch (ch) {
-            case 8: return dc == 8 ? k_row2<8, 8, 0, 16> : k_row2<8, 4, 0, 16>;
-            case 16: return dc == 8 ? k_row2<16, 8, 0, 16> : k_row2<16, 4, 0, 16>;
-            case 24: return dc == 8 ? k_row2<24, 8, 0, 16> : k_row2<24, 4, 0, 16>;
-            case 32: return dc == 8 ? k_row2<32, 8, 0, 16> : k_row2<32, 4, 0, 16>;
+            case 8: return dc == 8 ? k_row2<8, 8, 0, 16, true> : k_row2<8, 4, 0, 16, true>;
+            case 16: return dc == 8 ? k_row2<16, 8, 0, 16, true> : k_row2<16, 4, 0, 16, true>;
+            case 24: return dc == 8 ? k_row2<24, 8, 0, 16, true> : k_row2<24, 4, 0, 16, true>;
+            case 32: return dc == 8 ? k_row2<32, 8, 0, 16, true> : k_row2<32, 4, 0, 16, true>;
         }
         return nullptr;
     }
-    if (mlc == 32 && ch == 32) return dc == 8 ? k_row2<32, 8, 32, 8> : k_row2<32, 4, 32, 8>;   // the ADI shapes (m = 128: cluster of 4, m = 256: of 8)
-    switch (ch) {
-        case 8: return dc == 8 ? k_row2<8, 8, 0, 8> : k_row2<8, 4, 0, 8>;
-        case 16: return dc == 8 ? k_row2<16, 8, 0, 8> : k_row2<16, 4, 0, 8>;
-        case 24: return dc == 8 ? k_row2<24, 8, 0, 8> : k_row2<24, 4, 0, 8>;
-        case 32: return dc == 8 ? k_row2<32, 8, 0, 8> : k_row2<32, 4, 0, 8>;
-    }
-    return nullptr;
+    return r2_kernel_t8<true>(ch, dc, mlc);
 }
 
 static int r2_align(int x, int a) { return (x + a - 1) / a * a; }
@@ -889,9 +1079,22 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.mbw = (mlc + 2) * rb + 2 * R2_NBMAX * rb;
     const int nseg = 64 / rb;                                // scan segments per row (two hat warps share the rows)
     const int lp = (((op.nh + nseg - 1) / nseg) + 3) & ~3;  // hats per scan segment, a multiple of 4
-    const int hf_rows = std::max(nseg * lp + 2, op.m + 3);
-    // behind the ring: HF, the padded hat tables, the mailboxes
-    const int tail = r2_align(hf_rows * rb * 8, 128) + 2 * r2_align(nseg * lp * 8, 128) + r2_align(3 * nseg * lp * 8, 128) + r2_align(2 * cs * P.mbw * 8, 128);
+    // warp-per-row hat scan by the compute warps: needs a warp per row and at most 8 hats per lane
+    const int hat_L = (std::max(op.nh, op.m) + 3 + 31) / 32;   // 32 L entries of a row: the pad of hat -1, the hats, at least one pad behind (hats up to m + 1 are read)
+    // default: remote mode only (measured on one box: cluster mode 71.1 ms per ADI solve with the two hat warps, 74.5 with the
+    // compute warps scanning; remote mode 8-GPU shape 15.4 against 15.25)
+    const int hat_mode = (rem && nthr / 32 >= rb && hat_L <= 16 && r2_env("POP_ROW2_HATMODE", 1)) ? 1 : 0;
+    int hfs = std::max(hat_mode ? 32 * hat_L : nseg * lp, op.m + 2) + 4;   // zero entries in front of hat 0 and behind the last hat
+    if (hat_mode) {
+        hfs = (hfs + 1) & ~1;
+        if (!((hfs / 2) & 1)) hfs += 2;                                     // even with hfs / 2 odd: the rows start in different banks
+    }
+    // (shared memory beyond 196 KB costs the next carve-out step: 28 KB of L1 instead of 60 KB, and the spills of the compute
+    // warps live there -- measured 71.1 -> 74.5 ms per ADI solve on one GPU when these tables pushed the CTA over it)
+    const int ks_bytes = hat_mode ? (10 + 3 * hat_L) * 32 * 8 : 0;
+    // behind the ring: HF, the padded hat tables, the scan tables, the mailboxes
+    const int tail = r2_align(hfs * rb * 8, 128) + 2 * r2_align(nseg * lp * 8, 128) + r2_align(3 * nseg * lp * 8, 128) + r2_align(ks_bytes, 128) + r2_align(hfs * 4, 128) +
+                     r2_align(2 * cs * P.mbw * 8, 128);
     (void)want_cs;
     // degrees per chunk (TMA box, region of the row block buffer): 4 keeps the hand-over between the blocks fine-grained
     const int dc = r2_env("POP_ROW2_DC", 4) == 8 ? 8 : 4;
@@ -900,15 +1103,20 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     if (LF.ring + tail > ctx->max_smem_optin) return unsupported("shared memory too small for the row block");
     if (4 + 4 * ((2 * ch + dc - 1) / dc) > 128) return unsupported("too many barriers");
     int o = LF.ring;
-    P.o_hf = o; o += r2_align(hf_rows * rb * 8, 128);
+    P.o_hf = o; o += r2_align(hfs * rb * 8, 128);
     P.o_hrd = o; o += r2_align(nseg * lp * 8, 128);
     P.o_hcd = o; o += r2_align(nseg * lp * 8, 128);
     P.o_hcu = o; o += r2_align(3 * nseg * lp * 8, 128);   // hcu, hwd, hwu
+    P.o_ks = o; o += r2_align(ks_bytes, 128);
+    P.o_pos = o; o += r2_align(hfs * 4, 128);
     P.o_mb = o; o += r2_align(2 * cs * P.mbw * 8, 128);
     P.total = o;
     if ((size_t)P.total > (size_t)ctx->max_smem_optin) return unsupported("shared memory too small");
     P.lp = lp;
-    P.hf_rows = hf_rows;
+    P.hfs = hfs;
+    P.hat_mode = hat_mode;
+    P.hat_L = hat_L;
+    P.f_evict_first = r2_env("POP_F_EVICT_FIRST", 1);
     P.pf_dist = r2_env("POP_ROW2_PF", 0);   // L2 prefetch distance of F in row blocks (0: off)
 
     const int pm = rem ? op.ml : op.m, pnh = rem ? op.nhl : op.nh;   // the panel: all elements, or this GPU's
@@ -933,10 +1141,12 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
         P.epoch = rem->epoch;
         for (int g = 0; g < rem->world; ++g) P.mbox[g] = rem->mbox[g];
         P.merr = rem->merr;
+        P.no_send = (rem->standin && r2_env("POP_ROW2_NOSEND", 0)) ? 1 : 0;
         if ((int64_t)2 * P.nblk * P.csv * P.nr * P.mbw > rem->mbox_doubles) return unsupported("mailbox too small");
+        if (P.nr > 2 * mlc) return unsupported("more CTAs per row block than the edge buffer holds");   // HE aliases the coupling buffer [4][mlc][rb]
     }
 
-    r2_kernel_t kern = r2_kernel(ch, dc, mlc, rb);
+    r2_kernel_t kern = r2_kernel(ch, dc, mlc, rb, rem != nullptr);
     if (!kern) return unsupported("no kernel for this chain class");
     POP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.total));
     cudaLaunchConfig_t cfg = {};
@@ -989,26 +1199,36 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
                 P.nblk, P.useF);
     long long *dbg = nullptr;
     if (r2_env("POP_ROW2_TRACE", 0)) {
-        POP_CUDA(cudaMalloc(&dbg, 64 * 10 * sizeof(long long)));
-        POP_CUDA(cudaMemset(dbg, 0, 64 * 10 * sizeof(long long)));
+        POP_CUDA(cudaMalloc(&dbg, 64 * 16 * sizeof(long long)));
+        POP_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
         P.dbg = dbg;
     }
     POP_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     ctx->launches++;
     if (dbg) {   // debugging aid: phase durations of CTA 0 in SM clock cycles
-        long long h[64 * 10];
+        long long h[64 * 16];
         POP_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(dbg);
         static const char *names[8] = {"wait X", "load+backward", "couplings", "message", "forward", "wait hats", "corrections", "chunks"};
-        double sum[10] = {0};
+        static const char *sub[5] = {"messages in", "rhs built", "barrier", "scan", "barrier"};   // stamps 10..14 inside "wait hats"
+        double sum[10] = {0}, ssum[5] = {0};
         int nb = 0;
-        for (int t = 2; t < 64 && h[t * 10 + 9]; ++t, ++nb) {
-            for (int i = 0; i < 9; ++i) sum[i] += (double)(h[t * 10 + i + 1] - h[t * 10 + i]);
+        for (int t = 2; t < 64 && h[t * 16 + 9]; ++t, ++nb) {
+            for (int i = 0; i < 9; ++i) sum[i] += (double)(h[t * 16 + i + 1] - h[t * 16 + i]);
+            long long prev = h[t * 16 + 5];
+            for (int i = 0; i < 5; ++i)
+                if (h[t * 16 + 10 + i]) {
+                    ssum[i] += (double)(h[t * 16 + 10 + i] - prev);
+                    prev = h[t * 16 + 10 + i];
+                }
         }
         if (nb) {
             fprintf(stderr, "pop_row2 trace (CTA 0, thread 0, mean SM cycles over %d row blocks):", nb);
             for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %.0f |", names[i], sum[i] / nb);
-            fprintf(stderr, " hat rows + end %.0f | block %.0f\n", sum[8] / nb, (double)(h[(2 + nb - 1) * 10 + 9] - h[2 * 10]) / nb);
+            fprintf(stderr, " hat rows + end %.0f | block %.0f\n", sum[8] / nb, (double)(h[(2 + nb - 1) * 16 + 9] - h[2 * 16]) / nb);
+            fprintf(stderr, "  inside wait hats:");
+            for (int i = 0; i < 5; ++i) fprintf(stderr, " %s %.0f |", sub[i], ssum[i] / nb);
+            fprintf(stderr, "\n");
         }
     }
     return POP_OK;

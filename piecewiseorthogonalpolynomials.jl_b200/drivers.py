@@ -35,7 +35,7 @@ def adi_shifts(J, a, b, c, d):
     return p, q
 
 
-def adi_poisson(M, K, F, a, b, c=None, d=None, tol=1e-15, J=0):
+def adi_poisson(M, K, F, a, b, c=None, d=None, tol=1e-15, J=0, out=None):
     """Solve K X M + M X K = F by the reference's ADI iteration on ONE GPU.  F: CUDA torch tensor
     (n x n, column-major) or NumPy array; returns X of the same kind.  (a,b) enclose the spectrum
     of K^{-1}M; c,d default to -b,-a as in examples/adi_poisson.jl:107."""
@@ -45,7 +45,9 @@ def adi_poisson(M, K, F, a, b, c=None, d=None, tol=1e-15, J=0):
     if not hasattr(F, "data_ptr"):
         # host arrays: pop_adi_poisson_host (one copy in, the iteration on the device, one copy out)
         Fh = np.asfortranarray(F, dtype=np.float64)
-        X = np.empty(Fh.shape, dtype=np.float64, order="F")
+        X = np.empty(Fh.shape, dtype=np.float64, order="F") if out is None else out   # out: a Fortran-ordered array (e.g. a view of pinned memory)
+        if X.shape != Fh.shape or not X.flags.f_contiguous or X.dtype != np.float64:
+            raise ValueError("adi_poisson: out must be a Fortran-ordered float64 array of the shape of F")
         L.check(L.lib().pop_adi_poisson_host(Mb.ctx.handle, Kb._h, Mb._h, Fh.ctypes.data, Fh.shape[0], X.ctypes.data, X.shape[0], a, b, c, d, tol, int(J)), "ADI")
         return X
     pf = _Panel(F, False)

@@ -131,3 +131,65 @@ def transform(Q: _Basis, f, p: int, kind="gauss", check=True, ctx=None):
     ctx = ctx or L.default_context()
     dev = torch.from_numpy(np.ascontiguousarray(leg)).to(f"cuda:{ctx.device}")
     return legendre_to_c1(Q, p, dev.reshape(-1, 1), L.LEFT, check, ctx)[:, 0]
+
+
+# ---- inverse transforms (`Pl \\ cfs`, src/continuouspolynomial.jl:129-146,171-184; src/dirichlet.jl:97-110,143-163) -----------
+
+def legendre_synthesis_matrix(z, p: int):
+    """S[s, a] = P_a(z_s): values on the nodes z of the reference cell = S @ Legendre coefficients (the inverse of the
+    analysis matrix of legendre_grid_transform)."""
+    return np.asfortranarray(np.polynomial.legendre.legvander(np.asarray(z, dtype=np.float64), p - 1))
+
+
+def c1_to_legendre(Q: _Basis, N: int, X, side=L.LEFT, ctx=None):
+    """Coefficients in Q's blocks 1..N-1 (columns of X for side LEFT, rows for RIGHT) -> Legendre coefficients, N degrees per
+    element in P ordering: the `Pl.R \\ dat` step of the inverse transform, i.e. the truncated conversion P \\ Q
+    (src/continuouspolynomial.jl:226-235, src/dirichlet.jl:35-53).  Inverse of legendre_to_c1."""
+    px = _Panel(X, False)
+    if not px.torch:
+        raise TypeError("c1_to_legendre works on device-resident (CUDA torch) panels")
+    nP, n = Q.m * N, Q.nh + Q.m * (N - 2)
+    if (px.rows if side == L.LEFT else px.cols) != n:
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: blocks 1..{N - 1} of the basis are {n} entries, panel is {px.rows}x{px.cols}")
+    cnt = px.cols if side == L.LEFT else px.rows
+    Y = _new_like(X, (nP, cnt) if side == L.LEFT else (cnt, nP))
+    py = _Panel(Y, True)
+    ctx = ctx or L.default_context()
+    _bind_stream(ctx)
+    L.check(L.lib().pop_c1_to_legendre(ctx.handle, Q.basis_id, Q.m, int(N), side, px.ptr, px.ld, py.ptr, py.ld, cnt), "inverse transform")
+    return Y
+
+
+def synthesis_2d(F, n: int, p: int, S, ctx=None):
+    """Inverse of analysis_2d: F[i + n a, j + n b] (tensor Legendre coefficients, CUDA torch tensor) -> values
+    vals[i p + s, j p + t] on the cell grids; S = legendre_synthesis_matrix(z, p)."""
+    pf = _Panel(F, False)
+    if not pf.torch:
+        raise TypeError("synthesis_2d works on device-resident (CUDA torch) coefficients")
+    if pf.rows != n * p or pf.cols != n * p:
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: coefficients are {pf.rows}x{pf.cols}, expected {n * p}x{n * p}")
+    S = np.asfortranarray(np.asarray(S, dtype=np.float64))
+    if S.shape != (p, p):
+        raise L.DimensionMismatch(-2, f"DimensionMismatch: synthesis matrix is {S.shape}, expected {(p, p)}")
+    ctx = ctx or L.default_context()
+    V = _new_like(F, (n * p, n * p))
+    pv = _Panel(V, True)
+    _bind_stream(ctx)
+    L.check(L.lib().pop_legendre_synthesis_2d(ctx.handle, int(n), int(p), S.ctypes.data_as(C.c_void_p), pf.ptr, pf.ld, pv.ptr, pv.ld), "synthesis_2D")
+    return V
+
+
+def itransform_2d(Q: _Basis, Cf, p: int, S, ctx=None):
+    """plan_grid_transform(Q, Block(p-1, p-1)) \\ Cf (src/continuouspolynomial.jl:171-184, test_continuouspolynomial.jl:33
+    `F \\ V ≈ vals`): coefficients in Q (x) Q -> values on the p x p tensor grid of every cell."""
+    return synthesis_2d(c1_to_legendre(Q, p, c1_to_legendre(Q, p, Cf, L.LEFT, ctx), L.RIGHT, ctx), Q.m, p, S, ctx)
+
+
+def itransform(Q: _Basis, c, p: int, kind="gauss", ctx=None):
+    """plan_grid_transform(Q, Block(p-1)) \\ c for one vector of coefficients (src/continuouspolynomial.jl:129-146,
+    test_continuouspolynomial.jl:19,26): the device conversion to Legendre coefficients, then the O(m p^2) synthesis on
+    the p nodes of every cell on the host (as `transform` does the analysis).  Returns (x, values) as NumPy arrays."""
+    z, _ = legendre_grid_transform(p, kind)
+    leg = c1_to_legendre(Q, p, c.reshape(-1, 1), L.LEFT, ctx)[:, 0].cpu().numpy().reshape(p, Q.m)      # [degree, cell]
+    vals = (legendre_synthesis_matrix(z, p) @ leg).T.reshape(-1)                                    # node s of cell k at k p + s
+    return cell_grid(Q.points, z), vals

@@ -304,3 +304,151 @@ def test_theta_scheme_two_dimensions():
         U = _dev(torch, U0)
         P.heat_steps(M, K, U, 1e-2, 6, dims=2, theta=theta)
         assert relerr(U.cpu().numpy(), want) < 1e-11, theta
+
+
+# ------------------------------------------------------------------------------------------------ inverse transforms
+@pytest.mark.parametrize("basis", [O.C1, O.DIRICHLET])
+def test_inverse_transform_oracle_round_trip_and_pointwise(basis):
+    """`F \\ (F * vals) ≈ vals` (test/test_continuouspolynomial.jl:19,26; test_dirichlet.jl:70) for the oracle's restatement of
+    `Pl \\ cfs` (src/continuouspolynomial.jl:129-146): conversion to Legendre coefficients + synthesis; the synthesised
+    values are the expansion evaluated at the nodes (independent evaluation through basis_eval_matrix)."""
+    m, p = 5, 9
+    r = np.linspace(-1, 1, m + 1)
+    nh = m + 1 if basis == O.C1 else m - 1
+    n = nh + m * (p - 2)
+    rng = np.random.default_rng(11)
+    c = rng.standard_normal((n, 3))
+    leg = O.legendre_from_c1(basis, m, p, c)                              # [degree a of element k at a m + k]
+    assert relerr(O.c1_from_legendre(basis, m, p, leg), c) < 1e-12        # F * (F \ c) = c
+    z, T = O.legendre_grid_transform(p)
+    S = np.polynomial.legendre.legvander(z, p - 1)
+    assert np.allclose(S @ T, np.eye(p), atol=1e-13)
+    x = ((r[:-1] + r[1:])[:, None] / 2 + np.diff(r)[:, None] / 2 * z[None, :]).reshape(-1)
+    vals = np.einsum("sa,akc->ksc", S, leg.reshape(p, m, 3)).reshape(m * p, 3)
+    E = O.basis_eval_matrix(basis, r, p - 1, x)                           # blocks 1..p-1 of the basis: hats and W_2..W_{p-1}
+    assert E.shape[1] == n
+    assert relerr(vals, E @ c) < 1e-12
+
+
+def test_synthesis_2d_oracle_inverts_analysis_2d():
+    n, p = 3, 7
+    z, T = O.legendre_grid_transform(p)
+    S = np.polynomial.legendre.legvander(z, p - 1)
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((n * p, n * p))
+    assert relerr(O.synthesis_2d(O.analysis_2d(V, n, p, T), n, p, S), V) < 1e-12
+
+
+@pytest.mark.parametrize("basis", [O.C1, O.DIRICHLET])
+def test_variable_coefficient_laplacian_closed_form_matches_quadrature(basis):
+    """-(D*C)' * (a .* (D*C)) of examples/heat.jl:77-79 for a piecewise-constant a: element integrals scaled by a_k."""
+    m, N = 6, 7
+    rng = np.random.default_rng(2)
+    hk = 0.2 + rng.random(m)
+    a = 0.5 + rng.random(m)
+    Lp = O.assemble_weaklaplacian(basis, m, N, hk, a=a)
+    Ld = O.unpack(O.packed_symmetrize(Lp)).to_dense()
+    _, Lq = O.quadrature_matrices(basis, m, N, hk, a=a)
+    assert np.abs(Ld - Lq).max() < 1e-12 * np.abs(Lq).max()
+    # a = 1 is the plain weak Laplacian
+    L1 = O.unpack(O.packed_symmetrize(O.assemble_weaklaplacian(basis, m, N, hk, a=np.ones(m)))).to_dense()
+    L0 = O.unpack(O.packed_symmetrize(O.assemble_weaklaplacian(basis, m, N, hk))).to_dense()
+    assert np.array_equal(L1, L0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis", ["c1", "dirichlet"])
+@pytest.mark.parametrize("m,N", [(2, 2), (3, 3), (4, 7), (9, 11), (33, 40)])
+def test_c1_to_legendre_kernel_vs_oracle(basis, m, N):
+    torch, P = _gpu()
+    bo = O.C1 if basis == "c1" else O.DIRICHLET
+    Q = P.ContinuousPolynomial(1, np.linspace(0, 1, m + 1)) if basis == "c1" else P.DirichletPolynomial(np.linspace(0, 1, m + 1))
+    n = Q.nh + m * (N - 2)
+    rng = np.random.default_rng(3 * m + N)
+    c = rng.standard_normal((n, 5))
+    want = O.legendre_from_c1(bo, m, N, c)
+    got = P.c1_to_legendre(Q, N, _dev(torch, c), P.LEFT)
+    assert relerr(got.cpu().numpy(), want) < TOL
+    gotr = P.c1_to_legendre(Q, N, _dev(torch, c.T.copy()), P.RIGHT)
+    assert relerr(gotr.cpu().numpy(), want.T) < TOL
+    # the two conversions are inverses of each other (F * (F \ c) = c)
+    back = P.legendre_to_c1(Q, N, got, P.LEFT)
+    assert relerr(back.cpu().numpy(), c) < TOL
+    with pytest.raises(P.DimensionMismatch):
+        P.c1_to_legendre(Q, N + 1, _dev(torch, c), P.LEFT)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 5), (3, 16), (7, 33), (2, 64), (5, 62)])
+def test_synthesis_2d_kernel_vs_oracle(n, p):
+    torch, P = _gpu()
+    z, T = P.legendre_grid_transform(p)
+    S = P.legendre_synthesis_matrix(z, p)
+    rng = np.random.default_rng(p + n)
+    F = rng.standard_normal((n * p, n * p))
+    got = P.synthesis_2d(_dev(torch, F), n, p, S).cpu().numpy()
+    assert relerr(got, O.synthesis_2d(F, n, p, S)) < TOL
+    # F \ (F * vals) ≈ vals on the device (test_continuouspolynomial.jl:33)
+    V = rng.standard_normal((n * p, n * p))
+    back = P.synthesis_2d(P.analysis_2d(_dev(torch, V), n, p, T), n, p, S).cpu().numpy()
+    assert relerr(back, V) < 1e-11
+
+
+@pytest.mark.gpu
+def test_inverse_transforms_like_the_reference_tests():
+    """test_continuouspolynomial.jl:19-33 and test_dirichlet.jl:70: `F \\ (F * exp.(g)) ≈ exp.(g)` in one dimension and
+    `F \\ V ≈ vals` for f(x,y) = exp(x cos(y)) in two."""
+    torch, P = _gpu()
+    r = np.linspace(-1, 1, 10)
+    C1 = P.ContinuousPolynomial(1, r)
+    p = 11
+    c = P.transform(C1, np.exp, p)
+    x, vals = P.itransform(C1, c, p)
+    assert relerr(vals, np.exp(x)) < 1e-12
+    z, T = P.legendre_grid_transform(p)
+    S = P.legendre_synthesis_matrix(z, p)
+    xg = P.cell_grid(r, z)
+    v2 = np.exp(xg[:, None] * np.cos(xg[None, :]))
+    V = P.transform_2d(C1, _dev(torch, v2), p, T)
+    back = P.itransform_2d(C1, V, p, S).cpu().numpy()
+    assert relerr(back, v2) < 1e-11
+    # Dirichlet basis: a field that vanishes on the boundary
+    Q = P.DirichletPolynomial(r)
+    w2 = np.outer((1 - xg ** 2) * np.exp(xg), (1 - xg ** 2) * np.cos(xg))
+    W = P.transform_2d(Q, _dev(torch, w2), p, T)
+    assert relerr(P.itransform_2d(Q, W, p, S).cpu().numpy(), w2) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis", ["c1", "dirichlet"])
+def test_variable_coefficient_heat(basis):
+    """examples/heat.jl:77-83 with a piecewise-constant a (0.5 on the middle third, 1 elsewhere, as in the example): the
+    operator against the oracle's closed form and Gauss quadrature, then theta-scheme steps against the dense oracle (the
+    reference integrates this operator with an ODE solver, which stays out of scope)."""
+    torch, P = _gpu()
+    bo = O.C1 if basis == "c1" else O.DIRICHLET
+    m, N = 9, 12
+    r = np.linspace(-1, 1, m + 1)
+    Q = P.ContinuousPolynomial(1, r) if basis == "c1" else P.DirichletPolynomial(r)
+    mid = (r[:-1] + r[1:]) / 2
+    a = np.where(np.abs(mid) <= 1 / 3, 0.5, 1.0)
+    KR = P.Block.oneto(N)
+    Lv = P.weaklaplacian(Q, a=a)[KR, KR]
+    M = P.grammatrix(Q)[KR, KR]
+    hk = np.diff(r)
+    Lo = O.unpack(O.packed_symmetrize(O.assemble_weaklaplacian(bo, m, N, hk, a=a))).to_dense()
+    _, Lq = O.quadrature_matrices(bo, m, N, hk, a=a)
+    assert np.abs(Lv.to_dense() - Lo).max() < 1e-13 * np.abs(Lo).max()
+    assert np.abs(Lv.to_dense() - Lq).max() < 1e-12 * np.abs(Lq).max()
+    Md = M.to_dense()
+    n = Md.shape[0]
+    rng = np.random.default_rng(8)
+    u0 = rng.standard_normal(n)
+    for theta, steps in ((1.0, 20), (0.5, 20)):
+        U = _dev(torch, u0.reshape(-1, 1).copy())
+        P.heat_steps(M, -Lv, U, 1e-3, steps, theta=theta)
+        want = O.heat_theta_dense(Md, -Lo, u0, 1e-3, theta, steps)
+        assert relerr(U[:, 0].cpu().numpy(), want) < 1e-11, theta
+    # M + dt (-L_a) combines lazily as well
+    S = (P.grammatrix(Q) - 1e-3 * P.weaklaplacian(Q, a=a))[KR, KR]
+    assert np.abs(S.to_dense() - (Md - 1e-3 * Lo)).max() < 1e-13 * np.abs(Md).max()
