@@ -42,16 +42,16 @@ struct F2Plan {
     F2Params p;
 };
 
-static f2_kernel_t f2_kernel(int rows, int npar, int variant, bool mul) {
+static f2_kernel_t f2_kernel(int rows, int npar, int variant, bool mul, bool cl) {
     switch (rows) {
-        case 8: return f2_kernel_r8(npar, variant, mul);
-        case 16: return f2_kernel_r16(npar, variant, mul);
-        case 24: return f2_kernel_r24(npar, variant, mul);
-        case 32: return f2_kernel_r32(npar, variant, mul);
-        case 40: return f2_kernel_r40(npar, variant, mul);
-        case 48: return f2_kernel_r48(npar, variant, mul);
-        case 56: return f2_kernel_r56(npar, variant, mul);
-        case 64: return f2_kernel_r64(npar, variant, mul);
+        case 8: return f2_kernel_r8(npar, variant, mul, cl);
+        case 16: return f2_kernel_r16(npar, variant, mul, cl);
+        case 24: return f2_kernel_r24(npar, variant, mul, cl);
+        case 32: return f2_kernel_r32(npar, variant, mul, cl);
+        case 40: return f2_kernel_r40(npar, variant, mul, cl);
+        case 48: return f2_kernel_r48(npar, variant, mul, cl);
+        case 56: return f2_kernel_r56(npar, variant, mul, cl);
+        case 64: return f2_kernel_r64(npar, variant, mul, cl);
     }
     return nullptr;
 }
@@ -74,6 +74,7 @@ static int f2_num_regs(const void *kern) {
     return fa.numRegs;
 }
 
+static inline int hB_of_cs1(const pop_desc &d) { return d.nh; }   // a single CTA owns every hat of the column
 static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead *T, bool gamma_nonzero = false) {
     F2Plan pl = {};
     const pop_desc &d = U->d;
@@ -109,11 +110,7 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
     if (const char *e = getenv("POP_F2_OCC")) force_occ = atoi(e);
     if (const char *e = getenv("POP_F2_NF")) force_nf = atoi(e);
     const size_t limit = (size_t)ctx->max_smem_optin;
-    pl.kern = f2_kernel(pl.rows, pl.npar, pl.variant, T != nullptr);
-    if (!pl.kern) return pl;
     struct { int numRegs; } fa;
-    fa.numRegs = f2_num_regs((const void *)pl.kern);
-    if (fa.numRegs <= 0) return pl;
     F2Plan first = {};
     for (int cs = 1; cs <= 8; cs *= 2) {
         if (T && cs > 1) break;
@@ -125,6 +122,10 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         const int threads = ncE * pl.npar;
         if (threads > maxthreads) continue;
         if (cs > 1 && (d.m & 1)) continue;   // row parities would alternate inside a CTA's slab
+        pl.kern = f2_kernel(pl.rows, pl.npar, pl.variant, T != nullptr, cs > 1);   // single-CTA columns: the kernel without the cluster code
+        if (!pl.kern) continue;
+        fa.numRegs = f2_num_regs((const void *)pl.kern);
+        if (fa.numRegs <= 0) continue;
         F2Params &p = pl.p;
         p.cs = cs; p.mloc = mloc; p.ncE = ncE;
         p.contiguous = cs == 1 ? 1 : 0;
@@ -147,6 +148,8 @@ static F2Plan plan_f2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead 
         p.o_inb = o; o += F2_INB_SIZE;
         p.o_wagg = o; o += F2_WAGG;
         p.o_hw = o; o += cs > 1 ? 2 * p.hcap : 0;
+        p.hat_L = (std::max(hB_of_cs1(d), 1) + 31) / 32;
+        p.o_kst = o; o += (cs == 1 && !F2_OLD_SCAN) ? (10 + 3 * p.hat_L) * 32 : 0;
         o = (o + 15) & ~15;
         p.o_ring = o;
         const size_t fixed = F2_BAR_BYTES + (size_t)o * 8;

@@ -36,18 +36,19 @@ struct F2Params {
     int stagger_ns;        // start-up offset between clusters (de-phases the clusters' memory bursts)
     int cs, mloc, rp, nch, nslots, slot_stride, ncE, contiguous, hcap, nf;   // nf: slots of the F ring (fused product)
     int o_tab, o_tab1, o_tT, o_hrd, o_hoff, o_H, o_ct, o_xb, o_inb, o_wagg, o_hw, o_ring, o_fring;   // offsets in doubles
+    int o_kst, hat_L;      // single-CTA columns: tables of the one-warp hat scan, [10][32] step multipliers + cd, cu, rd as [hat_L][32]
 };
 
 typedef void (*f2_kernel_t)(const F2Params);
 // variant: 0 -> no D coupling, 1 -> second super-diagonal only (even/odd chains decoupled), 2 -> general (<= 2 bands)
-f2_kernel_t f2_kernel_r8(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r16(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r24(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r32(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r40(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r48(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r56(int npar, int variant, bool mul);
-f2_kernel_t f2_kernel_r64(int npar, int variant, bool mul);
+f2_kernel_t f2_kernel_r8(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r16(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r24(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r32(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r40(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r48(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r56(int npar, int variant, bool mul, bool cl);
+f2_kernel_t f2_kernel_r64(int npar, int variant, bool mul, bool cl);
 // largest block of a row class (registers: the chain of an element lives in 2*ROWS registers)
 __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : rows <= 48 ? 384 : 256; }
 
@@ -80,6 +81,11 @@ __host__ __device__ constexpr int f2_tmax(int rows) { return rows <= 40 ? 512 : 
 #define F2_STORE(p, v) (*(p) = (v))
 #endif
 #define F2_SCAN_WARPS 4   // warps that run the hat scans (the others wait at the block barrier)
+#ifndef F2_OLD_SCAN
+#define F2_OLD_SCAN 1     // 0: single-CTA columns solve their hats on ONE warp (Kogge-Stone over the lanes with tabulated multipliers, as k_row2 does);
+                          // measured equal (0.314 ms per half step, 70.0 / 12.1 ms per ADI solve at the 1- / 8-GPU shapes) and parity-green: the hat
+                          // stage of a column is covered by the other resident CTA, so the generic segmented scan stays
+#endif
 // Pass 1 + composition over the scan warps: thread-local map (t, Pm), then (at, aP) = composite of the scan warps
 // from this lane's warp on (lanes < nsw hold warp `lane`'s suffix / prefix composite).
 template <bool BW>
@@ -228,8 +234,12 @@ __device__ __forceinline__ void f2_issue_fchunk(const F2Params &P, uint64_t *ffu
         tma_load_1d(fring + (size_t)slot * P.slot_stride, fcol + a0, bytes, ffull + slot);
 }
 
-template <int ROWS, int NPAR, int ND, bool SKIP1, bool MUL>
+// CL: the kernel may run as a thread-block cluster (a column spread over cs CTAs).  Columns that fit one CTA get a kernel of
+// their own without the cluster set-up, mailboxes and segment-map exchange: a third less SASS to stream through the
+// instruction cache per column (profiles/r2_fused2_dd8_ncu.txt: no_instruction is the top stall of the short ADI panels).
+template <int ROWS, int NPAR, int ND, bool SKIP1, bool MUL, bool CL>
 __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_constant__ F2Params P) {
+    static_assert(!(MUL && CL), "the fused product runs on single-CTA columns");
     static_assert(NPAR == 1 || (ND != 1 && (ND == 0 || SKIP1)), "the even/odd split needs decoupled chains");
     static_assert(!(MUL && NPAR == 2 && !(ND == 0 || SKIP1)), "fused product with split chains: T must not couple j and j+1");
     static_assert(ROWS % F2_G == 0, "row classes are multiples of the chunk height");
@@ -257,10 +267,11 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     double *hwd = sm + P.o_hw, *hwu = hwd + P.hcap;   // cs > 1: weights of the segment maps (see the set-up below)
     double *ring = sm + P.o_ring;
     double *fring = sm + P.o_fring;
+    double *kst = sm + P.o_kst;   // CL == false only
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
-    const int cs = P.cs;
+    const int cs = CL ? P.cs : 1;
     const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
     const int m = P.m, nh = P.nh, q = P.q, nb = P.nb;
     const int ncE = P.ncE;
@@ -308,11 +319,42 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         hoffl[u] = (i >= 1 && i < nh) ? P.offA[i - 1] : 0.0;
     }
     // the hat scans run on the first nsw warps: scan thread t owns hats [lo,hi)
-    const int nsw = min(nw, F2_SCAN_WARPS);
+    constexpr bool KSCAN = !CL && !F2_OLD_SCAN;          // single-CTA columns: one warp solves the hats (tables below)
+    const int nsw = KSCAN ? 1 : min(nw, F2_SCAN_WARPS);
     const int nst = nsw * 32;
     const int sg = (nhl + nst - 1) / nst;
     const int lo = tid < nst ? min(tid * sg, nhl) : 0, hi = tid < nst ? min(lo + sg, nhl) : 0;
     __syncthreads();
+    if (KSCAN && warp == 0) {
+        // One-warp hat solve of a single-CTA column: lane l owns the hats [l L, (l+1) L).  Both bidiagonal recurrences
+        //   y_i = H_i rd_i - cd_i y_{i+1},  cd_i = off(i,i+1) rd_i      (src/arrowhead.jl:453)
+        //   h_i = y_i rd_i - cu_i h_{i-1},  cu_i = off(i-1,i) rd_i      (src/arrowhead.jl:472)
+        // are affine in the incoming value with multipliers that depend on the factor only: they are tabulated here, together
+        // with the products the Kogge-Stone steps over the lanes need (zero where a step has no partner).
+        const int L = P.hat_L;
+        double ad = 1.0, au = 1.0;
+        for (int i = 0; i < L; ++i) {
+            const int u = lane * L + i;
+            const bool in = u < nhl;
+            const double rdv = in ? hrd[u] : 0.0, cdv = in ? hoffl[u + 1] * rdv : 0.0, cuv = in ? hoffl[u] * rdv : 0.0;
+            kst[(10 + i) * 32 + lane] = cdv;
+            kst[(10 + L + i) * 32 + lane] = cuv;
+            kst[(10 + 2 * L + i) * 32 + lane] = rdv;
+            ad *= -cdv;
+            au *= -cuv;
+        }
+#pragma unroll 1
+        for (int st = 0; st < 5; ++st) {
+            double pd = 1.0, pu = 1.0;
+#pragma unroll 1
+            for (int j = 0; j < (1 << st); ++j) {
+                pd *= __shfl_sync(POP_FULL_MASK, ad, (lane + j) & 31);
+                pu *= __shfl_sync(POP_FULL_MASK, au, (lane - j) & 31);
+            }
+            kst[st * 32 + lane] = (lane + (1 << st) < 32) ? pd : 0.0;
+            kst[(5 + st) * 32 + lane] = (lane >= (1 << st)) ? pu : 0.0;
+        }
+    }
     if (cs > 1) {
         // multipliers of every rank's segment map (constants of the factor), shared through DSMEM
         double pd = 1.0, pu = 1.0;
@@ -595,7 +637,39 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
                 for (int c = iw; c < NCH; c += nissue) f2_issue_chunk(P, full, ring, lane, k0, ml, xcol + colstep, c, c);
         }
         F2_TICK(3)   // refill issue
-        if (warp < nsw) {
+        if (KSCAN) {
+            if (warp == 0) {
+                const int L = P.hat_L;
+                double *hp = Hs + lane * L;
+                const int nown = min(max(nhl - lane * L, 0), L);   // my hats that exist
+                const double *cdT = kst + 10 * 32 + lane, *cuT = cdT + L * 32, *rdT = cuT + L * 32;
+                double t = 0.0;
+                for (int i = nown - 1; i >= 0; --i) t = fma(-cdT[i * 32], t, hp[i] * rdT[i * 32]);
+#pragma unroll
+                for (int st = 0; st < 5; ++st) t = fma(kst[st * 32 + lane], __shfl_down_sync(POP_FULL_MASK, t, 1 << st), t);
+                double hin = __shfl_down_sync(POP_FULL_MASK, t, 1);
+                if (lane == 31) hin = 0.0;
+                for (int i = nown - 1; i >= 0; --i) {
+                    hin = fma(-cdT[i * 32], hin, hp[i] * rdT[i * 32]);
+                    hp[i] = hin;
+                }
+                t = 0.0;
+                for (int i = 0; i < nown; ++i) t = fma(-cuT[i * 32], t, hp[i] * rdT[i * 32]);
+#pragma unroll
+                for (int st = 0; st < 5; ++st) t = fma(kst[(5 + st) * 32 + lane], __shfl_up_sync(POP_FULL_MASK, t, 1 << st), t);
+                double xin = __shfl_up_sync(POP_FULL_MASK, t, 1);
+                if (lane == 0) xin = 0.0;
+                for (int i = 0; i < nown; ++i) {
+                    xin = fma(-cuT[i * 32], xin, hp[i] * rdT[i * 32]);
+                    hp[i] = xin;
+                }
+                if (lane == 0) {   // no neighbours: the hats next to the column's range are zero
+                    Hs[-1] = 0.0;
+                    Hs[nhl] = 0.0;
+                    Hs[nhl + 1] = 0.0;
+                }
+            }
+        } else if (warp < nsw) {
             double hl, t, Pm, at, aP, Gdn = 0.0, Gup = 0.0, Td = 0.0;
             double *ibc = inb + F2_INB_B + hb * 16;   // [rank][down, up]
             if (cs > 1) {
@@ -790,16 +864,18 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
 }
 
 // one translation unit per row class: NPAR = 1 for every class, NPAR = 2 (q up to 128) for 40..64
+template <int ROWS, int NPAR, int ND, bool SKIP1>
+static f2_kernel_t f2_pick3(bool mul, bool cl) {
+    if (mul) return cl ? nullptr : k_fused2<ROWS, NPAR, ND, SKIP1, true, false>;
+    return cl ? k_fused2<ROWS, NPAR, ND, SKIP1, false, true> : k_fused2<ROWS, NPAR, ND, SKIP1, false, false>;
+}
 template <int ROWS>
-static f2_kernel_t f2_pick(int npar, int variant, bool mul) {
-    if (npar == 2) {
-        if (variant == 0) return mul ? k_fused2<ROWS, 2, 0, false, true> : k_fused2<ROWS, 2, 0, false, false>;
-        return mul ? k_fused2<ROWS, 2, 2, true, true> : k_fused2<ROWS, 2, 2, true, false>;
-    }
-    if (variant == 0) return mul ? k_fused2<ROWS, 1, 0, false, true> : k_fused2<ROWS, 1, 0, false, false>;
-    if (variant == 1) return mul ? k_fused2<ROWS, 1, 2, true, true> : k_fused2<ROWS, 1, 2, true, false>;
-    return mul ? k_fused2<ROWS, 1, 2, false, true> : k_fused2<ROWS, 1, 2, false, false>;
+static f2_kernel_t f2_pick(int npar, int variant, bool mul, bool cl) {
+    if (npar == 2) return variant == 0 ? f2_pick3<ROWS, 2, 0, false>(mul, cl) : f2_pick3<ROWS, 2, 2, true>(mul, cl);
+    if (variant == 0) return f2_pick3<ROWS, 1, 0, false>(mul, cl);
+    if (variant == 1) return f2_pick3<ROWS, 1, 2, true>(mul, cl);
+    return f2_pick3<ROWS, 1, 2, false>(mul, cl);
 }
 #define F2_DEFINE_CLASS(ROWS) \
-    f2_kernel_t f2_kernel_r##ROWS(int npar, int variant, bool mul) { return f2_pick<ROWS>(npar, variant, mul); }
+    f2_kernel_t f2_kernel_r##ROWS(int npar, int variant, bool mul, bool cl) { return f2_pick<ROWS>(npar, variant, mul, cl); }
 #endif  // __CUDACC__

@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         }
         // step st of the suffix scan multiplies what comes from lane l + 2^st by the product of the multipliers of the lanes
         // [l, l + 2^st); the prefix scan (upward recurrence) mirrors it
+#pragma unroll 1
         for (int st = 0; st < 5; ++st) {
             double pd = 1.0, pu = 1.0;
+#pragma unroll 1
             for (int j = 0; j < (1 << st); ++j) {
                 pd *= __shfl_sync(POP_FULL_MASK, ad, (lane + j) & 31);
                 pu *= __shfl_sync(POP_FULL_MASK, au, (lane - j) & 31);
@@ -1097,7 +1099,8 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
                      r2_align(2 * cs * P.mbw * 8, 128);
     (void)want_cs;
     // degrees per chunk (TMA box, region of the row block buffer): 4 keeps the hand-over between the blocks fine-grained
-    const int dc = r2_env("POP_ROW2_DC", 4) == 8 ? 8 : 4;
+    // (16-row blocks of the remote mode: 8, measured 12.50 -> 12.22 ms per ADI solve at the 8-GPU shape; 8-row blocks: 4, 8 costs 3-7 %)
+    const int dc = r2_env("POP_ROW2_DC", (rem && rb == 16) ? 8 : 4) == 8 ? 8 : 4;
     const int nch = (op.q + dc - 1) / dc;
     const R2Fixed LF = r2_fixed(ch, dc, mlc, rb);
     if (LF.ring + tail > ctx->max_smem_optin) return unsupported("shared memory too small for the row block");
