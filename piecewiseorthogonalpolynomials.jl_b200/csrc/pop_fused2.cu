@@ -244,13 +244,20 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
     cfg.blockDim = dim3(pl.threads);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = p.cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // set-up under the tail of the previous kernel (pdl_wait in the kernel)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char *e = getenv("POP_PDL");
+        use_pdl = e ? atoi(e) : 0;   // measured slower with it (profiles/r2_pdl.txt): off by default
+    }
+    cfg.numAttrs = 1;   // the occupancy query below wants the cluster attribute alone
     if (p.cs > 1) {
         // persistent clusters: never launch more than can be resident at once (GPC boundaries strand a few
         // SMs for cluster sizes that do not divide the GPC), a second wave would serialise whole columns
@@ -279,6 +286,7 @@ int pop_launch_solve_fused2(pop_ctx *ctx, const pop_arrowhead *U, const pop_arro
     cudaMemsetAsync(prof, 0, 32 * 8, ctx->stream);
     p.prof = prof;
 #endif
+    cfg.numAttrs = use_pdl ? 2 : 1;
     POP_CUDA(cudaLaunchKernelEx(&cfg, pl.kern, p));
     ctx->launches++;
 #ifdef F2_PROF

@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
     const int64_t colstep = (int64_t)ncl * P.ldx;
 
     // ---- one-time setup ----------------------------------------------------------------------
+    pdl_launch_dependents();   // the next kernel may set itself up while this one drains
     if (tid == 0) {
         for (int s = 0; s < nslots; ++s) mbar_init(full + s, 1);
         if (MUL)
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(f2_tmax(ROWS), 1) k_fused2(const __grid_consta
         cluster_arrive();
         cluster_wait();
     }
+    pdl_wait();   // everything above read the factor only; the panel (and F) belong to the previous kernel until here
     if (P.stagger_ns > 0) {
         // clusters would otherwise run in phase (same work, same start): all loading, then all in the hat
         // scans, then all storing.  Offsetting their starts spreads the HBM traffic over the column period.

@@ -104,6 +104,12 @@ __device__ __forceinline__ void st_cluster_f64(uint32_t dst_cluster_addr, double
 __device__ __forceinline__ void stg_na_f64(double *p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// Programmatic dependent launch (no-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// launch_dependents lets the NEXT kernel of the stream start its CTAs as soon as SM resources free up, wait blocks until the
+// PREVIOUS kernel has completed and its writes are visible.  A kernel may run its set-up (tables of the factor into shared
+// memory, barrier initialisation) in front of the wait, under the tail of its predecessor.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
     const bool producer = tid >= nthr;   // set-up: everybody but the compute threads idles
 
     // ---- one-time set-up ------------------------------------------------------------------------------
+    pdl_launch_dependents();   // the next kernel may set itself up while this one drains
     if (tid == 0) {
         mbar_init(barH, 1);
         mbar_init(barH + 1, 1);
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
         cluster_arrive();
         cluster_wait();
     }
+    pdl_wait();   // the set-up above read the factor only; panel, F and mailboxes belong to the previous kernel until here
 
     // row blocks of this cluster: block t is number bbase + t * bstride.  With pairing, two clusters walk through
     // neighbouring row blocks side by side, so that both 64 B halves of every 128 B line are requested within
@@ -1153,16 +1155,18 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     if (!kern) return unsupported("no kernel for this chain class");
     POP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.total));
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // set-up under the tail of the previous kernel (pdl_wait in the kernel)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.blockDim = dim3(640);   // 512 compute slots (16 mlc of them work) + the TMA producer warp group
     cfg.dynamicSmemBytes = (size_t)P.total;
     cfg.stream = ctx->stream;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1;   // the occupancy query wants the cluster attribute alone
     static std::mutex plan_mu;
     static int cached_key[5] = {0, 0, 0, 0, -1}, cached_ncl = 0;
     const int key[5] = {ch * 16 + dc + (mlc == 32 ? 1024 : 0) + (rem ? 4096 : 0) + (rb == 16 ? 8192 : 0), rem ? rem->csv : cs, nthr, P.total, ctx->device};
@@ -1206,6 +1210,7 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
         POP_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
         P.dbg = dbg;
     }
+    cfg.numAttrs = r2_env("POP_PDL", 0) ? 2 : 1;   // measured: programmatic dependent launch costs 5 % here (70.1 -> 74.2 ms, 12.1 -> 12.7 ms per ADI solve): off
     POP_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     ctx->launches++;
     if (dbg) {   // debugging aid: phase durations of CTA 0 in SM clock cycles
