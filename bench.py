@@ -598,18 +598,25 @@ def main():
     if not args.no_e2e:
         ksteps = min(args.steps, 5)
 
-        def host_loop(hB, hX, k):
-            Xh = hX.numpy().T                                 # Fortran-ordered (n x nrhs) view
+        def host_loop(hB, hX, k, inplace):
+            Bh, Xh = hB.numpy().T, hX.numpy().T                  # Fortran-ordered (n x nrhs) views
             hX.copy_(hB)
-            P.ldiv(F, Xh, overwrite=True)                     # warm-up
+            if inplace:
+                P.ldiv(F, Xh, overwrite=True)                    # warm-up
+            else:
+                P.ldiv(F, Bh, out=Xh)
             te = 0.0
             for _ in range(k):
-                hX.copy_(hB)
+                if inplace:
+                    hX.copy_(hB)                                 # untimed restore of the right-hand sides
                 if world > 1:
                     dist.barrier()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                P.ldiv(F, Xh, overwrite=True)                 # pop_solve_host: returns after the D2H copy
+                if inplace:
+                    P.ldiv(F, Xh, overwrite=True)                # ldiv!(F, X): pop_solve_host, returns after the D2H copy
+                else:
+                    P.ldiv(F, Bh, out=Xh)                        # X = F \ B: pop_solve_host_to
                 te += time.perf_counter() - t0
             tte = torch.tensor([te], dtype=torch.float64, device=dev)
             if world > 1:
@@ -618,12 +625,16 @@ def main():
 
         hB = torch.randn((nrhs, n), dtype=torch.float64).pin_memory()
         hX = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
-        e2e = {"value": host_loop(hB, hX, ksteps), "unit": UNIT, "h2d_bytes_per_step": n * nrhs * 8,
-               "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps, "api": "pop_solve_host (ldiv(F, numpy array)), pinned host panel, flat address-aligned 32 MiB blocks H2D / compute / D2H overlapped"}
+        # the headline end-to-end number is the reference's own call shape `X = F \ B` (test/test_arrowhead.jl:130): right-hand sides
+        # in one pinned host panel, the solution into another; the in-place ldiv! of the same panel is reported beside it
+        e2e = {"value": host_loop(hB, hX, ksteps, False), "unit": UNIT, "h2d_bytes_per_step": n * nrhs * 8,
+               "d2h_bytes_per_step": n * nrhs * 8, "steps": ksteps,
+               "api": "pop_solve_host_to (X = ldiv(F, B, out=X) on NumPy arrays), pinned host panels, flat address-aligned 32 MiB blocks H2D / compute / D2H overlapped"}
+        e2e["inplace"] = {"value": host_loop(hB, hX, ksteps, True), "unit": UNIT, "note": "ldiv!(F, X) on one pinned panel (pop_solve_host): both directions of the link share the host buffer"}
         # the same call on PAGEABLE host memory (what a Julia Array or a plain NumPy array is)
         try:
             hXp = torch.empty((nrhs, n), dtype=torch.float64)
-            e2e["pageable"] = {"value": host_loop(hB, hXp, min(ksteps, 3)), "unit": UNIT, "note": "same call, host panel in ordinary (pageable) memory: worker threads stage it through pinned pieces (csrc/pop_host.cu StagedXfer)"}
+            e2e["pageable"] = {"value": host_loop(hB, hXp, min(ksteps, 3), True), "unit": UNIT, "note": "ldiv!(F, X), host panel in ordinary (pageable) memory: worker threads stage it through pinned pieces (csrc/pop_host.cu StagedXfer)"}
             del hXp
         except Exception as ex:
             e2e["pageable"] = {"error": f"{type(ex).__name__}: {ex}"}

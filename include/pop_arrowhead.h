@@ -184,6 +184,10 @@ int pop_solve(pop_ctx *ctx, const pop_arrowhead *U, int side, double *dX, int64_
               int64_t nrhs, int algo);
 int pop_solve_host(pop_ctx *ctx, const pop_arrowhead *U, int side, double *X, int64_t ldx,
                    int64_t nrhs, int algo);
+/* `Y = F \ X` / `Y = X / F` with X left untouched (what the reference's allocating `\` does; pop_solve_host is `ldiv!`):
+ * the two directions of the host link work on different buffers.  Y may be X. */
+int pop_solve_host_to(pop_ctx *ctx, const pop_arrowhead *U, int side, const double *X, int64_t ldx, double *Y,
+                      int64_t ldy, int64_t nrhs, int algo);
 /* nshift systems, shift i acting on the panel dX + i*stride_shift (BASELINE config 3) */
 int pop_solve_shift_batch(pop_ctx *ctx, pop_arrowhead *const *U, int nshift, double *dX,
                           int64_t ldx, int64_t stride_shift, int64_t nrhs, int algo);

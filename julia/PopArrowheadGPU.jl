@@ -199,6 +199,20 @@ function LinearAlgebra.rdiv!(X::StridedMatrix{Float64}, F::RevCholArrowhead)
         ctx(), h.ptr, POP_RIGHT, X, stride(X, 2), size(X, 1), 0), "rdiv!")
     X
 end
+# `F \ X` and `X / F` allocate their result in the reference; bound directly (instead of copy + ldiv!) the library reads X and
+# writes the new matrix, so the two directions of the host link work on different buffers
+function Base.:\(F::RevCholArrowhead, X::StridedMatrix{Float64})
+    Y = similar(X)
+    GC.@preserve X Y check(ccall((:pop_solve_host_to, libpop), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Cint),
+        ctx(), factor_handle(F).ptr, POP_LEFT, X, stride(X, 2), Y, stride(Y, 2), size(X, 2), 0), "\\")
+    Y
+end
+function Base.:/(X::StridedMatrix{Float64}, F::RevCholArrowhead)
+    Y = similar(X)
+    GC.@preserve X Y check(ccall((:pop_solve_host_to, libpop), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Cint),
+        ctx(), factor_handle(F).ptr, POP_RIGHT, X, stride(X, 2), Y, stride(Y, 2), size(X, 1), 0), "/")
+    Y
+end
 function LinearAlgebra.ldiv!(F::RevCholArrowhead, X::DevicePanel)
     check(ccall((:pop_solve, libpop), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Int64, Cint),
         ctx(), factor_handle(F).ptr, POP_LEFT, X.ptr, X.ld, X.cols, 0), "ldiv!")

@@ -86,6 +86,7 @@ _PROTOS = {
     "pop_trsm_host": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, i64, i64]),
     "pop_solve": (C.c_int, [vp, vp, C.c_int, vp, i64, i64, C.c_int]),
     "pop_solve_host": (C.c_int, [vp, vp, C.c_int, vp, i64, i64, C.c_int]),
+    "pop_solve_host_to": (C.c_int, [vp, vp, C.c_int, vp, i64, vp, i64, i64, C.c_int]),
     "pop_solve_shift_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, vp, i64, i64, i64, C.c_int]),
     "pop_solve_mul_axpy": (C.c_int, [vp, vp, vp, C.c_double, vp, i64, vp, i64, i64]),
     "pop_dist_handle_bytes": (C.c_int, []),

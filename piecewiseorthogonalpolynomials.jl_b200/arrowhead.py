@@ -455,18 +455,31 @@ def _bind_stream(ctx):
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
 
-def ldiv(T, X, overwrite=False, algo=L.SOLVE_AUTO):
+def ldiv(T, X, overwrite=False, algo=L.SOLVE_AUTO, out=None):
     """T \\ X for a triangular arrowhead or a ReverseCholesky factorisation
-    (src/arrowhead.jl:425-486; test/test_arrowhead.jl:64-68,130)."""
-    return _div(T, X, L.LEFT, overwrite, algo)
+    (src/arrowhead.jl:425-486; test/test_arrowhead.jl:64-68,130).  out: a host array of the shape and memory order of X that
+    receives `F \\ X` while X stays untouched (NumPy panels and ReverseCholesky only: the two directions of the host link
+    then work on different buffers)."""
+    return _div(T, X, L.LEFT, overwrite, algo, out)
 
 
-def rdiv(X, T, overwrite=False, algo=L.SOLVE_AUTO):
+def rdiv(X, T, overwrite=False, algo=L.SOLVE_AUTO, out=None):
     """X / T (rows), e.g. `X / reversecholesky(Symmetric(S))` in examples/adi_poisson.jl:54."""
-    return _div(T, X, L.RIGHT, overwrite, algo)
+    return _div(T, X, L.RIGHT, overwrite, algo, out)
 
 
-def _div(T, X, side, overwrite, algo):
+def _div(T, X, side, overwrite, algo, out=None):
+    if out is not None:
+        px, po = _Panel(X, False), _Panel(out, True)
+        if px.torch or po.torch or not isinstance(T, ReverseCholesky) or px.vector:
+            raise TypeError("out= is for host matrices solved with a ReverseCholesky factorisation")
+        if (px.rows, px.cols) != (po.rows, po.cols):
+            raise DimensionMismatch(-2, f"DimensionMismatch: X is {px.rows}x{px.cols}, out is {po.rows}x{po.cols}")
+        nrhs, veclen = (px.cols, px.rows) if side == L.LEFT else (px.rows, px.cols)
+        if veclen != T.factor.n:
+            raise DimensionMismatch(-2, f"DimensionMismatch: factor is {T.factor.n}x{T.factor.n}, right-hand side has {veclen}")
+        L.check(L.lib().pop_solve_host_to(T.factor.ctx.handle, T.factor._h, side, px.ptr, px.ld, po.ptr, po.ld, nrhs, algo), "ldiv")
+        return out
     Y = X if overwrite else _copy_like(X)
     p = _Panel(Y, True)
     if p.vector:

@@ -101,15 +101,16 @@ static bool host_is_pageable(const void *p) {
 struct StagedXfer {
     pop_ctx *ctx;
     HostStage *hs;
-    char *host, *dev;
+    char *host, *host_out, *dev;   // host: what goes to the device; host_out: where the results go (the same for in-place panels)
     std::vector<int64_t> pb;
     std::atomic<int> next_in{0}, next_out{0}, failed{0}, stop{0};
     std::unique_ptr<std::atomic<int>[]> issued;
     std::atomic<int64_t> out_ready{0};
     std::vector<std::thread> thr;
 
-    StagedXfer(pop_ctx *c, HostStage *h, void *hostp, void *devp, std::vector<int64_t> bounds)
-        : ctx(c), hs(h), host((char *)hostp), dev((char *)devp), pb(std::move(bounds)), issued(new std::atomic<int>[pb.size()]) {
+    StagedXfer(pop_ctx *c, HostStage *h, void *hostp, void *devp, std::vector<int64_t> bounds, void *host_outp = nullptr)
+        : ctx(c), hs(h), host((char *)hostp), host_out((char *)(host_outp ? host_outp : hostp)), dev((char *)devp), pb(std::move(bounds)),
+          issued(new std::atomic<int>[pb.size()]) {
         for (size_t i = 0; i < pb.size(); ++i) issued[i].store(0);
     }
     int npieces() const { return (int)pb.size() - 1; }
@@ -136,7 +137,7 @@ struct StagedXfer {
         auto finish = [&]() {
             if (pend < 0) return;
             if (cudaEventSynchronize(event(1, w, pend_slot)) != cudaSuccess) failed.store(1);
-            memcpy(host + pb[pend], slot(1, w, pend_slot), (size_t)(pb[pend + 1] - pb[pend]));
+            memcpy(host_out + pb[pend], slot(1, w, pend_slot), (size_t)(pb[pend + 1] - pb[pend]));
             pend = -1;
         };
         for (int i = 0;; ++i) {
@@ -191,7 +192,7 @@ struct StagedXfer {
 // chunks of an odd n give).  A device mirror of the whole panel receives the blocks; as soon as a block has landed, the
 // columns that are complete are re-pitched into the (even-pitch) work buffer, solved, re-pitched back, and every flat
 // block whose columns are all done goes home.  Copy streams and the compute stream only meet through events.
-static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, PanelOp &op, int64_t blk_bytes) {
+static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, const double *X, double *Y, PanelOp &op, int64_t blk_bytes) {   // Y: results (== X in place)
     const int64_t colb = n * 8, total = colb * nrhs;
     const int64_t ldd = (n + 1) & ~(int64_t)1;
     const int64_t A = 4096;
@@ -251,13 +252,13 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
     int rc = POP_OK;
     // pageable host memory: worker threads carry the panel through pinned pieces of one ramp unit (see StagedXfer)
     std::unique_ptr<StagedXfer> sx;
-    if (host_is_pageable(X)) {
+    if (host_is_pageable(X) || host_is_pageable(Y)) {
         if (HostStage *hs = host_stage_get(ctx, (size_t)U)) {
             std::vector<int64_t> pb;
             pb.push_back(0);
             for (int64_t b = off0 > 0 ? off0 : U; b < total; b += U) pb.push_back(b);
             pb.push_back(total);
-            sx.reset(new StagedXfer(ctx, hs, X, dflat, std::move(pb)));
+            sx.reset(new StagedXfer(ctx, hs, const_cast<double *>(X), dflat, std::move(pb), Y));
             sx->start_in();
             sx->start_out();
         }
@@ -301,7 +302,7 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
                 if (sx) sx->release_out(bnd[last]);
                 for (int j = blk_home; j < last && !sx; ++j) {
                     mark(ctx->s_copy[1], 4);
-                    e = cudaMemcpyAsync((char *)X + bnd[j], dflat + bnd[j], (size_t)(bnd[j + 1] - bnd[j]), cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+                    e = cudaMemcpyAsync((char *)Y + bnd[j], dflat + bnd[j], (size_t)(bnd[j + 1] - bnd[j]), cudaMemcpyDeviceToHost, ctx->s_copy[1]);
                     if (e != cudaSuccess) { pop_set_error("host panel D2H: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
                     mark(ctx->s_copy[1], 5);
                 }
@@ -330,9 +331,12 @@ static int run_host_flat(pop_ctx *ctx, int64_t n, int64_t nrhs, double *X, Panel
     return rc;
 }
 
-static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, double *X, int64_t ldx, PanelOp &op) {
+// X: the host panel that goes to the device; Y (leading dimension ldy): where the results go -- the same panel for the in-place
+// calls (ldiv!), another one for `Y = F \\ X`: the two directions of the link then work on different host buffers, which
+// this platform rewards (27.7 against 31 ms per 1.34 GB each way)
+static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, const double *X, int64_t ldx, double *Y, int64_t ldy, PanelOp &op) {
     if (nrhs == 0 || n == 0) return POP_OK;
-    if (side == POP_LEFT && ldx == n) {
+    if (side == POP_LEFT && ldx == n && ldy == n) {
         // contiguous panel: flat, address-aligned blocks through a device mirror (unless it would not fit)
         int64_t blk = (int64_t)32 << 20;
         if (const char *e = getenv("POP_HOST_CHUNK_MB")) blk = std::max<int64_t>(1, atoll(e)) << 20;
@@ -340,7 +344,7 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
         int use_flat = 1;
         if (const char *e = getenv("POP_HOST_FLAT")) use_flat = atoi(e);
         if (use_flat && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (size_t)n * nrhs * 8 < free_b / 2) {
-            const int rc = run_host_flat(ctx, n, nrhs, X, op, blk);
+            const int rc = run_host_flat(ctx, n, nrhs, X, Y, op, blk);
             if (rc != POP_HOST_FLAT_NOFIT) return rc;
         }
         cudaGetLastError();
@@ -357,7 +361,7 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
     const size_t buf_doubles = side == POP_LEFT ? (size_t)ldd * per : (size_t)ldd * n;
     // a contiguous host panel whose pitch differs from the (even) device pitch crosses PCIe as ONE linear copy per
     // chunk into a staging area and is re-pitched on the device (pitched 2-D DMA is ~25 % slower on this platform)
-    const bool linear = side == POP_LEFT && ldx == n && ldd != n;
+    const bool linear = side == POP_LEFT && ldx == n && ldy == n && ldd != n;
     const size_t stg_doubles = linear ? (size_t)n * per : 0;
     double *dbuf = nullptr;
     cudaError_t e = cudaMallocAsync(&dbuf, (buf_doubles + stg_doubles) * nbuf * sizeof(double), ctx->stream);
@@ -416,11 +420,11 @@ static int run_host_panels(pop_ctx *ctx, int side, int64_t n, int64_t nrhs, doub
         cudaStreamWaitEvent(ctx->s_copy[1], cmp[b], 0);
         mark(ctx->s_copy[1]);
         if (linear)
-            e = cudaMemcpyAsync(X + done * ldx, stg, (size_t)n * cnt * 8, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+            e = cudaMemcpyAsync(Y + done * ldy, stg, (size_t)n * cnt * 8, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
         else if (side == POP_LEFT)
-            e = cudaMemcpy2DAsync(X + done * ldx, ldx * 8, d, ldd * 8, n * 8, cnt, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+            e = cudaMemcpy2DAsync(Y + done * ldy, ldy * 8, d, ldd * 8, n * 8, cnt, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
         else
-            e = cudaMemcpy2DAsync(X + done, ldx * 8, d, ldd * 8, cnt * 8, n, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
+            e = cudaMemcpy2DAsync(Y + done, ldy * 8, d, ldd * 8, cnt * 8, n, cudaMemcpyDeviceToHost, ctx->s_copy[1]);
         if (e != cudaSuccess) { pop_set_error("host panel D2H: %s", cudaGetErrorString(e)); rc = POP_ERR_CUDA; break; }
         cudaEventRecord(d2h[b], ctx->s_copy[1]);
         mark(ctx->s_copy[1]);
@@ -463,12 +467,19 @@ static int check_host_panel(const pop_arrowhead *A, int side, const double *X, i
 }
 
 extern "C" int pop_solve_host(pop_ctx *ctx, const pop_arrowhead *U, int side, double *X, int64_t ldx, int64_t nrhs, int algo) {
+    return pop_solve_host_to(ctx, U, side, X, ldx, X, ldx, nrhs, algo);
+}
+
+extern "C" int pop_solve_host_to(pop_ctx *ctx, const pop_arrowhead *U, int side, const double *X, int64_t ldx, double *Y, int64_t ldy, int64_t nrhs,
+                                 int algo) {
     POP_REQUIRE(ctx && U, POP_ERR_ARG, "pop_solve_host: null argument");
     POP_REQUIRE(U->is_factor, POP_ERR_ARG, "pop_solve_host: handle is not a reverse-Cholesky factor");
     int rc = check_host_panel(U, side, X, ldx, nrhs, "pop_solve_host");
     if (rc) return rc;
+    rc = check_host_panel(U, side, Y, ldy, nrhs, "pop_solve_host");
+    if (rc) return rc;
     SolveOp op; op.U = U; op.side = side; op.algo = algo;
-    return run_host_panels(ctx, side, U->n(), nrhs, X, ldx, op);
+    return run_host_panels(ctx, side, U->n(), nrhs, X, ldx, Y, ldy, op);
 }
 
 extern "C" int pop_trsm_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int uplo, int trans, int unit, double *X, int64_t ldx, int64_t nrhs) {
@@ -476,7 +487,7 @@ extern "C" int pop_trsm_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int
     int rc = check_host_panel(A, side, X, ldx, nrhs, "pop_trsm_host");
     if (rc) return rc;
     TrsmOp op; op.A = A; op.side = side; op.uplo = uplo; op.trans = trans; op.unit = unit;
-    return run_host_panels(ctx, side, A->n(), nrhs, X, ldx, op);
+    return run_host_panels(ctx, side, A->n(), nrhs, X, ldx, X, ldx, op);
 }
 
 extern "C" int pop_mul_host(pop_ctx *ctx, const pop_arrowhead *A, int side, int sym, int trans, double alpha, const double *X, int64_t ldx,

@@ -451,6 +451,21 @@ def test_host_panels_flat_and_chunked(basis, m, N, nrhs, monkeypatch):
         assert np.array_equal(Xo, want) and raw[0] == 0.0, (flat, mb)
         U = F.U
         assert relerr(P.ldiv(U, np.asfortranarray(Bm)), host(P.ldiv(U, dev(Bm)))) < 1e-15
+        # Y = F \ X into another host panel (pop_solve_host_to): X untouched; also with a destination of another alignment
+        Xin = np.asfortranarray(Bm)
+        Yout = np.full((n, nrhs), np.nan, order="F")
+        assert P.ldiv(F, Xin, out=Yout) is Yout
+        assert np.array_equal(Yout, want) and np.array_equal(Xin, Bm), (flat, mb)
+        raw2 = np.full(n * nrhs + 3, np.nan)
+        Y2 = raw2[3:].reshape((n, nrhs), order="F")
+        P.ldiv(F, Xin, out=Y2)
+        assert np.array_equal(Y2, want) and np.isnan(raw2[:3]).all(), (flat, mb)
+        Rin = np.asfortranarray(Bm.T.copy())                     # rows are the systems: X / F
+        Rout = np.empty_like(Rin)
+        P.rdiv(Rin, F, out=Rout)
+        assert relerr(Rout, want.T) < 1e-14 and np.array_equal(Rin, Bm.T), (flat, mb)
+    with pytest.raises(P.DimensionMismatch):
+        P.ldiv(F, np.asfortranarray(Bm), out=np.empty((n + 1, nrhs), order="F"))
 
 
 @pytest.mark.parametrize("basis", ["c1", "dirichlet"])
