@@ -203,7 +203,8 @@ int pop_solve_mul_axpy(pop_ctx *ctx, const pop_arrowhead *U, const pop_arrowhead
  * (i p + s, j p + t) = f at node s of cell i in x and node t of cell j in y; T_host (p x p, column-major, host)
  * is the analysis matrix of the cell grid (`plan_grid_transform(legendre(0..dx), (p,p))`: coefficients = T * values).
  * dF receives the tensor Legendre coefficients interlaced like a block vector: F[i + n a, j + n b]
- * (`F[i+1:n:n*p, j+1:n:n*p] = T * f_.(z, z')`).  p <= 64.  Synchronises the stream. */
+ * (`F[i+1:n:n*p, j+1:n:n*p] = T * f_.(z, z')`).  p <= 64: one fused per-cell kernel; larger cells (the example's own p = 300):
+ * two tiled passes through an (n p)^2 intermediate.  Synchronises the stream. */
 int pop_legendre_analysis_2d(pop_ctx *ctx, int n, int p, const double *T_host, const double *dV, int64_t ldv,
                              double *dF, int64_t ldf);
 /* (Q'P)[KR,KR] = (P\Q)' (P'P), Q = ContinuousPolynomial{1} or DirichletPolynomial, P = ContinuousPolynomial{0}
@@ -234,7 +235,7 @@ int pop_legendre_to_c1(pop_ctx *ctx, int basis, int m, int N, int side, const do
  * pop_legendre_synthesis_2d: `legendretransform \ dat` for a 2D field: dF holds the tensor Legendre coefficients interlaced
  * as pop_legendre_analysis_2d writes them, S_host (p x p, column-major, host) is the synthesis matrix of the cell grid
  * (values = S * coefficients, S[s,a] = P_a(z_s), the inverse of the analysis matrix T); dV receives the values
- * (entry (i p + s, j p + t) = node s of cell i, node t of cell j).  p <= 64.  Synchronises the stream. */
+ * (entry (i p + s, j p + t) = node s of cell i, node t of cell j).  Synchronises the stream. */
 int pop_c1_to_legendre(pop_ctx *ctx, int basis, int m, int N, int side, const double *dX, int64_t ldx, double *dY,
                        int64_t ldy, int64_t cnt);
 int pop_legendre_synthesis_2d(pop_ctx *ctx, int n, int p, const double *S_host, const double *dF, int64_t ldf,

@@ -413,13 +413,105 @@ __global__ void __launch_bounds__(256, 2) k_analysis_2d(int n, int p, const doub
     }
 }
 
+// Cells of more than 64 nodes per dimension (examples/adi_poisson.jl:87 uses p = 300 on four cells): the per-cell kernel
+// above keeps a whole cell on chip, so these go through two tiled passes with the cell matrix T applied from the left, then from
+// the right, and an intermediate in global memory:  W[i p + a, c] = sum_k T[a,k] in[row(i,k), c]  and
+// out[row(r), col(j,b)] = sum_k W[r, col(j,k)] T[b,k].  64 x 64 output tiles, 16 x 16 threads with 4 x 4 accumulators each,
+// k in chunks of 16.  *_il: the index runs interlaced (cell + n * degree) instead of cell-major (cell * p + node).
+template <bool RIGHT>
+__global__ void __launch_bounds__(256) k_cell_apply(int n, int p, const double *__restrict__ T, const double *__restrict__ in, int64_t ldi, double *__restrict__ out,
+                                                    int64_t ldo, int in_il, int out_il, int out_rows_il) {
+    __shared__ double As[16][65], Bs[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, cell = blockIdx.z;
+    const int64_t np = (int64_t)n * p;
+    const int64_t t0 = (int64_t)blockIdx.x * 64;   // LEFT: first column of the tile; RIGHT: first row
+    const int b0 = blockIdx.y * 64;                // first row (LEFT) / column (RIGHT) of T
+    auto idx = [&](int il, int c, int k) -> int64_t { return il ? (int64_t)c + (int64_t)n * k : (int64_t)c * p + k; };
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < p; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e & 15, x = e >> 4, k = k0 + kk;
+            // As[kk][x]: the operand indexed by the output's first index, Bs[kk][x]: by its second
+            double av = 0.0, bv = 0.0;
+            if (k < p) {
+                if (!RIGHT) {
+                    if (b0 + x < p) av = T[(b0 + x) + (int64_t)p * k];
+                    if (t0 + x < np) bv = in[idx(in_il, cell, k) + (t0 + x) * ldi];
+                } else {
+                    if (t0 + x < np) av = in[(t0 + x) + idx(in_il, cell, k) * ldi];
+                    if (b0 + x < p) bv = T[(b0 + x) + (int64_t)p * k];
+                }
+            }
+            As[kk][x] = av;
+            Bs[kk][x] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = As[kk][ty * 4 + u];
+                b[u] = Bs[kk][tx * 4 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (!RIGHT) {
+                const int a = b0 + ty * 4 + u;
+                const int64_t c = t0 + tx * 4 + v;
+                if (a < p && c < np) out[idx(out_il, cell, a) + c * ldo] = acc[u][v];
+            } else {
+                const int64_t r = t0 + ty * 4 + u;
+                const int b = b0 + tx * 4 + v;
+                if (r < np && b < p) {
+                    const int64_t ro = out_rows_il ? (r / p) + (int64_t)n * (r % p) : r;
+                    out[ro + idx(out_il, cell, b) * ldo] = acc[u][v];
+                }
+            }
+        }
+}
+
+static int cell_transform_2d_tiled(pop_ctx *ctx, bool synth, int n, int p, const double *T_host, double *dV, int64_t ldv, double *dF, int64_t ldf) {
+    const int64_t np = (int64_t)n * p;
+    double *dT = nullptr, *W = nullptr;
+    POP_CUDA(cudaMallocAsync((void **)&dT, ((size_t)p * p + (size_t)np * np) * sizeof(double), ctx->stream));
+    W = dT + (size_t)p * p;
+    cudaError_t e = cudaMemcpyAsync(dT, T_host, (size_t)p * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const dim3 grid((unsigned)((np + 63) / 64), (unsigned)((p + 63) / 64), (unsigned)n);
+        if (!synth) {   // values (cell-major) -> W (rows cell-major) -> coefficients (interlaced)
+            k_cell_apply<false><<<grid, 256, 0, ctx->stream>>>(n, p, dT, dV, ldv, W, np, 0, 0, 0);
+            k_cell_apply<true><<<grid, 256, 0, ctx->stream>>>(n, p, dT, W, np, dF, ldf, 0, 1, 1);
+        } else {        // coefficients (interlaced) -> W (rows cell-major, columns still interlaced) -> values (cell-major)
+            k_cell_apply<false><<<grid, 256, 0, ctx->stream>>>(n, p, dT, dF, ldf, W, np, 1, 0, 0);
+            k_cell_apply<true><<<grid, 256, 0, ctx->stream>>>(n, p, dT, W, np, dV, ldv, 1, 0, 0);
+        }
+        ctx->launches += 2;
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);   // T_host may be reused at once
+    cudaFreeAsync(dT, ctx->stream);
+    if (e != cudaSuccess || e2 != cudaSuccess) { pop_set_error("cell transform (tiled): %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return POP_ERR_CUDA; }
+    return POP_OK;
+}
+
 static int cell_transform_2d(pop_ctx *ctx, bool synth, int n, int p, const double *T_host, double *dV, int64_t ldv, double *dF, int64_t ldf) {
     const char *who = synth ? "pop_legendre_synthesis_2d" : "pop_legendre_analysis_2d";
     POP_REQUIRE(ctx && T_host && dV && dF, POP_ERR_ARG, "%s: null argument", who);
     POP_REQUIRE(n >= 1 && p >= 1, POP_ERR_ARG, "%s: need n >= 1 cells per dimension and p >= 1 nodes per cell", who);
-    POP_REQUIRE(p <= 64, POP_ERR_DIM, "%s: p = %d nodes per cell: the per-cell kernel holds p <= 64", who, p);
+    POP_REQUIRE(p <= 4096, POP_ERR_DIM, "%s: p = %d nodes per cell is out of range", who, p);
     const int64_t np = (int64_t)n * p;
     POP_REQUIRE(ldv >= np && ldf >= np, POP_ERR_DIM, "%s: DimensionMismatch: panels need %lld rows", who, (long long)np);
+    if (p > 64) return cell_transform_2d_tiled(ctx, synth, n, p, T_host, dV, ldv, dF, ldf);   // the per-cell kernel holds p <= 64
     double *dT = nullptr;
     int rc = pop_ctx_scratch(ctx, (size_t)p * p * sizeof(double), (void **)&dT);
     if (rc) return rc;

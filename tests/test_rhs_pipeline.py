@@ -130,7 +130,7 @@ def _dev(torch, A):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,p", [(1, 1), (1, 5), (3, 16), (7, 33), (2, 64), (5, 62)])
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 5), (3, 16), (7, 33), (2, 64), (5, 62), (1, 65), (3, 100), (2, 129)])
 def test_analysis_2d_kernel_vs_oracle(n, p):
     torch, P = _gpu()
     z, T = P.legendre_grid_transform(p, "gauss" if p % 2 else "chebyshev1")
@@ -144,9 +144,6 @@ def test_analysis_2d_kernel_vs_oracle(n, p):
 @pytest.mark.gpu
 def test_analysis_2d_rejects_what_it_cannot_hold():
     torch, P = _gpu()
-    z, T = P.legendre_grid_transform(65)
-    with pytest.raises(P.DimensionMismatch):
-        P.analysis_2d(_dev(torch, np.zeros((65, 65))), 1, 65, T)
     z, T = P.legendre_grid_transform(4)
     with pytest.raises(P.DimensionMismatch):
         P.analysis_2d(_dev(torch, np.zeros((9, 8))), 2, 4, T)
@@ -198,6 +195,31 @@ def test_adi_poisson_example_end_to_end_gpu():
     E = O.basis_eval_matrix(O.DIRICHLET, r, p, pts)
     Ua = E @ Y.cpu().numpy() @ E.T
     assert np.abs(Ua - u(pts[:, None], pts[None, :])).max() < 1e-10
+
+
+@pytest.mark.gpu
+def test_adi_poisson_example_at_its_own_size():
+    """examples/adi_poisson.jl:78-117 with the example's OWN parameters: r = range(-1, 1, 5) (four cells), p = 300 -- cells of more
+    than 64 nodes go through the tiled analysis, chains of 299 degrees through the shared-memory column kernel and the two-pass
+    row kernels; checked like the example does, `u_exact.(z) ≈ Ua` on its 201 x 201 grid."""
+    torch, P = _gpu()
+    K, p = 4, 300
+    r, h, f, u, z, T, xs, vals = _poisson_example(K, p)
+    Q = P.DirichletPolynomial(r)
+    KR = P.Block.oneto(p)
+    fp = P.analysis_2d(_dev(torch, vals), K, p, T)
+    F = P.weakform_rhs(Q, KR, fp)
+    M = P.grammatrix(Q)[KR, KR]
+    Kh = -P.weaklaplacian(Q)[KR, KR]
+    a, b = P.spectrum_bounds(M, Kh)
+    X = P.adi_poisson(M, Kh, F, a, b)
+    Y = P.rdiv(X, P.reversecholesky(Kh))
+    pts = np.arange(-1, 1.0001, 0.01)                              # z = SVector.(-1:0.01:1, (-1:0.01:1)')
+    E = O.basis_eval_matrix(O.DIRICHLET, r, p, pts)
+    Ua = E @ Y.cpu().numpy() @ E.T
+    exact = u(pts[:, None], pts[None, :])
+    assert np.allclose(Ua, exact, rtol=1e-8, atol=1e-10)            # Julia's `≈` is rtol = sqrt(eps)
+    assert np.abs(Ua - exact).max() < 1e-9
 
 
 @pytest.mark.gpu
@@ -379,7 +401,7 @@ def test_c1_to_legendre_kernel_vs_oracle(basis, m, N):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,p", [(1, 1), (1, 5), (3, 16), (7, 33), (2, 64), (5, 62)])
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 5), (3, 16), (7, 33), (2, 64), (5, 62), (1, 65), (3, 100), (2, 129)])
 def test_synthesis_2d_kernel_vs_oracle(n, p):
     torch, P = _gpu()
     z, T = P.legendre_grid_transform(p)
