@@ -32,12 +32,14 @@ BYTES_PER_UNIT = 16.0   # one read + one write of X per unknown*RHS (SURVEY.md 8
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the headline kernel, from the committed
-    ncu --set full capture of this same command (profiles/r1_bench_traffic.json); None if absent."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_bench_traffic.json")) as f:
-            return float(json.load(f)["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    ncu --set full capture of this same command (profiles/r2z_bench_traffic.json, round 1: r1_bench_traffic.json); None if absent."""
+    for name in ("r2z_bench_traffic.json", "r1_bench_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak():
