@@ -62,7 +62,7 @@ struct R2Params {
     int o_in, o_inh, o_fh, o_ring, o_mb, o_hf, o_ct, o_tab, o_ttab, o_ftab, o_hrd, o_hcd, o_hcu, o_ss, o_st, total;
     int mbw;                       // doubles per mailbox message
     int f_evict_first;             // F loads carry the L2 evict_first policy
-    int no_send;                   // stand-in profiling only (POP_ROW2_NOSEND): skip the sends, to time them by difference
+    int use_senders;               // remote mode: the idle warps of the producer group carry the messages to the mailboxes
     long long *dbg;                // POP_ROW2_TRACE: phase time stamps of CTA 0 (clock64), [block][16]
     // remote mode (several GPUs, or forced): the row direction is split over nr = world * csv CTAs that meet through
     // mailboxes in (peer) global memory instead of a cluster's shared memory
@@ -194,7 +194,9 @@ __device__ __forceinline__ double r2_mbtake(const double *p, unsigned long long 
 #define R2_BAR_COMPUTE 1   // named barrier of the compute threads
 #define R2_STAMP(slot) do { if (P.dbg && blockIdx.x == 0 && tid == 0 && t < 64) P.dbg[t * 16 + (slot)] = clock64(); } while (0)
 #define R2_BAR_HATS 2      // compute threads + the two hat warps: hats solved
-#define R2_BAR_MSG 3       // compute threads (arrive) + the two hat warps (sync): this CTA's message is written
+#define R2_BAR_MSG 4       // 4, 5 (by block parity): compute threads arrive, the sender warps wait: the CTA's message is in the staging buffer
+#define R2_BAR_FREE 6      // 6, 7 (by block parity): the sender warps arrive, the compute threads wait: the staging buffer may be rewritten
+#define R2_SENDERS 96      // remote mode with the hats on the compute warps: the three idle warps of the producer group send the messages
 #define R2_COMPUTE_SLOTS 512   // threads [0, 512): compute (the first 16 mlc of them work), [512, 640): producer warp group
 // MLC > 0: elements per CTA fixed at compile time (every hot shared-memory address is then one register plus an immediate).
 // RB rows per block: 8 (64 B runs; clusters / groups walk in pairs) or 16 (128 B runs; for panels of few elements per CTA).
@@ -550,6 +552,29 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 named_bar_sync(R2_BAR_HATS, nthr + 64);   // the hats of the 8 rows are solved
             }
         }
+        if (REM && hatm && P.use_senders && tid >= R2_COMPUTE_SLOTS + 32) {
+            // =========================== three sender warps (remote mode) ===============================================
+            // The message of a block goes to every CTA that shares the row block, on every GPU: 8 byte stores into their
+            // mailboxes.  These warps take that off the compute warps, which go on with the forward sweep; the staging
+            // buffer alternates with the block parity, two named barriers per parity hand it back and forth.
+            const int st = tid - (R2_COMPUTE_SLOTS + 32);
+            for (int t = 0; t < nloc; ++t) {
+                const int pb = t & 1;
+                named_bar_sync(R2_BAR_MSG + pb, nthr + R2_SENDERS);   // the message of block t is complete
+                const double *src = MB + (size_t)pb * mbw;
+                const size_t mslot = ((size_t)(P.epoch & 1) * P.nblk + (size_t)(bbase + t * bstride)) * G;
+                for (int gi = 0; gi < P.world; ++gi) {
+                    const int g = (P.me + 1 + gi) % P.world;   // every GPU starts with another target; its own mailboxes come last
+                    for (int dc = 0; dc < G; ++dc) {
+                        double *dst = P.mbox[g] + ((mslot + dc) * nr + rank) * mbw;
+                        // two entries per store (mbw is even, the mailboxes are 16-byte aligned); every 8-byte word still arrives whole
+                        for (int x = 2 * st; x < mbw; x += 2 * R2_SENDERS)
+                            asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(dst + x), "d"(src[x]), "d"(src[x + 1]) : "memory");
+                    }
+                }
+                named_bar_arrive(R2_BAR_FREE + pb, nthr + R2_SENDERS);   // the staging buffer of this parity is free again
+            }
+        }
     } else {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
       if (tid < nthr) {
@@ -571,7 +596,8 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
             const uint32_t phMB = (uint32_t)(t >> 1) & 1u;
             const int row0 = (bbase + t * bstride) * RB;
             const double *inh = INH + pb * HBS, *fh = FH + pb * HBS;
-            double *mbme = remote ? MB : MB + ((size_t)pb * cs + rank) * mbw;   // remote: staging of my message only
+            const bool senders = REM && hatm && P.use_senders;   // the sender warps carry the message to the mailboxes
+            double *mbme = remote ? MB + (senders ? (size_t)pb * mbw : 0) : MB + ((size_t)pb * cs + rank) * mbw;   // remote: staging of my message only
             const size_t mslot = ((size_t)(P.epoch & 1) * P.nblk + (size_t)(bbase + t * bstride)) * G;   // mailboxes of this row block: one per reading CTA
             const double *mbp = remote ? P.mbox[P.me] + (mslot + (blockIdx.x % (unsigned)G)) * nr * mbw : MB + (size_t)pb * cs * mbw;
             // ---- A+B: the row block, shared memory -> registers, chunk by chunk from the top degrees down, and the
@@ -612,6 +638,7 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 }
             }
             R2_STAMP(2);
+            if (senders && t >= 2) named_bar_sync(R2_BAR_FREE + pb, nthr + R2_SENDERS);   // the sender warps are done with this staging buffer (block t - 2)
             {
                 double c0 = 0.0, c1 = 0.0, c2 = 0.0;
 #pragma unroll
@@ -652,10 +679,11 @@ __global__ void __launch_bounds__(640, 1) k_row2(const __grid_constant__ R2Param
                 }
                 mbme[tid] = v;
             }
-            if (remote) {
+            if (remote && senders) {
+                named_bar_arrive(R2_BAR_MSG + pb, nthr + R2_SENDERS);   // the sender warps take it from here
+            } else if (remote) {
                 // my message into the mailbox of every CTA that shares this row block, on every GPU (mine included)
                 named_bar_sync(R2_BAR_COMPUTE, nthr);
-                if (!P.no_send)
                 for (int g = 0; g < P.world; ++g)
                     for (int dc = 0; dc < G; ++dc) {
                         volatile double *dst = P.mbox[g] + ((mslot + dc) * nr + rank) * mbw;
@@ -1122,6 +1150,9 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
     P.hat_mode = hat_mode;
     P.hat_L = hat_L;
     P.f_evict_first = r2_env("POP_F_EVICT_FIRST", 1);
+    // measured on 8 real GPUs, same box (profiles/r2z_dd8_senders.txt): 12.85 ms per ADI solve with the compute warps sending, 13.25 with the
+    // sender warps (the one-GPU stand-in, where a message is an L2 round trip, had shown the opposite: 12.08 -> 11.9): off
+    P.use_senders = r2_env("POP_ROW2_SENDERS", 0);
     P.pf_dist = r2_env("POP_ROW2_PF", 0);   // L2 prefetch distance of F in row blocks (0: off)
 
     const int pm = rem ? op.ml : op.m, pnh = rem ? op.nhl : op.nh;   // the panel: all elements, or this GPU's
@@ -1146,7 +1177,6 @@ int pop_row2_half_step(pop_ctx *ctx, const RowOp &op, const double *F, double *R
         P.epoch = rem->epoch;
         for (int g = 0; g < rem->world; ++g) P.mbox[g] = rem->mbox[g];
         P.merr = rem->merr;
-        P.no_send = (rem->standin && r2_env("POP_ROW2_NOSEND", 0)) ? 1 : 0;
         if ((int64_t)2 * P.nblk * P.csv * P.nr * P.mbw > rem->mbox_doubles) return unsupported("mailbox too small");
         if (P.nr > 2 * mlc) return unsupported("more CTAs per row block than the edge buffer holds");   // HE aliases the coupling buffer [4][mlc][rb]
     }
