@@ -175,8 +175,8 @@ end
 
 "Device handle of the factor behind `F`: the cached one, or -- for a factor computed elsewhere, e.g. by the reference's
 own CPU code -- an upload of `F.U` marked as a factor (pop_arrowhead_as_factor; it is NOT factored again)."
-function factor_handle(F::ReverseCholesky{Float64,<:UpperTriangular{Float64,<:BBBArrowheadMatrix}})
-    A = parent(F.U)
+function factor_handle(F::ReverseCholesky{Float64})
+    A = parent(F.U)::BBBArrowheadMatrix
     k = cachekey(A)
     k !== nothing && haskey(FACTORS, k) && return FACTORS[k]
     h = upload(UpperTriangular(A))                               # upper data only: C = ()
@@ -186,7 +186,10 @@ function factor_handle(F::ReverseCholesky{Float64,<:UpperTriangular{Float64,<:BB
 end
 
 # ---- F \ X and X / F: one call for the whole panel (test/test_arrowhead.jl:130, adi_poisson.jl:54-55) --
-const RevCholArrowhead = ReverseCholesky{Float64,<:UpperTriangular{Float64,<:BBBArrowheadMatrix}}
+# (MatrixFactorizations stores either the matrix itself or its UpperTriangular view as `factors`, depending on the version:
+# both are bound; `F.U` is an UpperTriangular of the BBBArrowheadMatrix in either case)
+const RevCholArrowhead = Union{ReverseCholesky{Float64,<:BBBArrowheadMatrix},
+                               ReverseCholesky{Float64,<:UpperTriangular{Float64,<:BBBArrowheadMatrix}}}
 function LinearAlgebra.ldiv!(F::RevCholArrowhead, X::StridedVecOrMat{Float64})
     h = factor_handle(F)
     GC.@preserve X check(ccall((:pop_solve_host, libpop), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Int64, Cint),
