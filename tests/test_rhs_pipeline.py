@@ -114,6 +114,24 @@ def test_oracle_reproduces_rhs_fixtures():
     assert relerr(O.analysis_2d(RG["analysis/vals"], n, p, O.legendre_grid_transform(p)[1]), RG["analysis/F"]) < 1e-13
 
 
+def test_oracle_reproduces_inverse_transform_and_varcoef_fixtures():
+    """The fixtures of the inverse transforms come from evaluating the basis functions at the nodes, those of the
+    variable-coefficient Laplacian from Gauss quadrature: neither uses the closed forms under test."""
+    for name, basis in (("itransform_c1", O.C1), ("itransform_dirichlet", O.DIRICHLET)):
+        pts, p = RG[f"{name}/points"], int(RG[f"{name}/p"])
+        m = len(pts) - 1
+        z, T = O.legendre_grid_transform(p)
+        S = np.polynomial.legendre.legvander(z, p - 1)
+        leg = O.legendre_from_c1(basis, m, p, RG[f"{name}/c"][:, None])[:, 0].reshape(p, m)
+        assert relerr((S @ leg).T.reshape(-1), RG[f"{name}/vals"]) < 1e-13
+        L = O.lowering_dense(basis, m, p)[:, :RG[f"{name}/c"].size]
+        assert relerr(O.synthesis_2d(L @ RG[f"{name}/C2"] @ L.T, m, p, S), RG[f"{name}/vals2"]) < 1e-13
+    for name, basis in (("varcoef_c1", O.C1), ("varcoef_dirichlet", O.DIRICHLET)):
+        pts, a, N = RG[f"{name}/points"], RG[f"{name}/a"], int(RG[f"{name}/N"])
+        Ld = O.unpack(O.packed_symmetrize(O.assemble_weaklaplacian(basis, len(pts) - 1, N, np.diff(pts), a=a))).to_dense()
+        assert np.abs(Ld - RG[f"{name}/L"]).max() < 1e-12 * np.abs(RG[f"{name}/L"]).max()
+
+
 # ------------------------------------------------------------------------------------------------ CUDA kernels
 def _gpu():
     import torch
@@ -304,6 +322,24 @@ def test_kernels_reproduce_rhs_fixtures():
     n, p = int(RG["analysis/n"]), int(RG["analysis/p"])
     F = P.analysis_2d(_dev(torch, RG["analysis/vals"]), n, p, P.legendre_grid_transform(p)[1])
     assert relerr(F.cpu().numpy(), RG["analysis/F"]) < TOL
+
+
+@pytest.mark.gpu
+def test_kernels_reproduce_inverse_transform_and_varcoef_fixtures():
+    torch, P = _gpu()
+    for name, basis in (("itransform_c1", "c1"), ("itransform_dirichlet", "dirichlet")):
+        pts, p = RG[f"{name}/points"], int(RG[f"{name}/p"])
+        Q = P.ContinuousPolynomial(1, pts) if basis == "c1" else P.DirichletPolynomial(pts)
+        x, vals = P.itransform(Q, _dev(torch, RG[f"{name}/c"][:, None])[:, 0], p)
+        assert relerr(vals, RG[f"{name}/vals"]) < TOL
+        z, _ = P.legendre_grid_transform(p)
+        V2 = P.itransform_2d(Q, _dev(torch, RG[f"{name}/C2"]), p, P.legendre_synthesis_matrix(z, p))
+        assert relerr(V2.cpu().numpy(), RG[f"{name}/vals2"]) < TOL
+    for name, basis in (("varcoef_c1", "c1"), ("varcoef_dirichlet", "dirichlet")):
+        pts, a, N = RG[f"{name}/points"], RG[f"{name}/a"], int(RG[f"{name}/N"])
+        Q = P.ContinuousPolynomial(1, pts) if basis == "c1" else P.DirichletPolynomial(pts)
+        Lv = P.weaklaplacian(Q, a=a)[P.Block.oneto(N), P.Block.oneto(N)]
+        assert np.abs(Lv.to_dense() - RG[f"{name}/L"]).max() < 1e-12 * np.abs(RG[f"{name}/L"]).max()
 
 
 @pytest.mark.gpu
