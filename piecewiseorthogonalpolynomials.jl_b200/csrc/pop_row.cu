@@ -43,6 +43,7 @@ struct pop_dd {
     double *xb;      // [4][ml][nrows] x of the coupled bubbles (for the hat rows of the product)
     double *pconst;  // [2][world]
     double *work;    // nrows x nloc work panel (leading dimension ld)
+    cudaStream_t pool_stream;   // the stream the local buffers were allocated on (stream-ordered pool)
     bool hats_merged;   // the hat phase runs as ONE kernel (k_row_hats): tile fits, grid co-resident
     int hats_ny;        // lanes over the hats in k_row_hats (block = 32 rows x hats_ny)
     size_t hats_smem;
@@ -119,14 +120,19 @@ extern "C" int pop_dd_create(pop_ctx *ctx, int rank, int world, int m, int nh, i
             d->r2_ok = true;
         }
     }
+    // The slab is what the peers map (CUDA IPC needs a cudaMalloc allocation); everything else is local and comes from the
+    // stream-ordered pool, which keeps it between calls: the single-GPU entry points build a decomposition per solve.
+    d->pool_stream = ctx->stream;
     cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&d->hx, (size_t)(d->nhl + 3) * d->nrows * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->gdn, (size_t)d->nrows * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->xb, (size_t)4 * d->ml * d->nrows * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->pconst, (size_t)2 * POP_DD_MAXWORLD * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->work, (size_t)d->ld * d->nloc * 8);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d->hx, (size_t)(d->nhl + 3) * d->nrows * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d->gdn, (size_t)d->nrows * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d->xb, (size_t)4 * d->ml * d->nrows * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d->pconst, (size_t)2 * POP_DD_MAXWORLD * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d->work, (size_t)d->ld * d->nloc * 8, ctx->stream);
     if (e != cudaSuccess) {
         pop_set_error("pop_dd_create: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        pop_dd_destroy(ctx, d);   // nothing half-built survives
         return POP_ERR_ALLOC;
     }
     POP_CUDA(cudaMemsetAsync(d->slab, 0, d->slab_bytes, ctx->stream));
@@ -179,11 +185,12 @@ extern "C" int pop_dd_destroy(pop_ctx *ctx, pop_dd *d) {
     for (int r = 0; r < d->world; ++r)
         if (!d->fake_peers && r != d->rank && d->peer_slab[r]) cudaIpcCloseMemHandle(d->peer_slab[r]);
     cudaFree(d->slab);
-    cudaFree(d->hx);
-    cudaFree(d->gdn);
-    cudaFree(d->xb);
-    cudaFree(d->pconst);
-    cudaFree(d->work);
+    const cudaStream_t ps = ctx ? ctx->stream : d->pool_stream;
+    if (d->hx) cudaFreeAsync(d->hx, ps);
+    if (d->gdn) cudaFreeAsync(d->gdn, ps);
+    if (d->xb) cudaFreeAsync(d->xb, ps);
+    if (d->pconst) cudaFreeAsync(d->pconst, ps);
+    if (d->work) cudaFreeAsync(d->work, ps);
     delete d;
     return POP_OK;
 }
