@@ -478,6 +478,31 @@ def test_inverse_transforms_like_the_reference_tests():
 
 
 @pytest.mark.gpu
+def test_dirichlet_transform_testset_of_the_reference():
+    """test/test_dirichlet.jl:58-71 ("transform"): r = range(-1, 1; length=3), Block(20): `Q[0.1,1:39]' * (F*f.(x)) ≈ f(0.1)`,
+    `F \\ (F*f.(x)) ≈ f.(x)`, and in two dimensions `Q[0.1,KR]' * V * Q[0.2,KR] ≈ f(0.1,0.2)`, `F \\ V ≈ vals` (square here: the
+    reference's second dimension has 21 blocks)."""
+    torch, P = _gpu()
+    r = np.linspace(-1, 1, 3)
+    Q = P.DirichletPolynomial(r)
+    p = 21                                          # Block(20): hats + bubbles up to degree 20
+    f = lambda x: (1 - x * x) * np.exp(x)
+    c = P.transform(Q, f, p)
+    assert c.numel() == 39
+    E = O.basis_eval_matrix(O.DIRICHLET, r, p - 1, np.array([0.1, 0.2]))
+    assert abs(E[0] @ c.cpu().numpy() - f(0.1)) < 1e-12
+    x, vals = P.itransform(Q, c, p)
+    assert relerr(vals, f(x)) < 1e-12
+    z, T = P.legendre_grid_transform(p)
+    xg = P.cell_grid(r, z)
+    f2 = lambda x, y: (1 - x ** 2) * (1 - y ** 2) * np.exp(x * np.cos(y))
+    v2 = f2(xg[:, None], xg[None, :])
+    V = P.transform_2d(Q, _dev(torch, v2), p, T)
+    assert abs(E[0] @ V.cpu().numpy() @ E[1] - f2(0.1, 0.2)) < 1e-11
+    assert relerr(P.itransform_2d(Q, V, p, P.legendre_synthesis_matrix(z, p)).cpu().numpy(), v2) < 1e-11
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("basis", ["c1", "dirichlet"])
 def test_variable_coefficient_heat(basis):
     """examples/heat.jl:77-83 with a piecewise-constant a (0.5 on the middle third, 1 elsewhere, as in the example): the
