@@ -180,6 +180,19 @@ def cpu_baseline_sample(seconds=12.0):
            "sample": f"all {ncols} columns of the same workload solved {reps} times ({t:.1f} s of CPU work), C/OpenMP restatement of "
                      f"src/arrowhead.jl:425-486 (oracle/pop_oracle.c), column-parallel over {CO.num_threads()} threads"}
     try:
+        # context: the same arithmetic with the reference's own loop structure (a matrix right-hand side goes column by column,
+        # elements threaded inside a column, src/arrowhead.jl:439,480) -- what the favourable column-parallel port above is kinder than
+        ncs = 96
+        Xs = np.asfortranarray(rng.standard_normal((n, ncs)))
+        CO.solve_refloop(U, Xs.copy(order="F"))
+        t0 = time.perf_counter()
+        CO.solve_refloop(U, Xs)
+        dt = time.perf_counter() - t0
+        out["reference_loop_structure"] = {"value": n * ncs / dt, "unit": UNIT, "cores": CO.num_threads(),
+                                           "sample": f"{ncs} columns, one after the other, element loop of the upper solve threaded, lower solve serial"}
+    except Exception as ex:
+        out["reference_loop_structure"] = {"error": f"{type(ex).__name__}: {ex}"}
+    try:
         out["adi_poisson"] = cpu_adi_sample(O, CO)
     except Exception as ex:
         out["adi_poisson"] = {"error": f"{type(ex).__name__}: {ex}"}

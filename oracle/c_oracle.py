@@ -69,6 +69,16 @@ def solve(U: Packed, X: np.ndarray):
     return X
 
 
+def solve_refloop(U: Packed, X: np.ndarray):
+    """The same solve with the reference's loop structure (column by column, elements threaded in the upper solve, serial in
+    the lower one; src/arrowhead.jl:439,480): a timing context for the favourable column-parallel port, same arithmetic."""
+    assert X.dtype == np.float64 and (X.ndim == 1 or X.flags.f_contiguous)
+    Ad, Au, B, D = _upper(U)
+    nrhs = 1 if X.ndim == 1 else X.shape[1]
+    lib().oracle_solve_refloop(U.m, U.nh, U.q, U.nB, U.uD, _p(Ad), _p(Au), _p(B), _p(D), _p(X), C.c_int64(X.shape[0]), C.c_int64(nrhs))
+    return X
+
+
 def mul_sym(P: Packed, X: np.ndarray, alpha=1.0, beta=0.0, Y=None):
     assert X.dtype == np.float64 and (X.ndim == 1 or X.flags.f_contiguous)
     Ad, Au, B, D = _upper(P)

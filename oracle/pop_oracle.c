@@ -162,6 +162,55 @@ void oracle_solve(int m, int nh, int q, int nB, int uD, const double *Ad, const 
     }
 }
 
+/* The same solve with the LOOP STRUCTURE of the reference (timing context only, not a checker): a matrix right-hand side is
+ * solved column by column (ArrayLayouts has no MatLdivMat method for the arrowhead); inside a column the upper solve threads over the
+ * mesh elements (Threads.@threads, src/arrowhead.jl:439) with each element's chain on a stride-m view (b[nh+k : m : end]), and the
+ * lower solve runs its element loop serially (:480). */
+void oracle_solve_refloop(int m, int nh, int q, int nB, int uD, const double *Ad, const double *Au, const double *B, const double *D,
+                          double *X, int64_t ld, int64_t nrhs) {
+    int nb = nB < q ? nB : q;
+    for (int64_t c = 0; c < nrhs; ++c) {
+        double *H = X + c * ld, *Z = H + nh;
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < m; ++k) /* :439-441 */
+            for (int j = q - 1; j >= 0; --j) {
+                double v = Z[(size_t)j * m + k];
+                for (int d = 1; d <= uD; ++d)
+                    if (j + d < q) v -= DD(d, j, k) * Z[(size_t)(j + d) * m + k];
+                Z[(size_t)j * m + k] = v / DD(0, j, k);
+            }
+        for (int b = 0; b < nb; ++b) /* :449-451 */
+            for (int t = 0; t < 3; ++t)
+                for (int k = 0; k < m; ++k) {
+                    int i = k + t - 1;
+                    if (i >= 0 && i < nh) H[i] -= BB(b, t, k) * Z[(size_t)b * m + k];
+                }
+        for (int i = nh - 1; i >= 0; --i) { /* :453 */
+            double v = H[i];
+            if (i + 1 < nh) v -= Au[i] * H[i + 1];
+            H[i] = v / Ad[i];
+        }
+        for (int i = 0; i < nh; ++i) { /* :472 */
+            double v = H[i];
+            if (i > 0) v -= Au[i - 1] * H[i - 1];
+            H[i] = v / Ad[i];
+        }
+        for (int b = 0; b < nb; ++b) /* :475-477 */
+            for (int t = 0; t < 3; ++t)
+                for (int k = 0; k < m; ++k) {
+                    int i = k + t - 1;
+                    if (i >= 0 && i < nh) Z[(size_t)b * m + k] -= BB(b, t, k) * H[i];
+                }
+        for (int k = 0; k < m; ++k) /* :480-482, serial in the reference */
+            for (int j = 0; j < q; ++j) {
+                double v = Z[(size_t)j * m + k];
+                for (int d = 1; d <= uD; ++d)
+                    if (j - d >= 0) v -= DD(d, j - d, k) * Z[(size_t)(j - d) * m + k];
+                Z[(size_t)j * m + k] = v / DD(0, j, k);
+            }
+    }
+}
+
 /* Y <- alpha * Symmetric(P) * X + beta * Y with P given by upper data. */
 void oracle_mul_sym(int m, int nh, int q, int nB, int uD, const double *Ad, const double *Au, const double *B, const double *D,
                     double alpha, const double *X, int64_t ldx, double beta, double *Y, int64_t ldy, int64_t nrhs) {

@@ -36,3 +36,16 @@ def test_c_oracle_general_bands_and_not_pd():
     A.D[2][1, 1] = -3.0
     with pytest.raises(np.linalg.LinAlgError):
         CO.revchol(O.pack(A, lD=0))
+
+
+def test_reference_loop_structure_variant_is_the_same_arithmetic():
+    """oracle_solve_refloop (columns serial, elements threaded above / serial below, as src/arrowhead.jl:439,480 run) performs
+    the operations of oracle_solve in the same order per entry: bit-identical results."""
+    for basis, m, N in ((O.C1, 9, 7), (O.DIRICHLET, 12, 10)):
+        h = 2.0 / m
+        S = O.packed_axpby(-1.0, O.assemble_weaklaplacian(basis, m, N, h), 1.0, O.assemble_mass(basis, m, N, h))
+        U = CO.revchol(S)
+        X = np.asfortranarray(np.random.default_rng(3).standard_normal((S.n, 5)))
+        a = CO.solve(U, X.copy(order="F"))
+        b = CO.solve_refloop(U, X.copy(order="F"))
+        assert np.array_equal(a, b)
